@@ -1,0 +1,789 @@
+// hps_capi.cpp -- implementation of the C ABI in include/hpsim_b200.h on top of the sm_100a kernels.
+// Host side of the hot path: owns the device state, turns simulate() into a planned program
+// (hps_plan.cpp) and enqueues it on the context's stream without any host synchronisation.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <strings.h>
+#include <vector>
+
+#include "hps_comm.h"
+#include "hps_launch.h"
+#include "hps_plan.h"
+
+using namespace hps;
+
+namespace {
+std::string g_err;  // error of the last failed hps_ctx_create
+
+u32 next_pow2(u32 v) {  // util/src/utility.cpp:7-16
+  --v; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+  return ++v;
+}
+}  // namespace
+
+struct hps_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 0;
+  int compat = 1;
+  std::string err;
+  EngineState eng;
+  // scratch shared by every reducing kernel of this context
+  double* partials = nullptr;
+  u32* ticket = nullptr;
+  unsigned max_grid = 0;
+  // program upload buffers
+  Op* d_ops = nullptr;
+  Op* h_ops = nullptr;  // pinned
+  size_t ops_cap = 0;
+  Comm comm;
+  uint64_t launches = 0;
+};
+
+struct hps_beam {
+  hps_ctx* ctx;
+  BeamHost h;           // mass charge current freq design_w n_global
+  u32 n = 0, offset = 0, n_alloc = 0;
+  char* slab = nullptr;  // one allocation: 6 fp64 arrays + 2 u32 arrays
+  double* c[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  u32 *loss = nullptr, *lloss = nullptr;
+  DevStats* st = nullptr;
+  double* tmp = nullptr;  // n doubles of scratch (relative-phase download)
+  struct Slot { char* slab = nullptr; bool valid = false; double design_w, freq, current; } slot[2];
+  size_t slab_bytes = 0;
+};
+
+struct hps_lattice {
+  hps_ctx* ctx;
+  std::vector<hps_elem> e;
+};
+
+struct hps_scheff {
+  hps_ctx* ctx;
+  ScHost h;
+  u32 nr_init, nz_init;
+  double interval_init = 0.01, mesh_w = 0.0;
+  ScDev* dev = nullptr;
+  double* bins = nullptr;
+  double2* field = nullptr;
+};
+
+namespace {
+
+int fail(hps_ctx* c, int code, const std::string& m) {
+  if (c) c->err = m; else g_err = m;
+  return code;
+}
+#define CK(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, HPS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+BeamView view(const hps_beam* b) {
+  BeamView v;
+  v.x = b->c[0]; v.xp = b->c[1]; v.y = b->c[2]; v.yp = b->c[3]; v.phi = b->c[4]; v.w = b->c[5];
+  v.loss = b->loss; v.lloss = b->lloss;
+  v.n = b->n; v.offset = b->offset; v.n_global = b->h.n_global;
+  const u32 np2 = next_pow2(b->h.n_global);
+  v.np2_quarter = np2 >= 4 ? np2 / 4 : 1;
+  v.mass = b->h.mass; v.charge = b->h.charge;
+  return v;
+}
+
+LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
+  LaunchCfg l;
+  l.stream = c->stream;
+  const unsigned pairs = (b->n + 1) / 2;
+  l.grid_pairs = std::max(1u, std::min((pairs + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
+  l.grid_single = std::max(1u, std::min((b->n + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
+  l.grid_deposit = std::max(1u, std::min((b->n + 511) / 512, (unsigned)c->num_sms * 2));
+  l.partials = c->partials;
+  l.ticket = c->ticket;
+  return l;
+}
+
+void carve(hps_beam* b, char* slab, double* c[6], u32** loss, u32** lloss) {
+  const size_t da = align_up((size_t)b->n_alloc * sizeof(double), 256), ua = align_up((size_t)b->n_alloc * sizeof(u32), 256);
+  for (int i = 0; i < 6; ++i) c[i] = reinterpret_cast<double*>(slab + i * da);
+  *loss = reinterpret_cast<u32*>(slab + 6 * da);
+  *lloss = reinterpret_cast<u32*>(slab + 6 * da + ua);
+}
+
+// ---- Beam::Update* family on the device ------------------------------------------------------
+StatReq req(int kind, int a = 0, int bvar = -1, int good = 0, int out0 = 0) {
+  StatReq r;
+  std::memset(&r, 0, sizeof(r));
+  r.kind = kind; r.var_a = a; r.var_b = bvar; r.good_only = good; r.out[0] = out0;
+  return r;
+}
+void stat(hps_beam* b, const StatReq& r) {
+  launch_stat(cfg(b->ctx, b), view(b), b->st, r);
+  b->ctx->launches++;
+}
+void UpdateLoss(hps_beam* b) { stat(b, req(KS_COUNT_LOSS)); }
+void UpdateGoodParticleCount(hps_beam* b) { stat(b, req(KS_COUNT_GOOD, 0, -1, 1)); }
+void UpdateAvg(hps_beam* b, int var, int out, bool good) { stat(b, req(KS_AVG, var, -1, good, out)); }
+void UpdateSig(hps_beam* b, int var, int out, bool good) {
+  if (b->h.n_global > 2) stat(b, req(KS_SIG, var, -1, good, out));
+}
+void UpdateLongitudinalLoss(hps_beam* b) {  // beam.cpp:776-782
+  UpdateGoodParticleCount(b);
+  UpdateAvg(b, HPS_PHI, HPS_STAT_PHI_AVG_GOOD, true);
+  stat(b, req(KS_MARK_LLOSS));
+}
+int ref_phi_of(hps_beam* b, double* out) {
+  // phi[0] lives on the rank that owns global particle 0
+  double v = 0.0;
+  if (b->offset == 0) CK(b->ctx, cudaMemcpyAsync(&v, b->c[4], sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
+  CK(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+  if (b->ctx->comm.nranks > 1) {
+    int rc = comm_bcast_double(b->ctx->comm, &v, 0, b->ctx->stream);
+    if (rc) return fail(b->ctx, HPS_ERR_COMM, "broadcast of the reference phase failed");
+  }
+  *out = v;
+  return HPS_OK;
+}
+int ref_w_of(hps_beam* b, double* out) {
+  double v = 0.0;
+  if (b->offset == 0) CK(b->ctx, cudaMemcpyAsync(&v, b->c[5], sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
+  CK(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+  if (b->ctx->comm.nranks > 1) {
+    int rc = comm_bcast_double(b->ctx->comm, &v, 0, b->ctx->stream);
+    if (rc) return fail(b->ctx, HPS_ERR_COMM, "broadcast of the reference energy failed");
+  }
+  *out = v;
+  return HPS_OK;
+}
+int UpdateRelativePhi(hps_beam* b, bool use_good) {  // beam.cu:1122-1130
+  double phi0 = 0.0;
+  if (!use_good) { int rc = ref_phi_of(b, &phi0); if (rc) return rc; }
+  launch_set_phi_ref(cfg(b->ctx, b), view(b), b->st, use_good ? 1 : 0, phi0);
+  b->ctx->launches++;
+  return HPS_OK;
+}
+int UpdateEmittance(hps_beam* b) {  // beam.cpp:981-990
+  if (!(b->h.n_global > 2)) return HPS_OK;
+  double w0;
+  int rc = ref_w_of(b, &w0);
+  if (rc) return rc;
+  StatReq r = req(KS_EMIT_T, HPS_X, HPS_XP);
+  r.w_ref = w0;
+  r.out[0] = HPS_STAT_X_AVG; r.out[1] = HPS_STAT_X_SIG; r.out[2] = HPS_STAT_XP_AVG; r.out[3] = HPS_STAT_XP_SIG; r.out[4] = HPS_STAT_X_EMIT;
+  stat(b, r);
+  r = req(KS_EMIT_T, HPS_Y, HPS_YP);
+  r.w_ref = w0;
+  r.out[0] = HPS_STAT_Y_AVG; r.out[1] = HPS_STAT_Y_SIG; r.out[2] = HPS_STAT_YP_AVG; r.out[3] = HPS_STAT_YP_SIG; r.out[4] = HPS_STAT_Y_EMIT;
+  stat(b, r);
+  rc = UpdateRelativePhi(b, false);
+  if (rc) return rc;
+  stat(b, req(KS_EMIT_Z, 6, HPS_W));
+  return HPS_OK;
+}
+void InitPhiAvgGood(hps_beam* b) {  // beam.cpp:655-661
+  UpdateLoss(b);
+  UpdateAvg(b, HPS_PHI, HPS_STAT_PHI_AVG, false);
+  launch_copy_stat(cfg(b->ctx, b), b->st, HPS_STAT_PHI_AVG_GOOD, HPS_STAT_PHI_AVG);
+  b->ctx->launches++;
+}
+// beam.cpp:1003-1016 through the same three kernels the kick loop uses
+void UpdateStatForSpaceCharge(hps_beam* b) {
+  if (!(b->h.n_global > 2)) return;
+  hps_ctx* c = b->ctx;
+  LaunchCfg l = cfg(c, b);
+  BeamView v = view(b);
+  KickParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.n_global = b->h.n_global; kp.mass = b->h.mass;
+  launch_segment(l, v, c->d_ops, 0, FIN_KICK, 0, c->compat, b->st, nullptr, nullptr, kp);
+  launch_lloss_pass(l, v, b->st, nullptr);
+  launch_moments(l, v, b->st, nullptr, nullptr, kp, 0);
+  c->launches += 3;
+}
+
+int dirty_mask(const Op* ops, u32 n) {
+  int d = 0;
+  for (u32 i = 0; i < n; ++i) switch (ops[i].type) {
+      case OP_DRIFT: d |= 1 | 4 | 16 | 64; break;
+      case OP_QUAD_HALF: d |= 1 | 2 | 4 | 8 | 16 | 64; break;
+      case OP_GAP_FIRST: d |= 1 | 4 | 16; break;
+      case OP_GAP_SECOND: d |= 127; break;
+      case OP_DIPOLE_FIRST: case OP_DIPOLE_SECOND: d |= 1 | 2 | 4 | 8 | 16; break;
+      case OP_BUNCHER: d |= 2 | 8 | 32 | 64; break;
+      case OP_ROTATION: d |= 1 | 2 | 4 | 8; break;
+      case OP_STEERER: d |= 2 | 8; break;
+      case OP_CAPERTURE: case OP_RAPERTURE: d |= 64; break;
+      case OP_SC_KICK: d |= 2 | 8 | 32 | 64; break;
+      case OP_FREQ_CHANGE: d |= 16; break;
+      default: break;
+    }
+  return d;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int hps_abi_version(void) { return HPS_ABI_VERSION; }
+
+hps_ctx* hps_ctx_create(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fail(nullptr, HPS_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { fail(nullptr, HPS_ERR_ARG, "device ordinal out of range"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail(nullptr, HPS_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    fail(nullptr, HPS_ERR_CUDA, "hpsim_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    return nullptr;
+  }
+  hps_ctx* c = new hps_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+  int occ = ok ? segment_occupancy() : 0;
+  if (occ < 1) occ = 1;
+  c->max_grid = (unsigned)c->num_sms * (unsigned)occ;
+  ok = ok && cudaMalloc(&c->partials, (size_t)c->max_grid * HPS_NSLOT * sizeof(double)) == cudaSuccess &&
+       cudaMalloc(&c->ticket, 256) == cudaSuccess && cudaMemset(c->ticket, 0, 256) == cudaSuccess;
+  c->ops_cap = 4096;
+  ok = ok && cudaMalloc(&c->d_ops, c->ops_cap * sizeof(Op)) == cudaSuccess &&
+       cudaHostAlloc(&c->h_ops, c->ops_cap * sizeof(Op), cudaHostAllocDefault) == cudaSuccess;
+  if (!ok) {
+    fail(nullptr, HPS_ERR_CUDA, std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+void hps_ctx_destroy(hps_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  comm_destroy(c->comm);
+  cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_ops); cudaFreeHost(c->h_ops);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
+  delete c;
+}
+const char* hps_last_error(const hps_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+int hps_ctx_set_compat(hps_ctx* c, int v) { c->compat = v; return HPS_OK; }
+int hps_ctx_synchronize(hps_ctx* c) { CK(c, cudaStreamSynchronize(c->stream)); return HPS_OK; }
+uint64_t hps_ctx_launch_count(hps_ctx* c) { return c->launches; }
+
+int hps_comm_unique_id(void* out128) { return comm_unique_id(out128) ? HPS_ERR_COMM : HPS_OK; }
+int hps_ctx_comm_init(hps_ctx* c, int rank, int nranks, const void* id) {
+  if (nranks <= 1) return HPS_OK;
+  cudaSetDevice(c->device);
+  std::string err;
+  if (comm_init(c->comm, rank, nranks, id, &err)) return fail(c, HPS_ERR_COMM, err);
+  return HPS_OK;
+}
+
+void* hps_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void hps_host_free(void* p) { cudaFreeHost(p); }
+
+// ---- beam -----------------------------------------------------------------------------------------
+hps_beam* hps_beam_create(hps_ctx* c, uint64_t n_global, double mass, double charge, double current) {
+  if (!c) return nullptr;
+  if (n_global == 0 || n_global > 0xffffffffull) { fail(c, HPS_ERR_ARG, "bad particle count"); return nullptr; }
+  cudaSetDevice(c->device);
+  hps_beam* b = new hps_beam();
+  b->ctx = c;
+  b->h.mass = mass; b->h.charge = charge; b->h.current = current; b->h.freq = 0.0; b->h.design_w = 0.0;
+  b->h.n_global = (u32)n_global;
+  // contiguous index blocks; even block starts keep the 2-particle vector lanes aligned
+  const int nr = std::max(1, c->comm.nranks), rk = c->comm.rank;
+  const uint64_t per = ((n_global + nr - 1) / nr + 1) & ~1ull;
+  const uint64_t lo = std::min<uint64_t>(n_global, per * rk), hi = std::min<uint64_t>(n_global, per * (rk + 1));
+  b->offset = (u32)lo;
+  b->n = (u32)(hi - lo);
+  b->n_alloc = (u32)align_up(std::max<u32>(b->n, 4), 4);
+  const size_t da = align_up((size_t)b->n_alloc * sizeof(double), 256), ua = align_up((size_t)b->n_alloc * sizeof(u32), 256);
+  b->slab_bytes = 6 * da + 2 * ua;
+  bool ok = cudaMalloc(&b->slab, b->slab_bytes) == cudaSuccess && cudaMemsetAsync(b->slab, 0, b->slab_bytes, c->stream) == cudaSuccess &&
+            cudaMalloc(&b->st, sizeof(DevStats)) == cudaSuccess && cudaMemsetAsync(b->st, 0, sizeof(DevStats), c->stream) == cudaSuccess &&
+            cudaMalloc(&b->tmp, (size_t)b->n_alloc * sizeof(double)) == cudaSuccess;
+  if (!ok) {
+    fail(c, HPS_ERR_CUDA, std::string("beam allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    cudaFree(b->slab); cudaFree(b->st); cudaFree(b->tmp);
+    delete b;
+    return nullptr;
+  }
+  carve(b, b->slab, b->c, &b->loss, &b->lloss);
+  return b;
+}
+void hps_beam_destroy(hps_beam* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  cudaFree(b->slab); cudaFree(b->st); cudaFree(b->tmp);
+  for (auto& s : b->slot) cudaFree(s.slab);
+  delete b;
+}
+int hps_beam_local_range(const hps_beam* b, uint64_t* off, uint64_t* nl) {
+  if (off) *off = b->offset;
+  if (nl) *nl = b->n;
+  return HPS_OK;
+}
+
+int hps_beam_upload(hps_beam* b, const double* x, const double* xp, const double* y, const double* yp,
+                    const double* phi, const double* w, const uint32_t* loss, const uint32_t* lloss) {
+  hps_ctx* c = b->ctx;
+  cudaSetDevice(c->device);
+  const double* src[6] = {x, xp, y, yp, phi, w};
+  const size_t nb = (size_t)b->n * sizeof(double);
+  for (int i = 0; i < 6; ++i) {
+    if (!src[i]) return fail(c, HPS_ERR_ARG, "coordinate array is NULL");
+    CK(c, cudaMemcpyAsync(b->c[i], src[i], nb, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (loss) CK(c, cudaMemcpyAsync(b->loss, loss, (size_t)b->n * 4, cudaMemcpyHostToDevice, c->stream));
+  else CK(c, cudaMemsetAsync(b->loss, 0, (size_t)b->n * 4, c->stream));
+  if (lloss) CK(c, cudaMemcpyAsync(b->lloss, lloss, (size_t)b->n * 4, cudaMemcpyHostToDevice, c->stream));
+  else CK(c, cudaMemsetAsync(b->lloss, 0, (size_t)b->n * 4, c->stream));
+  if (b->offset == 0 && b->n > 0) {
+    // reference particle: on the axis, never lost (beam.cpp:344-359)
+    for (int i = 0; i < 4; ++i) CK(c, cudaMemsetAsync(b->c[i], 0, sizeof(double), c->stream));
+    CK(c, cudaMemsetAsync(b->loss, 0, 4, c->stream));
+    CK(c, cudaMemsetAsync(b->lloss, 0, 4, c->stream));
+  }
+  InitPhiAvgGood(b);
+  return HPS_OK;
+}
+int hps_beam_download(hps_beam* b, double* x, double* xp, double* y, double* yp, double* phi, double* w,
+                      uint32_t* loss, uint32_t* lloss) {
+  hps_ctx* c = b->ctx;
+  cudaSetDevice(c->device);
+  UpdateLoss(b);  // wrap_beam.cpp:456
+  double* dst[6] = {x, xp, y, yp, phi, w};
+  for (int i = 0; i < 6; ++i)
+    if (dst[i]) CK(c, cudaMemcpyAsync(dst[i], b->c[i], (size_t)b->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (loss) CK(c, cudaMemcpyAsync(loss, b->loss, (size_t)b->n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (lloss) CK(c, cudaMemcpyAsync(lloss, b->lloss, (size_t)b->n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return HPS_OK;
+}
+int hps_beam_download_phi_relative(hps_beam* b, int use_good, double* out) {
+  hps_ctx* c = b->ctx;
+  cudaSetDevice(c->device);
+  int rc = UpdateRelativePhi(b, use_good != 0);
+  if (rc) return rc;
+  launch_rel_phi_out(cfg(c, b), view(b), b->st, b->tmp);
+  c->launches++;
+  CK(c, cudaMemcpyAsync(out, b->tmp, (size_t)b->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return HPS_OK;
+}
+
+// Host generators.  Every rank draws the complete glibc rand() sequence and keeps its own block, so a
+// sharded beam is bit-identical to the single-GPU one.
+static int upload_generated(hps_beam* b, std::vector<double> v[6]) {
+  const u32 o = b->offset;
+  return hps_beam_upload(b, v[0].data() + o, v[1].data() + o, v[2].data() + o, v[3].data() + o, v[4].data() + o,
+                         v[5].data() + o, nullptr, nullptr);
+}
+static inline double urand() { return 2.0 * std::rand() / RAND_MAX - 1.0; }
+
+int hps_beam_set_dc(hps_beam* b, double ax, double bx, double ex, double ay, double by, double ey, double dphi,
+                    double sync_phi, double sync_w, uint32_t seed) {
+  // Beam::InitDCBeam (beam.cpp:481-537): uniform 4-D ball by nested rejection, phase ramp, constant W
+  const u32 n = b->h.n_global;
+  std::vector<double> v[6];
+  for (auto& a : v) a.resize(n);
+  std::srand(seed == 0 ? (unsigned)std::time(NULL) : seed);
+  const double gx = (1.0 + ax * ax) / bx, xmx = std::sqrt(ex / gx), xpmx = std::sqrt(ex * gx), dx = -ax / gx;
+  const double gy = (1.0 + ay * ay) / by, ymx = std::sqrt(ey / gy), ypmx = std::sqrt(ey * gy), dy = -ay / gy;
+  for (u32 i = 0; i < n; ++i) {
+    double r[4];
+    for (;;) {
+      for (int pair = 0; pair < 2; ++pair)
+        do { r[2 * pair] = urand(); r[2 * pair + 1] = urand(); } while (r[2 * pair] * r[2 * pair] + r[2 * pair + 1] * r[2 * pair + 1] > 1.0);
+      if (!(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3] > 1.0)) break;
+    }
+    const double ramp = 2.0 * (double)(i + 1.0) / (double)n - 1.0;
+    v[0][i] = 0.01 * (r[0] * xmx + dx * r[1] * xpmx);
+    v[1][i] = r[1] * xpmx;
+    v[2][i] = 0.01 * (r[2] * ymx + dy * r[3] * ypmx);
+    v[3][i] = r[3] * ypmx;
+    v[4][i] = ramp * dphi + sync_phi;
+    v[5][i] = sync_w;
+  }
+  return upload_generated(b, v);
+}
+int hps_beam_set_waterbag(hps_beam* b, double ax, double bx, double ex, double ay, double by, double ey, double az,
+                          double bz, double ez, double sync_phi, double sync_w, double freq, uint32_t seed) {
+  // Beam::InitWaterbagBeam (beam.cpp:391-463): uniform 6-D ball; also sets the beam frequency (:421)
+  const u32 n = b->h.n_global;
+  std::vector<double> v[6];
+  for (auto& a : v) a.resize(n);
+  std::srand(seed == 0 ? (unsigned)std::time(NULL) : seed);
+  const double gx = (1.0 + ax * ax) / bx, xmx = std::sqrt(ex / gx), xpmx = std::sqrt(ex * gx), dx = -ax / gx;
+  const double gy = (1.0 + ay * ay) / by, ymx = std::sqrt(ey / gy), ypmx = std::sqrt(ey * gy), dy = -ay / gy;
+  const double gz = (1.0 + az * az) / bz, zmx = std::sqrt(ez / gz), zpmx = ez / zmx, dz = -az / gz;
+  const double wave_len = 29979.2458 / freq;  // cm (H15)
+  b->h.freq = freq;
+  const double gm = sync_w / b->h.mass + 1.0;
+  const double beta = std::sqrt(1.0 - 1.0 / (gm * gm));
+  for (u32 i = 0; i < n; ++i) {
+    double r[6];
+    for (;;) {
+      for (int pair = 0; pair < 3; ++pair)
+        do { r[2 * pair] = urand(); r[2 * pair + 1] = urand(); } while (r[2 * pair] * r[2 * pair] + r[2 * pair + 1] * r[2 * pair + 1] > 1.0);
+      if (!(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3] + r[4] * r[4] + r[5] * r[5] > 1.0)) break;
+    }
+    v[0][i] = 0.01 * (r[0] * xmx + dx * r[1] * xpmx);
+    v[1][i] = r[1] * xpmx;
+    v[2][i] = 0.01 * (r[2] * ymx + dy * r[3] * ypmx);
+    v[3][i] = r[3] * ypmx;
+    v[4][i] = -(r[4] * zmx + dz * zpmx * r[5]) * 2.0 * M_PI / (beta * wave_len) + sync_phi;
+    v[5][i] = 2.0 * sync_w * zpmx * r[5] + sync_w;
+  }
+  return upload_generated(b, v);
+}
+
+int hps_beam_save(hps_beam* b, int k) {  // beam.cpp:547-593 (device-resident copy)
+  hps_ctx* c = b->ctx;
+  if (k < 0 || k > 1) return fail(c, HPS_ERR_ARG, "slot must be 0 or 1");
+  cudaSetDevice(c->device);
+  auto& s = b->slot[k];
+  if (!s.slab) CK(c, cudaMalloc(&s.slab, b->slab_bytes));
+  CK(c, cudaMemcpyAsync(s.slab, b->slab, b->slab_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  s.design_w = b->h.design_w; s.freq = b->h.freq; s.current = b->h.current;
+  s.valid = true;
+  return HPS_OK;
+}
+int hps_beam_restore(hps_beam* b, int k) {  // beam.cpp:603-647
+  hps_ctx* c = b->ctx;
+  if (k < 0 || k > 1) return fail(c, HPS_ERR_ARG, "slot must be 0 or 1");
+  auto& s = b->slot[k];
+  if (!s.valid) return fail(c, HPS_ERR_STATE, "Beam can't be restored because no previous beam has been saved");
+  cudaSetDevice(c->device);
+  CK(c, cudaMemcpyAsync(b->slab, s.slab, b->slab_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  b->h.design_w = s.design_w; b->h.freq = s.freq; b->h.current = s.current;
+  UpdateAvg(b, HPS_PHI, HPS_STAT_PHI_AVG_GOOD, true);  // H21: divides by the pre-restore num_good
+  return UpdateRelativePhi(b, true);
+}
+
+int hps_beam_set_ref_w(hps_beam* b, double w) {  // beam.cpp:1051-1055
+  hps_ctx* c = b->ctx;
+  cudaSetDevice(c->device);
+  if (b->offset == 0) CK(c, cudaMemcpyAsync(b->c[5], &w, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  b->h.design_w = w;
+  return HPS_OK;
+}
+int hps_beam_set_ref_phi(hps_beam* b, double phi) {
+  hps_ctx* c = b->ctx;
+  cudaSetDevice(c->device);
+  if (b->offset == 0) CK(c, cudaMemcpyAsync(b->c[4], &phi, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return HPS_OK;
+}
+int hps_beam_set_frequency(hps_beam* b, double f) { b->h.freq = f; return HPS_OK; }
+double hps_beam_get_ref_w(hps_beam* b) { double v = 0; cudaSetDevice(b->ctx->device); ref_w_of(b, &v); return v; }
+double hps_beam_get_ref_phi(hps_beam* b) { double v = 0; cudaSetDevice(b->ctx->device); ref_phi_of(b, &v); return v; }
+double hps_beam_get_frequency(const hps_beam* b) { return b->h.freq; }
+double hps_beam_get_mass(const hps_beam* b) { return b->h.mass; }
+double hps_beam_get_charge(const hps_beam* b) { return b->h.charge; }
+double hps_beam_get_current(const hps_beam* b) { return b->h.current; }
+uint64_t hps_beam_get_size(const hps_beam* b) { return b->h.n_global; }
+
+int hps_beam_shift(hps_beam* b, int coord, double v) {  // beam.cpp:1595-1642
+  if (coord < 0 || coord > 5) return fail(b->ctx, HPS_ERR_ARG, "bad coordinate");
+  cudaSetDevice(b->ctx->device);
+  if (b->n) launch_shift(cfg(b->ctx, b), b->c[coord], v, b->n, b->offset);
+  b->ctx->launches++;
+  if (coord == HPS_PHI) InitPhiAvgGood(b);
+  return HPS_OK;
+}
+int hps_beam_cut(hps_beam* b, int coord, double lo, double hi) {  // beam.cpp:1574-1588
+  if (!(coord == HPS_X || coord == HPS_Y || coord == HPS_W || coord == HPS_PHI))
+    return fail(b->ctx, HPS_ERR_ARG, "cut supports x, y, w, phi");
+  cudaSetDevice(b->ctx->device);
+  if (b->n) launch_cut(cfg(b->ctx, b), b->c[coord], b->loss, lo, hi, b->n, b->offset);
+  b->ctx->launches++;
+  return HPS_OK;
+}
+
+int hps_beam_update(hps_beam* b, int id) {
+  cudaSetDevice(b->ctx->device);
+  if (b->ctx->comm.nranks > 1 && id != HPS_UPD_REL_PHI && id != HPS_UPD_REL_PHI_GOOD)
+    return fail(b->ctx, HPS_ERR_COMM, "hps_beam_update on a sharded beam is not supported in this round");
+  switch (id) {
+    case HPS_UPD_LOSS: UpdateLoss(b); break;
+    case HPS_UPD_LLOSS: UpdateLongitudinalLoss(b); break;
+    case HPS_UPD_GOOD_COUNT: UpdateGoodParticleCount(b); break;
+    case HPS_UPD_AVG_X: UpdateAvg(b, HPS_X, HPS_STAT_X_AVG, false); break;
+    case HPS_UPD_AVG_X_GOOD: UpdateAvg(b, HPS_X, HPS_STAT_X_AVG_GOOD, true); break;
+    case HPS_UPD_AVG_XP: UpdateAvg(b, HPS_XP, HPS_STAT_XP_AVG, false); break;
+    case HPS_UPD_AVG_Y: UpdateAvg(b, HPS_Y, HPS_STAT_Y_AVG, false); break;
+    case HPS_UPD_AVG_Y_GOOD: UpdateAvg(b, HPS_Y, HPS_STAT_Y_AVG_GOOD, true); break;
+    case HPS_UPD_AVG_YP: UpdateAvg(b, HPS_YP, HPS_STAT_YP_AVG, false); break;
+    case HPS_UPD_AVG_PHI: UpdateAvg(b, HPS_PHI, HPS_STAT_PHI_AVG, false); break;
+    case HPS_UPD_AVG_PHI_GOOD: UpdateAvg(b, HPS_PHI, HPS_STAT_PHI_AVG_GOOD, true); break;
+    case HPS_UPD_AVG_PHI_R: UpdateAvg(b, 6, HPS_STAT_PHI_AVG_R, false); break;
+    case HPS_UPD_AVG_PHI_R_GOOD: UpdateAvg(b, 6, HPS_STAT_PHI_AVG_R, true); break;
+    case HPS_UPD_AVG_W: UpdateAvg(b, HPS_W, HPS_STAT_W_AVG, false); break;
+    case HPS_UPD_AVG_W_GOOD: UpdateAvg(b, HPS_W, HPS_STAT_W_AVG_GOOD, true); break;
+    case HPS_UPD_SIG_X: UpdateSig(b, HPS_X, HPS_STAT_X_SIG, false); break;
+    case HPS_UPD_SIG_X_GOOD: UpdateSig(b, HPS_X, HPS_STAT_X_SIG_GOOD, true); break;
+    case HPS_UPD_SIG_XP: UpdateSig(b, HPS_XP, HPS_STAT_XP_SIG, false); break;
+    case HPS_UPD_SIG_Y: UpdateSig(b, HPS_Y, HPS_STAT_Y_SIG, false); break;
+    case HPS_UPD_SIG_Y_GOOD: UpdateSig(b, HPS_Y, HPS_STAT_Y_SIG_GOOD, true); break;
+    case HPS_UPD_SIG_YP: UpdateSig(b, HPS_YP, HPS_STAT_YP_SIG, false); break;
+    case HPS_UPD_SIG_PHI: UpdateSig(b, HPS_PHI, HPS_STAT_PHI_SIG, false); break;
+    case HPS_UPD_SIG_PHI_R: UpdateSig(b, 6, HPS_STAT_PHI_SIG_R, false); break;
+    case HPS_UPD_SIG_PHI_R_GOOD: UpdateSig(b, 6, HPS_STAT_PHI_SIG_GOOD, true); break;
+    case HPS_UPD_SIG_W: UpdateSig(b, HPS_W, HPS_STAT_W_SIG, false); break;
+    case HPS_UPD_SIG_W_GOOD: UpdateSig(b, HPS_W, HPS_STAT_W_SIG_GOOD, true); break;
+    case HPS_UPD_EMITTANCE: return UpdateEmittance(b);
+    case HPS_UPD_STAT_FOR_SPCH: UpdateStatForSpaceCharge(b); break;
+    case HPS_UPD_AVG_XY: stat(b, req(KS_AVG_XY, HPS_X, HPS_Y)); break;
+    case HPS_UPD_MAX_R_PHI: stat(b, req(KS_MAX_R_PHI)); break;
+    case HPS_UPD_REL_PHI: return UpdateRelativePhi(b, false);
+    case HPS_UPD_REL_PHI_GOOD: return UpdateRelativePhi(b, true);
+    default: return fail(b->ctx, HPS_ERR_ARG, "unknown update id");
+  }
+  return HPS_OK;
+}
+int hps_beam_get(hps_beam* b, int id, double* out) {
+  hps_ctx* c = b->ctx;
+  if (id < 0 || id >= HPS_STAT_COUNT) return fail(c, HPS_ERR_ARG, "unknown stat id");
+  cudaSetDevice(c->device);
+  DevStats h;
+  CK(c, cudaMemcpyAsync(&h, b->st, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (id == HPS_STAT_NUM_LOSS) *out = h.num_loss;
+  else if (id == HPS_STAT_NUM_LLOSS) *out = h.num_lloss;
+  else if (id == HPS_STAT_NUM_GOOD) *out = h.num_good;
+  else *out = h.v[id];
+  return HPS_OK;
+}
+
+// ---- lattice ----------------------------------------------------------------------------------------
+hps_lattice* hps_lattice_create(hps_ctx* c, const hps_elem* e, uint32_t n) {
+  if (!c || (!e && n)) return nullptr;
+  hps_lattice* l = new hps_lattice();
+  l->ctx = c;
+  l->e.assign(e, e + n);
+  return l;
+}
+void hps_lattice_destroy(hps_lattice* l) { delete l; }
+uint32_t hps_lattice_size(const hps_lattice* l) { return (uint32_t)l->e.size(); }
+int64_t hps_lattice_index(const hps_lattice* l, const char* name) {  // beamline.cpp:70-77
+  for (size_t i = 0; i < l->e.size(); ++i)
+    if (strncasecmp(l->e[i].name, name, HPS_NAME_LEN) == 0) return (int64_t)i;
+  return -1;
+}
+int hps_lattice_get_elem(const hps_lattice* l, uint32_t i, hps_elem* out) {
+  if (i >= l->e.size()) return HPS_ERR_ARG;
+  *out = l->e[i];
+  return HPS_OK;
+}
+int hps_lattice_update_elem(hps_lattice* l, uint32_t i, const hps_elem* in) {
+  if (i >= l->e.size()) return HPS_ERR_ARG;
+  l->e[i] = *in;
+  return HPS_OK;
+}
+
+// ---- SCHEFF -----------------------------------------------------------------------------------------
+static int scheff_alloc(hps_scheff* s) {
+  hps_ctx* c = s->ctx;
+  cudaFree(s->bins); cudaFree(s->field);
+  s->bins = nullptr; s->field = nullptr;
+  const size_t nb = (size_t)s->h.nr * s->h.nz, nf = (size_t)(s->h.nr + 1) * (s->h.nz + 1);
+  CK(c, cudaMalloc(&s->bins, nb * sizeof(double)));
+  CK(c, cudaMalloc(&s->field, nf * sizeof(double2)));
+  CK(c, cudaMemsetAsync(s->bins, 0, nb * sizeof(double), c->stream));
+  CK(c, cudaMemsetAsync(s->field, 0, nf * sizeof(double2), c->stream));
+  return HPS_OK;
+}
+static int scheff_check_mesh(hps_ctx* c, u32 nr, u32 nz) {
+  KickParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.nr = nr; kp.nz = nz;
+  const int th = field_threads(kp);
+  if (nr == 0 || nz == 0 || th == 0 || field_smem(kp, th) > 220 * 1024 || deposit_smem(kp) > 200 * 1024)
+    return fail(c, HPS_ERR_ARG, "SCHEFF mesh too large for the shared-memory field solve (need nz <= 1024 and 24*nr*nz + 16 KB <= 220 KB)");
+  return HPS_OK;
+}
+hps_scheff* hps_scheff_create(hps_ctx* c, uint32_t nr, uint32_t nz, int adj_bunch) {
+  if (!c) return nullptr;
+  if (scheff_check_mesh(c, nr, nz)) return nullptr;
+  cudaSetDevice(c->device);
+  hps_scheff* s = new hps_scheff();
+  s->ctx = c;
+  s->h.on = true; s->h.nr = nr; s->h.nz = nz; s->h.adj_bunch = (u32)adj_bunch;
+  s->nr_init = nr; s->nz_init = nz;
+  bool ok = cudaMalloc(&s->dev, sizeof(ScDev)) == cudaSuccess &&
+            cudaMemsetAsync(s->dev, 0, sizeof(ScDev), c->stream) == cudaSuccess && scheff_alloc(s) == HPS_OK;
+  if (!ok) {
+    if (c->err.empty()) fail(c, HPS_ERR_CUDA, "SCHEFF allocation failed");
+    cudaFree(s->dev); cudaFree(s->bins); cudaFree(s->field);
+    delete s;
+    return nullptr;
+  }
+  return s;
+}
+void hps_scheff_destroy(hps_scheff* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->dev); cudaFree(s->bins); cudaFree(s->field);
+  delete s;
+}
+int hps_scheff_set(hps_scheff* s, int p, double v) {
+  switch (p) {
+    case HPS_SC_INTERVAL: s->h.interval = v; s->interval_init = v; break;
+    case HPS_SC_ADJ_BUNCH: s->h.adj_bunch = (u32)(int)v; break;
+    case HPS_SC_ADJ_BUNCH_CUTOFF_W: s->h.adj_bunch_w = v; break;
+    case HPS_SC_MESH_CUTOFF_W: s->mesh_w = v; break;
+    case HPS_SC_REMESH_THRESHOLD: s->h.remesh_val = v; break;
+    case HPS_SC_FRACTION: s->h.fraction = v; break;
+    default: return fail(s->ctx, HPS_ERR_ARG, "parameter is read-only or unknown");
+  }
+  return HPS_OK;
+}
+int hps_scheff_get(hps_scheff* s, int p, double* v) {
+  switch (p) {
+    case HPS_SC_INTERVAL: *v = s->h.interval; break;
+    case HPS_SC_ADJ_BUNCH: *v = s->h.adj_bunch; break;
+    case HPS_SC_ADJ_BUNCH_CUTOFF_W: *v = s->h.adj_bunch_w; break;
+    case HPS_SC_MESH_CUTOFF_W: *v = s->mesh_w; break;
+    case HPS_SC_REMESH_THRESHOLD: *v = s->h.remesh_val; break;
+    case HPS_SC_FRACTION: *v = s->h.fraction; break;
+    case HPS_SC_NR: *v = s->h.nr; break;
+    case HPS_SC_NZ: *v = s->h.nz; break;
+    default: return fail(s->ctx, HPS_ERR_ARG, "unknown parameter");
+  }
+  return HPS_OK;
+}
+int hps_scheff_set_mesh_size(hps_scheff* s, uint32_t nr, uint32_t nz) {  // space_charge.cpp:62-74
+  if (nr == s->h.nr && nz == s->h.nz) return HPS_OK;
+  int rc = scheff_check_mesh(s->ctx, nr, nz);
+  if (rc) return rc;
+  cudaSetDevice(s->ctx->device);
+  CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+  s->h.nr = nr; s->h.nz = nz;
+  return scheff_alloc(s);
+}
+int hps_scheff_download_tables(hps_scheff* s, double* bins, double* field, double* dr_dz) {
+  hps_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  if (bins) CK(c, cudaMemcpyAsync(bins, s->bins, (size_t)s->h.nr * s->h.nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (field) CK(c, cudaMemcpyAsync(field, s->field, (size_t)(s->h.nr + 1) * (s->h.nz + 1) * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+  ScDev h;
+  CK(c, cudaMemcpyAsync(&h, s->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (dr_dz) { dr_dz[0] = h.dr; dr_dz[1] = h.dz; }
+  return HPS_OK;
+}
+
+// ---- simulate ---------------------------------------------------------------------------------------
+int hps_engine_reset(hps_ctx* c, hps_beam* b) {  // simulation_engine.cu:101-111
+  c->eng.ccl_cell_num = 0;
+  c->eng.design_w = b->h.design_w;
+  c->eng.wavelen = 299.792458 / b->h.freq;
+  return HPS_OK;
+}
+
+int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint32_t first, uint32_t last,
+                 hps_run_stats* out) {
+  if (!c || !b || !lat) return fail(c, HPS_ERR_ARG, "null handle");
+  if (last >= lat->e.size()) return fail(c, HPS_ERR_ARG, "element index out of range");
+  if (sc && sc->mesh_w != 0.0)
+    return fail(c, HPS_ERR_ARG, "mesh_size_cutoff_w != 0 (energy-dependent mesh halving, space_charge.cpp:107-117) is not supported yet");
+  if (sc && !(b->h.n_global > 2)) return fail(c, HPS_ERR_ARG, "space charge needs more than 2 particles");
+  if (!(b->h.freq > 0.0)) return fail(c, HPS_ERR_STATE, "beam frequency is not set");
+  cudaSetDevice(c->device);
+
+  ScHost off;
+  ScHost& sh = sc ? sc->h : off;
+  sh.on = sc != nullptr;
+  Plan plan = build_plan(lat->e, first, last, c->eng, b->h, sh);
+  if (!plan.error.empty()) return fail(c, HPS_ERR_LATTICE, plan.error);
+
+  // upload the program
+  const size_t nops = plan.ops.size();
+  if (nops > c->ops_cap) {
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_ops); cudaFreeHost(c->h_ops);
+    c->d_ops = nullptr; c->h_ops = nullptr;
+    c->ops_cap = nops * 2;
+    CK(c, cudaMalloc(&c->d_ops, c->ops_cap * sizeof(Op)));
+    CK(c, cudaHostAlloc(&c->h_ops, c->ops_cap * sizeof(Op), cudaHostAllocDefault));
+  }
+  CK(c, cudaStreamSynchronize(c->stream));  // h_ops may still feed the previous call's copy
+  if (nops) {
+    std::memcpy(c->h_ops, plan.ops.data(), nops * sizeof(Op));
+    CK(c, cudaMemcpyAsync(c->d_ops, c->h_ops, nops * sizeof(Op), cudaMemcpyHostToDevice, c->stream));
+  }
+
+  ScDev before;
+  std::memset(&before, 0, sizeof(before));
+  if (sc) CK(c, cudaMemcpyAsync(&before, sc->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
+
+  const LaunchCfg l = cfg(c, b);
+  const BeamView v = view(b);
+  const uint64_t launches0 = c->launches;
+  uint64_t sweeps = 0, extra = 0;
+  const bool sharded = c->comm.nranks > 1;
+  CK(c, cudaEventRecord(c->ev0, c->stream));
+  for (const Segment& s : plan.segs) {
+    const int dirty = dirty_mask(plan.ops.data() + s.op_begin, s.op_count);
+    launch_segment(l, v, c->d_ops + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
+                   sc ? sc->field : nullptr, s.kp);
+    c->launches++;
+    sweeps++;
+    if (!s.kick_follows) { extra++; continue; }
+    if (sharded) return fail(c, HPS_ERR_COMM, "sharded space-charge kick is not wired up yet");
+    launch_lloss_pass(l, v, b->st, sc->dev);
+    launch_moments(l, v, b->st, sc->dev, sc->bins, s.kp, 1);
+    cudaError_t e = launch_deposit(l, v, b->st, sc->dev, sc->bins, s.kp);
+    if (e == cudaSuccess) e = launch_field(l, b->st, sc->dev, sc->bins, sc->field, s.kp);
+    if (e != cudaSuccess) return fail(c, HPS_ERR_CUDA, std::string("kick launch: ") + cudaGetErrorString(e));
+    c->launches += 4;
+  }
+  CK(c, cudaEventRecord(c->ev1, c->stream));
+  CK(c, cudaGetLastError());
+  if (out) {
+    std::memset(out, 0, sizeof(*out));
+    ScDev after;
+    std::memset(&after, 0, sizeof(after));
+    if (sc) CK(c, cudaMemcpyAsync(&after, sc->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    out->particles = b->h.n_global;
+    out->elements = last >= first ? (uint64_t)last - first + 1 : 0;
+    out->kicks = after.n_kicks - before.n_kicks;
+    out->remesh = after.n_remesh - before.n_remesh;
+    out->stat_redo = after.n_lloss_pass - before.n_lloss_pass;
+    out->sweeps = sweeps;
+    // the sweep that opens the range and every sweep not followed by a kick are "extra" (P)
+    out->extra_sweeps = extra;
+    out->launches = c->launches - launches0;
+    out->device_ms = ms;
+  }
+  return HPS_OK;
+}
+
+}  // extern "C"

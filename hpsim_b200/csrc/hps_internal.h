@@ -1,0 +1,105 @@
+// hps_internal.h -- structures shared by the host planner, the C-ABI layer and the kernels.
+//
+// Data layout in HBM
+//   particle state  : SoA, one 256-byte aligned fp64 array per coordinate (x, x', y, y', phi, W)
+//                     plus two uint32 flag arrays (loss, lloss); 56 B/particle.  The relative phase
+//                     array of the reference (beam/inc/beam.h:166) is NOT stored: it is recomputed
+//                     from phi and the reference phase wherever the reference reads it.
+//   DevStats        : the 33 one-element device scalars of the reference Beam
+//                     (beam/inc/beam.h:200-262) as one struct.
+//   ScDev           : SCHEFF device state: mesh cell sizes (reference `scheff_sz`,
+//                     space_charge_kernel.cu:12), num_on_mesh, the remesh memory that the reference
+//                     keeps on the host (space_charge.h:112-122) and the per-kick decision.
+//   program         : the flat list of Op records one simulate() call executes; one "segment"
+//                     (= one kernel launch = one sweep over the particles) is a contiguous slice.
+#ifndef HPS_INTERNAL_H
+#define HPS_INTERNAL_H
+
+#include <stdint.h>
+#include "../../include/hpsim_b200.h"
+
+typedef uint32_t u32;
+
+// ---- per-particle micro-ops executed by the fused segment kernel -------------------------------
+enum OpType {
+  OP_NONE = 0,
+  OP_DRIFT,        // p: 0 half_len, 1 aperture, 2 wavelen
+  OP_QUAD_HALF,    // p: 0 length, 1 aperture, 2 gradient, 3 wavelen
+  OP_GAP_FIRST,    // p: 0..24 RFGapParameter, 25 design_w_in, 26 phi_in, 27 qlen1, 28 qlen2; flag = ccl
+  OP_GAP_SECOND,   // p: same + 29 ccl_cell_num, 30 wavelen (d_wavelen in force); flag = ccl
+  OP_DIPOLE_FIRST, // p: 0..8 DipoleParameter, 9 wavelen
+  OP_DIPOLE_SECOND,
+  OP_BUNCHER,      // p: 0 w_ref, 1 freq, 2 voltage, 3 phase, 4 aperture, 5 freq_ratio, 6 wavelen
+  OP_ROTATION,     // p: 0 angle
+  OP_STEERER,      // p: 0 blh, 1 blv
+  OP_CAPERTURE,    // p: 0 aperture                     (uses stats x_avg / y_avg)
+  OP_RAPERTURE,    // p: 0 xl, 1 xr, 2 yt, 3 yb
+  OP_SC_KICK,      // p: 0 length, 1 current*fraction, 2 freq
+  OP_FREQ_CHANGE   // p: 0 ratio  (applies to lost particles too)
+};
+
+#define HPS_OP_NPARAM 31
+struct Op {
+  int type;
+  u32 elem;  // model index: the loss code written by aperture checks
+  int flag;
+  int pad;
+  double p[HPS_OP_NPARAM];
+};
+
+// what the segment kernel's last block does with its partial sums
+enum FinMode {
+  FIN_NONE = 0,
+  FIN_KICK = 1,      // first stage of Beam::UpdateStatForSpaceCharge (good count, <phi>_good, lloss trigger)
+  FIN_APERTURE = 2,  // Beam::UpdateLoss + UpdateAvgXY ahead of an "in" aperture
+};
+#define FIN_FREQ 4   // OR-ed in: segment contains OP_FREQ_CHANGE -> refresh phi_avg like Beam::ChangeFrequency
+
+struct DevStats {
+  double v[HPS_STAT_COUNT];  // doubles; the three counters below shadow v[NUM_*]
+  u32 num_loss, num_lloss, num_good;
+  u32 need_lloss_pass;       // set by FIN_KICK when some particle crosses <phi>_good + 3 pi
+  double phi_r_ref;          // reference phase of the (virtual) relative-phase array
+};
+
+struct ScDev {
+  double dr, dz;
+  u32 num_on_mesh;
+  u32 good_cnt_old;
+  double sigr_old, sigz_old, gm_old;
+  // decision of the current kick
+  int remesh;
+  u32 adj_bunch;   // effective number of adjacent bunches for this kick
+  double beta;
+  double ratio_r, ratio_z, ratio_q, ratio_g;
+  unsigned long long abs_phi_max_bits;
+  unsigned long long n_kicks, n_remesh, n_lloss_pass;
+};
+
+// static (host-known) parameters of one space-charge kick
+struct KickParams {
+  double freq;            // beam frequency in force [MHz]
+  double mass;
+  double current_frac;    // beam current * compensation fraction
+  double remesh_val;
+  double adj_bunch_w;
+  u32 adj_bunch_cfg;
+  u32 nr, nz;
+  u32 n_global;
+};
+
+struct BeamView {
+  double *x, *xp, *y, *yp, *phi, *w;
+  u32 *loss, *lloss;
+  u32 n;        // local particles
+  u32 offset;   // global index of local particle 0
+  u32 n_global;
+  u32 np2_quarter;  // NextPow2(n_global)/4: stride of the reference's kick launch (H2)
+  double mass, charge;
+};
+
+#define HPS_BLOCK 256
+#define HPS_NSLOT 16          // partial-sum slots per block
+#define HPS_MAX_SEG_OPS 24    // ops staged in shared memory per segment
+
+#endif

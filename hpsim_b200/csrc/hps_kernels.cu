@@ -1,0 +1,782 @@
+// hps_kernels.cu -- __global__ kernels + their launch wrappers (see hps_launch.h).
+#include "hps_kernels.cuh"
+#include "hps_launch.h"
+
+namespace hps {
+
+enum { SEG_NS = 8, MOM_NS = 12, LL_NS = 4, STAT_NS = 8 };
+
+// ================================================================================================
+// K1: fused segment sweep
+// ================================================================================================
+// slots: 0 n_good, 1 sum phi (good), 2 MAX phi over lloss==0, 3 n_loss, 4 sum x (loss==0),
+//        5 sum y (loss==0), 6 n_lloss, 7 sum phi (loss==0) right after OP_FREQ_CHANGE
+__device__ void finalize_segment(int fin, const double* t, DevStats* st, u32 n_global) {
+  if (fin & FIN_FREQ) {
+    // Beam::ChangeFrequency -> UpdateAvgPhi() (beam.cpp:1666; divides by N - num_loss, stale count)
+    st->v[HPS_STAT_PHI_AVG] = t[7] / (double)(u32)(n_global - st->num_loss);
+  }
+  switch (fin & 3) {
+    case FIN_KICK: {
+      // Beam::UpdateLongitudinalLoss steps 1-2 (beam.cpp:776-779); finalisers beam_kernel.cu:1420-1427
+      const u32 ng = (u32)t[0];
+      st->num_good = ng;
+      const double avg = ng > 0 ? t[1] / ng : -99999;
+      st->v[HPS_STAT_PHI_AVG_GOOD] = avg;
+      st->num_lloss = (u32)t[6];
+      // beam_kernel.cu:1556: a particle is marked when phi > <phi>_good + 2pi + pi; if nobody with
+      // lloss==0 crosses, steps 3-6 of the chain change nothing and the lloss pass is skipped.
+      st->need_lloss_pass = (t[2] > avg + K_TWOPI + K_PI) ? 1u : 0u;
+      break;
+    }
+    case FIN_APERTURE: {
+      // Beam::UpdateLoss + UpdateAvgXY (simulation_engine.cu:311-312; beam_kernel.cu:1385-1394)
+      const u32 nl = (u32)t[3];
+      st->num_loss = nl;
+      const double surv = (double)(u32)(n_global - nl);
+      st->v[HPS_STAT_X_AVG] = t[4] / surv;
+      st->v[HPS_STAT_Y_AVG] = t[5] / surv;
+      break;
+    }
+    default: break;
+  }
+}
+
+// one op applied to one register-resident particle
+__device__ __forceinline__ void apply_op(Pt& pt, const u32 ll, const u32 gidx, const Op& op, const KickCtx& kc,
+                                         const double* cxy, const double2* __restrict__ field, const BeamView& b,
+                                         int compat, double& phi_fc, bool& live_fc) {
+  const double* q = op.p;
+  const double mass = b.mass, charge = b.charge;
+  switch (op.type) {
+    case OP_DRIFT: if (pt.loss == 0) op_drift(pt, q, op.elem, mass); break;
+    case OP_QUAD_HALF: if (pt.loss == 0) op_quad_half(pt, q, op.elem, mass, charge); break;
+    case OP_GAP_FIRST: if (pt.loss == 0) op_gap_first(pt, q, op.flag != 0, mass); break;
+    case OP_GAP_SECOND: if (pt.loss == 0) op_gap_second(pt, q, op.flag != 0, mass, charge); break;
+    case OP_DIPOLE_FIRST: if (pt.loss == 0) op_dipole(pt, q, false, mass); break;
+    case OP_DIPOLE_SECOND: if (pt.loss == 0) op_dipole(pt, q, true, mass); break;
+    case OP_BUNCHER: if (pt.loss == 0) op_buncher(pt, q, op.elem, mass, charge); break;
+    case OP_ROTATION:  // simulation_kernel.cu:511-529
+      if (pt.loss == 0) {
+        const double cosa = cos(q[0]), sina = sin(q[0]);
+        const double x = pt.x, y = pt.y, xp = pt.xp, yp = pt.yp;
+        pt.x = x * cosa + y * sina; pt.y = y * cosa - x * sina;
+        pt.xp = xp * cosa + yp * sina; pt.yp = yp * cosa - xp * sina;
+      }
+      break;
+    case OP_STEERER:  // simulation_kernel.cu:120-140
+      if (pt.loss == 0) {
+        const double gm1 = pt.w / mass;
+        const double pm = sqrt(gm1 * (gm1 + 2.0)) * mass / K_CLIGHT;
+        if (q[0] > 1e-10) pt.xp += q[0] * charge / pm;
+        if (q[1] > 1e-10) pt.yp += q[1] * charge / pm;
+      }
+      break;
+    case OP_CAPERTURE:  // simulation_kernel.cu:543-556 (reference particle exempt, H1)
+      if (gidx > 0 && pt.loss == 0) {
+        const double x = pt.x - cxy[0], y = pt.y - cxy[1];
+        if (x * x + y * y > q[0] * q[0]) pt.loss = op.elem;
+      }
+      break;
+    case OP_RAPERTURE:  // simulation_kernel.cu:558-575
+      if (gidx > 0 && pt.loss == 0) {
+        const double xmin = cxy[0] - q[0], xmax = cxy[0] + q[1];
+        const double ymin = cxy[1] - q[3], ymax = cxy[1] + q[2];
+        if (pt.x < xmin || pt.x > xmax || pt.y < ymin || pt.y > ymax) pt.loss = op.elem;
+      }
+      break;
+    case OP_SC_KICK:
+      // H2: the reference launches the kick <<<grid, blck/4>>> with `while(indx > 0 && ...)`, so
+      // global thread 0 exits at once and particles k*NextPow2(N)/4 never see a kick.
+      if (!(gidx == 0 || (compat && (gidx % b.np2_quarter) == 0)))
+        op_sc_kick(pt, ll, q, kc, field, mass, b.n_global);
+      break;
+    case OP_FREQ_CHANGE:  // beam_kernel.cu:1531-1538: every particle, lost or not
+      pt.phi *= q[0];
+      phi_fc = pt.phi;
+      live_fc = pt.loss == 0;
+      break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ void seg_accumulate(double (&acc)[SEG_NS], const Pt& p, u32 ll, double phi_fc, bool live_fc) {
+  const bool alive = p.loss == 0, good = alive && ll == 0;
+  if (good) { acc[0] += 1.0; acc[1] += p.phi; }
+  if (ll == 0) acc[2] = fmax(acc[2], p.phi);
+  else acc[6] += 1.0;
+  if (alive) { acc[4] += p.x; acc[5] += p.y; }
+  else acc[3] += 1.0;
+  if (live_fc) acc[7] += phi_fc;
+}
+
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_segment(BeamView b, const Op* __restrict__ ops, int nops, int fin_mode, int dirty, int compat, DevStats* st,
+          const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials, u32* ticket) {
+  __shared__ Op s_ops[HPS_MAX_SEG_OPS];
+  __shared__ KickCtx s_k;
+  __shared__ double s_cxy[2];
+  __shared__ double s_total[SEG_NS];
+  __shared__ double s_scratch[(HPS_BLOCK / 32) * SEG_NS];
+
+  {  // stage the segment's op records (block-uniform) in shared memory
+    const int nw = nops * (int)(sizeof(Op) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(ops);
+    double* dst = reinterpret_cast<double*>(s_ops);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+  }
+  if (threadIdx.x == 0) {
+    s_cxy[0] = st->v[HPS_STAT_X_AVG];
+    s_cxy[1] = st->v[HPS_STAT_Y_AVG];
+    s_k.phimc = st->v[HPS_STAT_PHI_AVG_R];
+    s_k.xbar = st->v[HPS_STAT_X_AVG_GOOD];
+    s_k.ybar = st->v[HPS_STAT_Y_AVG_GOOD];
+    s_k.epsq = st->v[HPS_STAT_X_SIG_GOOD] / st->v[HPS_STAT_Y_SIG_GOOD];
+    s_k.phi_ref = st->v[HPS_STAT_PHI_AVG_GOOD];
+    if (sc) {
+      s_k.dr = sc->dr; s_k.dz = sc->dz; s_k.beta = sc->beta;
+      s_k.ratio_r = sc->ratio_r; s_k.ratio_z = sc->ratio_z; s_k.ratio_q = sc->ratio_q; s_k.ratio_g = sc->ratio_g;
+      s_k.adj_bunch = sc->adj_bunch; s_k.num_on_mesh = sc->num_on_mesh;
+    }
+    s_k.nr = kp.nr; s_k.nz = kp.nz;
+  }
+  __syncthreads();
+
+  double acc[SEG_NS];
+#pragma unroll
+  for (int s = 0; s < SEG_NS; ++s) acc[s] = 0.0;
+  acc[2] = -DBL_MAX;
+
+  const u32 npairs = (b.n + 1) >> 1;
+  for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
+    const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
+    const double2 XP = reinterpret_cast<const double2*>(b.xp)[i2];
+    const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
+    const double2 YP = reinterpret_cast<const double2*>(b.yp)[i2];
+    const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
+    const double2 W = reinterpret_cast<const double2*>(b.w)[i2];
+    const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
+    const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
+    Pt p0 = {X.x, XP.x, Y.x, YP.x, PH.x, W.x, L.x};
+    Pt p1 = {X.y, XP.y, Y.y, YP.y, PH.y, W.y, L.y};
+    const bool valid1 = 2 * i2 + 1 < b.n;
+    const u32 g0 = b.offset + 2 * i2, g1 = g0 + 1;
+    double fc0 = 0.0, fc1 = 0.0;
+    bool lf0 = false, lf1 = false;
+
+    for (int k = 0; k < nops; ++k) {
+      const Op& op = s_ops[k];
+      apply_op(p0, LL.x, g0, op, s_k, s_cxy, field, b, compat, fc0, lf0);
+      if (valid1) apply_op(p1, LL.y, g1, op, s_k, s_cxy, field, b, compat, fc1, lf1);
+    }
+
+    if (nops > 0) {
+      if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p0.x, p1.x);
+      if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p0.xp, p1.xp);
+      if (dirty & 4) reinterpret_cast<double2*>(b.y)[i2] = make_double2(p0.y, p1.y);
+      if (dirty & 8) reinterpret_cast<double2*>(b.yp)[i2] = make_double2(p0.yp, p1.yp);
+      if (dirty & 16) reinterpret_cast<double2*>(b.phi)[i2] = make_double2(p0.phi, p1.phi);
+      if (dirty & 32) reinterpret_cast<double2*>(b.w)[i2] = make_double2(p0.w, p1.w);
+      if ((dirty & 64) && (p0.loss != L.x || p1.loss != L.y))
+        reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p0.loss, p1.loss);
+    }
+    if (fin_mode != FIN_NONE) {
+      seg_accumulate(acc, p0, LL.x, fc0, lf0);
+      if (valid1) seg_accumulate(acc, p1, LL.y, fc1, lf1);
+    }
+  }
+  if (fin_mode == FIN_NONE) return;
+  if (grid_reduce<SEG_NS>(acc, 1u << 2, partials, ticket, s_total, s_scratch)) {
+    if (threadIdx.x == 0) finalize_segment(fin_mode, s_total, st, b.n_global);
+  }
+}
+
+// ================================================================================================
+// K2: longitudinal-loss pass (only does work when K1 found a particle beyond <phi>_good + 3 pi)
+// ================================================================================================
+// Beam::UpdateLongitudinalLoss steps 3-4 + the recount of UpdateStatForSpaceCharge
+// (beam.cpp:776-782, 1007-1009; beam_kernel.cu:1549-1559).  slots: 0 n_good 1 sum phi good 2 n_lloss
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_lloss_pass(BeamView b, DevStats* st, ScDev* sc, double* partials, u32* ticket) {
+  __shared__ double s_total[LL_NS];
+  __shared__ double s_scratch[(HPS_BLOCK / 32) * LL_NS];
+  if (st->need_lloss_pass == 0) return;
+  const double thr = st->v[HPS_STAT_PHI_AVG_GOOD] + K_TWOPI + K_PI;
+  double acc[LL_NS] = {0.0, 0.0, 0.0, 0.0};
+  const u32 npairs = (b.n + 1) >> 1;
+  for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
+    const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
+    const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
+    uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
+    const bool v1 = 2 * i2 + 1 < b.n;
+    bool changed = false;
+    if (PH.x > thr && LL.x != 1u) { LL.x = 1u; changed = true; }
+    if (v1 && PH.y > thr && LL.y != 1u) { LL.y = 1u; changed = true; }
+    if (changed) reinterpret_cast<uint2*>(b.lloss)[i2] = LL;
+    if (L.x == 0 && LL.x == 0) { acc[0] += 1.0; acc[1] += PH.x; }
+    if (LL.x != 0) acc[2] += 1.0;
+    if (v1) {
+      if (L.y == 0 && LL.y == 0) { acc[0] += 1.0; acc[1] += PH.y; }
+      if (LL.y != 0) acc[2] += 1.0;
+    }
+  }
+  if (grid_reduce<LL_NS>(acc, 0u, partials, ticket, s_total, s_scratch)) {
+    if (threadIdx.x == 0) {
+      const u32 ng = (u32)s_total[0];
+      st->num_good = ng;
+      st->v[HPS_STAT_PHI_AVG_GOOD] = ng > 0 ? s_total[1] / ng : -99999;
+      st->num_lloss = (u32)s_total[2];
+      st->need_lloss_pass = 0;
+      if (sc) sc->n_lloss_pass++;
+    }
+  }
+}
+
+// ================================================================================================
+// K3: moment pass + the host policy of Scheff::Start evaluated on the device
+// ================================================================================================
+// slots: 0 sum phi_r (loss==0)  1 sum phi_r (good)  2 sum phi_r^2 (good)  3 sum x  4 sum x^2  5 sum y
+//        6 sum y^2  7 sum w (all good)  8 MAX (x-x_avg)^2+(y-y_avg)^2 over loss==0
+__device__ void scheff_policy(DevStats* st, ScDev* sc, const KickParams& kp, double r2max) {
+  // space_charge.cpp:82-139.  This is HOST arithmetic in the reference (x86-64, no FMA), hence the
+  // explicit round-to-nearest intrinsics: nvcc must not contract these into FMAs.
+  const u32 good_cnt = st->num_good;
+  const double sigphi = st->v[HPS_STAT_PHI_SIG_GOOD];
+  const double sigx = st->v[HPS_STAT_X_SIG_GOOD], sigy = st->v[HPS_STAT_Y_SIG_GOOD];
+  const double ke = st->v[HPS_STAT_W_AVG_GOOD];
+  const double gamma = __dadd_rn(__ddiv_rn(ke, kp.mass), 1.0);
+  const double beta = __dsqrt_rn(__dsub_rn(1.0, __ddiv_rn(1.0, __dmul_rn(gamma, gamma))));
+  const double lmbd = __ddiv_rn(299.792458, kp.freq);
+  const double sigz = __dmul_rn(__dmul_rn(__ddiv_rn(__dmul_rn(sigphi, 0.5), 3.14159265), beta), lmbd);
+  const double sigr = __dsqrt_rn(__dadd_rn(__dmul_rn(sigx, sigx), __dmul_rn(sigy, sigy)));
+  const double cratior = __dmul_rn(sigr, sigz);
+  const double cratioz = __dmul_rn(__dmul_rn(__dmul_rn(sigz, sigz), gamma), gamma);
+  const double cratior_old = __dmul_rn(sc->sigr_old, sc->sigz_old);
+  const double cratioz_old = __dmul_rn(__dmul_rn(__dmul_rn(sc->sigz_old, sc->sigz_old), sc->gm_old), sc->gm_old);
+  u32 adj = (kp.adj_bunch_w == 0.0 || ke < kp.adj_bunch_w) ? kp.adj_bunch_cfg : 0u;
+  sc->adj_bunch = adj;
+  sc->beta = beta;
+  sc->n_kicks++;
+  const bool remesh = cratior_old == 0.0 || cratioz_old == 0.0 ||
+                      __ddiv_rn(fabs(__dsub_rn(cratior, cratior_old)), cratior_old) > kp.remesh_val ||
+                      __ddiv_rn(fabs(__dsub_rn(cratioz, cratioz_old)), cratioz_old) > kp.remesh_val;
+  sc->remesh = remesh ? 1 : 0;
+  if (remesh) {
+    sc->n_remesh++;
+    sc->sigr_old = sigr; sc->sigz_old = sigz; sc->gm_old = gamma; sc->good_cnt_old = good_cnt;
+    sc->ratio_r = 1.0; sc->ratio_z = 1.0; sc->ratio_q = 1.0; sc->ratio_g = 1.0;
+    sc->num_on_mesh = 0u;
+    sc->abs_phi_max_bits = 0ull;
+    // UpdateMeshKernelCall (space_charge.cu:122-138) + UpdateScheffMeshSizeKernel (space_charge_kernel.cu:19-32)
+    const double bl = beta * K_CLIGHT / kp.freq;
+    if (adj != 0) {
+      const double rmax = sqrt(r2max);  // Beam::UpdateMaxRPhi, with the stale x_avg / y_avg (H5)
+      st->v[HPS_STAT_R_MAX] = rmax;
+      sc->dr = 1.0 * rmax / kp.nr;
+      sc->dz = bl / kp.nz;
+    } else {
+      // H6: the reference picks the sigma by comparing device POINTERS (x_sig_good > y_sig_good is false
+      // for its allocation order) -> always y_sig_good.  H8: the 3*sigma > pi clamp is dead code.
+      sc->dr = 3.0 * sigy / kp.nr;
+      sc->dz = 3.0 * bl * sigphi / (kp.nz * K_PI);
+    }
+  } else {
+    sc->ratio_r = sigr / sc->sigr_old;
+    sc->ratio_z = sigz / sc->sigz_old;
+    sc->ratio_q = sc->good_cnt_old ? (double)(good_cnt / sc->good_cnt_old) : 0.0;  // H7: uint division
+    sc->ratio_g = gamma / sc->gm_old;
+  }
+}
+
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, double* partials,
+          u32* ticket) {
+  __shared__ double s_total[MOM_NS];
+  __shared__ double s_scratch[(HPS_BLOCK / 32) * MOM_NS];
+  const double ref = st->v[HPS_STAT_PHI_AVG_GOOD];
+  const double xa = st->v[HPS_STAT_X_AVG], ya = st->v[HPS_STAT_Y_AVG];
+  double acc[MOM_NS];
+#pragma unroll
+  for (int s = 0; s < MOM_NS; ++s) acc[s] = 0.0;
+  const u32 npairs = (b.n + 1) >> 1;
+  for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
+    const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
+    const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
+    const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
+    const double2 W = reinterpret_cast<const double2*>(b.w)[i2];
+    const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
+    const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
+    const double x[2] = {X.x, X.y}, y[2] = {Y.x, Y.y}, ph[2] = {PH.x, PH.y}, w[2] = {W.x, W.y};
+    const u32 l[2] = {L.x, L.y}, ll[2] = {LL.x, LL.y};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (j == 1 && !(2 * i2 + 1 < b.n)) continue;
+      if (l[j] != 0) continue;
+      const double pr = rel_phi(ph[j], ref);
+      acc[0] += pr;
+      const double tx = x[j] - xa, ty = y[j] - ya;
+      acc[8] = fmax(acc[8], tx * tx + ty * ty);
+      if (ll[j] == 0) {
+        acc[1] += pr; acc[2] += pr * pr;
+        acc[3] += x[j]; acc[4] += x[j] * x[j];
+        acc[5] += y[j]; acc[6] += y[j] * y[j];
+        acc[7] += w[j];
+      }
+    }
+  }
+  if (!grid_reduce<MOM_NS>(acc, 1u << 8, partials, ticket, s_total, s_scratch)) return;
+  if (threadIdx.x == 0) {
+    const double* t = s_total;
+    // beam.cpp:1010-1015; finalisers beam_kernel.cu:1396-1446.  H4: surv uses the stale num_loss.
+    const double surv = (double)(u32)(b.n_global - st->num_loss);
+    const u32 ng = st->num_good;
+    st->phi_r_ref = ref;
+    st->v[HPS_STAT_PHI_AVG_R] = t[0] / surv;
+    {
+      const double avg = t[1] / ng, avg2 = t[2] / ng;
+      st->v[HPS_STAT_PHI_SIG_GOOD] = sqrt(avg2 - avg * avg);
+    }
+    {
+      const double xavg = t[3] / surv, x2avg = t[4] / surv, yavg = t[5] / surv, y2avg = t[6] / surv;
+      st->v[HPS_STAT_X_AVG_GOOD] = xavg;
+      st->v[HPS_STAT_X_SIG_GOOD] = sqrt(x2avg - xavg * xavg);
+      st->v[HPS_STAT_Y_AVG_GOOD] = yavg;
+      st->v[HPS_STAT_Y_SIG_GOOD] = sqrt(y2avg - yavg * yavg);
+    }
+    st->v[HPS_STAT_W_AVG_GOOD] = ng > 0 ? t[7] / ng : -99999;
+    if (do_policy) scheff_policy(st, sc, kp, t[8]);
+  }
+  __syncthreads();
+  if (do_policy && sc->remesh) {  // ResetBinTbl (space_charge.cu:92-105)
+    const u32 nb = kp.nr * kp.nz;
+    for (u32 k = threadIdx.x; k < nb; k += blockDim.x) bins[k] = 0.0;
+  }
+}
+
+// ================================================================================================
+// K4: r-z ring charge deposit, privatised in shared memory
+// ================================================================================================
+// space_charge_kernel.cu:123-224.  The reference does 4 global atomicAdds per particle into a 16-32 KB
+// table; here each block accumulates a private fp64 copy in shared memory and flushes its non-zero
+// bins once.
+__global__ void __launch_bounds__(512)
+k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp) {
+  extern __shared__ double s_bins[];
+  if (!sc->remesh) return;
+  const int nx = (int)kp.nr, nz = (int)kp.nz;
+  const u32 nb = kp.nr * kp.nz;
+  for (u32 k = threadIdx.x; k < nb; k += blockDim.x) s_bins[k] = 0.0;
+  __syncthreads();
+  const double phimc = st->v[HPS_STAT_PHI_AVG_R], xbar = st->v[HPS_STAT_X_AVG_GOOD], ybar = st->v[HPS_STAT_Y_AVG_GOOD];
+  const double epsq = st->v[HPS_STAT_X_SIG_GOOD] / st->v[HPS_STAT_Y_SIG_GOOD];
+  const double ref = st->v[HPS_STAT_PHI_AVG_GOOD];
+  const double beta = sc->beta;
+  const double gm = rsqrt(1.0 - beta * beta);
+  const double dr = sc->dr;
+  const double dzg = sc->dz * gm;
+  const double wave_len = K_CLIGHT / kp.freq;
+  const double hl = nz * 0.5 * dzg;
+  const double c2 = beta * gm * wave_len / K_TWOPI;
+  const double drdr = dr * dr;
+  u32 cnt = 0;
+  double pmax = 0.0;
+  for (u32 np = blockIdx.x * blockDim.x + threadIdx.x; np < b.n; np += gridDim.x * blockDim.x) {
+    const u32 l = b.loss[np];
+    if (l != 0) continue;
+    const double pr = rel_phi(b.phi[np], ref);
+    {  // Beam::UpdateMaxRPhi's phase half (beam_kernel.cu:836-842); only reported, never fed back
+      double tp = pr - phimc;
+      tp = tp > 0.0 ? tp : -tp;
+      pmax = pmax < tp ? tp : pmax;
+    }
+    if (b.lloss[np] != 0) continue;
+    const double x = b.x[np], y = b.y[np];
+    const double rsq_sh = (x - xbar) * (x - xbar) / epsq + (y - ybar) * (y - ybar) * epsq;
+    const int i = (int)(sqrt(rsq_sh) / dr + 1);
+    if (!(i <= nx)) continue;
+    double ddz = pr - phimc;
+    while (ddz > K_PI || ddz < -K_PI) {
+      if (ddz > 0.0) ddz -= K_TWOPI; else ddz += K_TWOPI;
+    }
+    const double z = -c2 * ddz;
+    if (!(fabs(z) < hl)) continue;
+    const double zz = z + hl;
+    const int jm1 = (int)(zz / dzg + 1);
+    int i1 = i + 1;
+    if (rsq_sh < 0.5 * drdr * (double)(i * i + (i - 1) * (i - 1))) i1 = i - 1;
+    if (i1 < 1) i1 = 1;
+    if (i1 > nx) i1 = nx;
+    int j1 = jm1 + 1;
+    if (zz < (jm1 - 1 + 0.5) * dzg) j1 = jm1 - 1;
+    if (j1 < 1) j1 = 1;
+    if (j1 > nz) j1 = nz;
+    double a;
+    if (i1 == i) a = 1.0;
+    else {
+      const double sqrtmp = sqrt(4.0 * rsq_sh / drdr - 1.0);
+      const double rminsq = 0.25 * drdr * (sqrtmp - 1.0) * (sqrtmp - 1.0);
+      const double rmaxsq = rminsq + sqrtmp * drdr;
+      if (i1 < i) a = (rmaxsq - (i - 1) * (i - 1) * drdr) / (rmaxsq - rminsq);
+      else a = ((i1 - 1) * (i1 - 1) * drdr - rminsq) / (rmaxsq - rminsq);
+    }
+    double cc = 1.0;
+    if (j1 != jm1) cc = (zz - (j1 - 1 + 0.5) * dzg) / ((jm1 - j1) * dzg);
+    const double bb = 1.0 - a, d = 1.0 - cc;
+    // jm1 can reach nz+1 when zz/dzg rounds up to nz exactly; the reference then writes one row past
+    // its table.  Such a particle is dropped here instead (it carries weight cc = 1 into nowhere).
+    int k = (jm1 - 1) * nx + i;
+    if (jm1 >= 1 && jm1 <= nz) {
+      atomicAdd(&s_bins[k - 1], a * cc);
+      if (i1 != i) atomicAdd(&s_bins[k + (i1 - i) - 1], bb * cc);
+    }
+    if (j1 != jm1) {  // d == 0 otherwise: the reference adds exact zeros
+      k = (j1 - 1) * nx + i;
+      atomicAdd(&s_bins[k - 1], a * d);
+      if (i1 != i) atomicAdd(&s_bins[k + (i1 - i) - 1], bb * d);
+    }
+    cnt++;
+  }
+  __syncthreads();
+  for (u32 k = threadIdx.x; k < nb; k += blockDim.x) {
+    const double v = s_bins[k];
+    if (v != 0.0) atomicAdd(&bins[k], v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    pmax = fmax(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt) atomicAdd(&sc->num_on_mesh, cnt);
+    atomicMax(&sc->abs_phi_max_bits, (unsigned long long)__double_as_longlong(pmax));
+  }
+}
+
+// ================================================================================================
+// K5: ring-to-ring Green's function + field at the mesh nodes, one block per receiving radius
+// ================================================================================================
+// space_charge_kernel.cu:39-100 (Green table) and :472-568 (field, the -DDOUBLE_PRECISION variant).
+// The reference materialises the 2.1 MB Green table in HBM and re-reads it from every block; here
+// block rp computes its own [nr][nz] slice straight into shared memory and consumes it in place.
+__device__ __forceinline__ void ellip_ke(double g, double& ee, double& ek) {
+  const double h = log(g);
+  ee = 1.0 + g * (0.4630106 - 0.2452740 * h + g * (0.1077857 - 0.04125321 * h));
+  ek = 1.38629436 - 0.5 * h + g * (0.1119697 - 0.1213486 * h + g * (0.07253230 - 0.02887472 * h));
+}
+
+__global__ void __launch_bounds__(1024)
+k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, KickParams kp) {
+  extern __shared__ double s_mem[];
+  if (!sc->remesh) return;
+  const u32 nr = kp.nr, nz = kp.nz, nb = nr * nz;
+  double* s_bins = s_mem;                                      // [nb]
+  double2* s_green = reinterpret_cast<double2*>(s_mem + nb);   // [nr][nz]
+  double2* s_part = s_green + nb;                              // [blockDim.x]
+  const u32 irp = blockIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
+    st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
+
+  for (u32 k = threadIdx.x; k < nb; k += blockDim.x) s_bins[k] = bins[k];
+  {
+    const double beta = sc->beta;
+    const double gm = rsqrt(1.0 - beta * beta);
+    const double dr = sc->dr;
+    const double dzg = sc->dz * gm;
+    const double wave_len = K_CLIGHT / kp.freq;
+    const double pl = beta * gm * wave_len;
+    const double c1 = 5721.67 * (kp.current_frac / kp.mass) / (kp.freq * 1e6 * (double)kp.n_global);
+    const double rp = irp * dr;
+    const int adj = (int)sc->adj_bunch;
+    for (u32 e = threadIdx.x; e < nb; e += blockDim.x) {
+      const u32 jz = e % nz, k = e / nz;
+      const double rs = sqrt(0.5 * (k * k + (k + 1) * (k + 1))) * dr;
+      const double zs = 0.5 * dzg, zp = (jz + 1) * dzg;
+      const double d = zp - zs;
+      double d2 = d * d;
+      const double c = (rp - rs) * (rp - rs), bq = (rp + rs) * (rp + rs);
+      const double rsrp = rs * rp;
+      double a = 4.0 * rsrp / (bq + d2);
+      double ee, ek;
+      ellip_ke(1.0 - a, ee, ek);
+      double er1 = 0.0;
+      a = sqrt(bq + d2);
+      const double rs2mrp2 = rs * rs - rp * rp;
+      if (rp != 0.0) er1 = (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
+      double ez1 = d * ee / (a * (c + d2));
+      for (int i = 1; i <= adj; ++i) {
+        double xi = i;
+        for (int j = 0; j < 2; ++j) {
+          const double d1 = d - xi * pl;
+          d2 = d1 * d1;
+          a = 4.0 * rsrp / (bq + d2);
+          ellip_ke(1.0 - a, ee, ek);
+          a = sqrt(bq + d2);
+          if (rp != 0.0) er1 += (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
+          ez1 += d1 * ee / (a * (c + d2));
+          xi = -xi;
+        }
+      }
+      s_green[e] = make_double2(c1 * er1, c1 * ez1);
+    }
+  }
+  __syncthreads();
+
+  // nodes (zp = 0..nz-1, rp): thread -> (zp, chunk of source bins); chunks are summed in a fixed order
+  const u32 nchunk = blockDim.x / nz;
+  const u32 per = (nb + nchunk - 1) / nchunk;
+  {
+    const u32 zp = threadIdx.x % nz, ch = threadIdx.x / nz;
+    double tx = 0.0, tz = 0.0;
+    if (ch < nchunk) {
+      const u32 b0 = ch * per, b1 = min(nb, b0 + per);
+      for (u32 bi = b0; bi < b1; ++bi) {
+        const double v = s_bins[bi];
+        if (v == 0.0) continue;
+        const u32 rs = bi % nr, zs = bi / nr;
+        u32 dz;
+        double sign = 1.0;
+        if (zs >= zp) { dz = zs - zp; sign = -1.0; } else dz = zp - zs - 1;
+        const double2 g = s_green[rs * nz + dz];
+        tx += v * g.x;
+        tz += sign * v * g.y;
+      }
+    }
+    s_part[threadIdx.x] = make_double2(tx, tz);
+  }
+  __syncthreads();
+  if (threadIdx.x < nz) {
+    double tx = 0.0, tz = 0.0;
+    for (u32 ch = 0; ch < nchunk; ++ch) {
+      const double2 v = s_part[ch * nz + threadIdx.x];
+      tx += v.x; tz += v.y;
+    }
+    field[threadIdx.x * (nr + 1) + irp] = make_double2(tx, tz);
+  }
+  __syncthreads();
+  // node (zp = nz, rp): every source bin lies upstream (dz = nz - zs - 1)
+  {
+    double tx = 0.0, tz = 0.0;
+    for (u32 bi = threadIdx.x; bi < nb; bi += blockDim.x) {
+      const double v = s_bins[bi];
+      if (v == 0.0) continue;
+      const u32 rs = bi % nr, zs = bi / nr;
+      const double2 g = s_green[rs * nz + (nz - zs - 1)];
+      tx += v * g.x;
+      tz += v * g.y;
+    }
+    s_part[threadIdx.x] = make_double2(tx, tz);
+  }
+  __syncthreads();
+  for (u32 s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (threadIdx.x < s && threadIdx.x + s < blockDim.x) {
+      s_part[threadIdx.x].x += s_part[threadIdx.x + s].x;
+      s_part[threadIdx.x].y += s_part[threadIdx.x + s].y;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) field[nz * (nr + 1) + irp] = s_part[0];
+}
+
+// ================================================================================================
+// generic statistics kernel behind hps_beam_update() (the reference's Beam::Update* family)
+// ================================================================================================
+__device__ __forceinline__ double pick(const BeamView& b, int var, u32 i, double phi_ref) {
+  switch (var) {
+    case 0: return b.x[i];
+    case 1: return b.xp[i];
+    case 2: return b.y[i];
+    case 3: return b.yp[i];
+    case 4: return b.phi[i];
+    case 5: return b.w[i];
+    default: return rel_phi(b.phi[i], phi_ref);
+  }
+}
+
+// slots: 0 count(filter passes) 1 sum a 2 sum a^2 3 sum b 4 sum b^2 5 sum ab 6 MAX 7 MAX
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_stat(BeamView b, DevStats* st, StatReq rq, double* partials, u32* ticket) {
+  __shared__ double s_total[STAT_NS];
+  __shared__ double s_scratch[(HPS_BLOCK / 32) * STAT_NS];
+  const double phi_ref = st->phi_r_ref;
+  const double xa = st->v[HPS_STAT_X_AVG], ya = st->v[HPS_STAT_Y_AVG], pa = st->v[HPS_STAT_PHI_AVG_R];
+  const double thr = st->v[HPS_STAT_PHI_AVG_GOOD] + K_TWOPI + K_PI;
+  double acc[STAT_NS];
+#pragma unroll
+  for (int s = 0; s < STAT_NS; ++s) acc[s] = 0.0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x) {
+    const u32 l = b.loss[i];
+    u32 ll = b.lloss[i];
+    if (rq.kind == KS_MARK_LLOSS) {  // beam_kernel.cu:1549-1559
+      if (b.phi[i] > thr && ll != 1u) { ll = 1u; b.lloss[i] = 1u; }
+      if (ll != 0) acc[0] += 1.0;
+      continue;
+    }
+    if (rq.kind == KS_COUNT_LOSS) { if (l != 0) acc[0] += 1.0; continue; }
+    if (rq.kind == KS_COUNT_LLOSS) { if (ll != 0) acc[0] += 1.0; continue; }
+    const bool pass = rq.good_only ? (l + ll == 0) : (l == 0);
+    if (!pass) continue;
+    acc[0] += 1.0;
+    if (rq.kind == KS_COUNT_GOOD) continue;
+    if (rq.kind == KS_MAX_R_PHI) {  // beam_kernel.cu:792-932
+      const double tx = b.x[i] - xa, ty = b.y[i] - ya;
+      double tp = rel_phi(b.phi[i], phi_ref) - pa;
+      tp = tp > 0.0 ? tp : -tp;
+      acc[6] = fmax(acc[6], tx * tx + ty * ty);
+      acc[7] = fmax(acc[7], tp);
+      continue;
+    }
+    const double a = pick(b, rq.var_a, i, phi_ref);
+    acc[1] += a; acc[2] += a * a;
+    if (rq.var_b >= 0) {
+      const double c = pick(b, rq.var_b, i, phi_ref);
+      acc[3] += c; acc[4] += c * c; acc[5] += a * c;
+    }
+  }
+  if (!grid_reduce<STAT_NS>(acc, (1u << 6) | (1u << 7), partials, ticket, s_total, s_scratch)) return;
+  if (threadIdx.x != 0) return;
+  const double* t = s_total;
+  const double surv = (double)(u32)(b.n_global - st->num_loss);
+  switch (rq.kind) {
+    case KS_COUNT_LOSS: st->num_loss = (u32)t[0]; break;
+    case KS_COUNT_LLOSS: case KS_MARK_LLOSS: st->num_lloss = (u32)t[0]; break;
+    case KS_COUNT_GOOD: st->num_good = (u32)t[0]; break;
+    case KS_AVG:  // beam_kernel.cu:1412-1427
+      if (!rq.good_only) st->v[rq.out[0]] = t[1] / surv;
+      else st->v[rq.out[0]] = st->num_good > 0 ? t[1] / st->num_good : -99999;
+      break;
+    case KS_SIG: {  // beam_kernel.cu:1429-1446
+      const double d = rq.good_only ? (double)st->num_good : surv;
+      const double avg = t[1] / d, avg2 = t[2] / d;
+      st->v[rq.out[0]] = sqrt(avg2 - avg * avg);
+      break;
+    }
+    case KS_AVG_XY:  // beam_kernel.cu:1385-1394
+      st->v[HPS_STAT_X_AVG] = t[1] / surv;
+      st->v[HPS_STAT_Y_AVG] = t[3] / surv;
+      break;
+    case KS_EMIT_T: {  // beam_kernel.cu:1333-1354; out: avg sig pavg psig emit
+      const double x = t[1] / surv, x2 = t[2] / surv, xp = t[3] / surv, xp2 = t[4] / surv, xxp = t[5] / surv;
+      const double gamma1 = rq.w_ref / b.mass;
+      const double betagamma = sqrt(gamma1 * (gamma1 + 2.0));
+      st->v[rq.out[0]] = x;
+      st->v[rq.out[1]] = sqrt(x2 - x * x);
+      st->v[rq.out[2]] = xp;
+      st->v[rq.out[3]] = sqrt(xp2 - xp * xp);
+      st->v[rq.out[4]] = sqrt((x2 - x * x) * (xp2 - xp * xp) - (xxp - x * xp) * (xxp - x * xp)) * betagamma;
+      break;
+    }
+    case KS_EMIT_Z: {  // beam_kernel.cu:1356-1375
+      const double phi = t[1] / surv, phi2 = t[2] / surv, w = t[3] / surv, w2 = t[4] / surv, phi_w = t[5] / surv;
+      const double phi_var = phi2 - phi * phi, w_var = w2 - w * w, cov = phi_w - phi * w;
+      st->v[HPS_STAT_PHI_AVG_R] = phi;
+      st->v[HPS_STAT_W_AVG] = w;
+      st->v[HPS_STAT_PHI_SIG_R] = sqrt(phi_var);
+      st->v[HPS_STAT_W_SIG] = sqrt(w_var);
+      st->v[HPS_STAT_Z_EMIT] = sqrt(phi_var * w_var - cov * cov);
+      break;
+    }
+    case KS_MAX_R_PHI:  // beam_kernel.cu:1377-1383
+      st->v[HPS_STAT_R_MAX] = sqrt(t[6]);
+      st->v[HPS_STAT_ABS_PHI_MAX] = t[7];
+      break;
+    default: break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+// Beam::UpdateRelativePhi (beam.cu:1122-1130): only the reference phase is recorded
+__global__ void k_set_phi_ref(BeamView b, DevStats* st, int use_good, double phi0) {
+  st->phi_r_ref = use_good ? st->v[HPS_STAT_PHI_AVG_GOOD] : phi0;
+}
+__global__ void k_copy_stat(DevStats* st, int dst, int src) { st->v[dst] = st->v[src]; }
+// beam_kernel.cu:1489-1496 (global particle 0 is never shifted)
+__global__ void k_shift(double* a, double v, u32 n, u32 offset) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && offset + i > 0) a[i] += v;
+}
+// beam_kernel.cu:1464-1480
+__global__ void k_cut(const double* a, u32* loss, double lo, double hi, u32 n, u32 offset) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && offset + i > 0 && loss[i] == 0) {
+    const double x = a[i];
+    if (x < hi && x > lo) loss[i] = 99999u;
+  }
+}
+__global__ void k_rel_phi_out(BeamView b, const DevStats* st, double* out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < b.n) out[i] = rel_phi(b.phi[i], st->phi_r_ref);
+}
+
+// ================================================================================================
+// launch wrappers
+// ================================================================================================
+static int g_field_smem_set = 0, g_deposit_smem_set = 0;
+
+void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* ops, int nops, int fin_mode, int dirty, int compat,
+                    DevStats* st, const ScDev* sc, const double2* field, const KickParams& kp) {
+  k_segment<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, ops, nops, fin_mode, dirty, compat, st, sc, field, kp,
+                                                      c.partials, c.ticket);
+}
+void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
+  k_lloss_pass<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, c.partials, c.ticket);
+}
+void launch_moments(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins, const KickParams& kp,
+                    int do_policy) {
+  k_moments<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, bins, kp, do_policy, c.partials, c.ticket);
+}
+size_t deposit_smem(const KickParams& kp) { return (size_t)kp.nr * kp.nz * sizeof(double); }
+size_t field_smem(const KickParams& kp, int threads) {
+  return (size_t)kp.nr * kp.nz * (sizeof(double) + sizeof(double2)) + (size_t)threads * sizeof(double2);
+}
+int field_threads(const KickParams& kp) {
+  if (kp.nz == 0 || kp.nz > 1024) return 0;
+  return (int)(kp.nz * (1024 / kp.nz));
+}
+cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
+                           const KickParams& kp) {
+  const size_t smem = deposit_smem(kp);
+  if (smem > 48 * 1024 && !g_deposit_smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    g_deposit_smem_set = 1;
+  }
+  k_deposit<<<c.grid_deposit, 512, smem, c.stream>>>(b, st, sc, bins, kp);
+  return cudaSuccess;
+}
+cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const double* bins, double2* field,
+                         const KickParams& kp) {
+  const int threads = field_threads(kp);
+  const size_t smem = field_smem(kp, threads);
+  if (!g_field_smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    g_field_smem_set = 1;
+  }
+  k_field<<<kp.nr + 1, threads, smem, c.stream>>>(st, sc, bins, field, kp);
+  return cudaSuccess;
+}
+void launch_stat(const LaunchCfg& c, const BeamView& b, DevStats* st, const StatReq& rq) {
+  k_stat<<<c.grid_single, HPS_BLOCK, 0, c.stream>>>(b, st, rq, c.partials, c.ticket);
+}
+void launch_set_phi_ref(const LaunchCfg& c, const BeamView& b, DevStats* st, int use_good, double phi0) {
+  k_set_phi_ref<<<1, 1, 0, c.stream>>>(b, st, use_good, phi0);
+}
+void launch_copy_stat(const LaunchCfg& c, DevStats* st, int dst, int src) { k_copy_stat<<<1, 1, 0, c.stream>>>(st, dst, src); }
+void launch_shift(const LaunchCfg& c, double* a, double v, u32 n, u32 offset) {
+  k_shift<<<(n + 255) / 256, 256, 0, c.stream>>>(a, v, n, offset);
+}
+void launch_cut(const LaunchCfg& c, const double* a, u32* loss, double lo, double hi, u32 n, u32 offset) {
+  k_cut<<<(n + 255) / 256, 256, 0, c.stream>>>(a, loss, lo, hi, n, offset);
+}
+void launch_rel_phi_out(const LaunchCfg& c, const BeamView& b, const DevStats* st, double* out) {
+  k_rel_phi_out<<<(b.n + 255) / 256, 256, 0, c.stream>>>(b, st, out);
+}
+int segment_occupancy() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment, HPS_BLOCK, 0);
+  return nb;
+}
+
+}  // namespace hps

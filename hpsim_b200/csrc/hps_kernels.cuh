@@ -1,0 +1,514 @@
+// hps_kernels.cuh -- sm_100a kernels of the HPSim tracking + SCHEFF hot path.
+//
+// One "segment" kernel applies every element map between two grid-wide dependency points
+// (space-charge kick, centroid-centred aperture) to particles held in registers: 2 adjacent
+// particles per thread, 128-bit coalesced loads/stores of each SoA array, no tensor cores
+// (nothing here is a contraction).  The reference launches one kernel per half element
+// (simulation/src/simulation_engine.cu:125-373); the maps themselves restate
+// simulation/inc/simulation_kernel.cu:16-871 and space_charge_kernel.cu:573-706.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include "hps_internal.h"
+
+namespace hps {
+
+// util/inc/constant.h:7-11
+#define K_CLIGHT 299.792458
+#define K_PI 3.14159265358979323846
+#define K_TWOPI (3.14159265358979323846 * 2.0)
+
+struct Pt {
+  double x, xp, y, yp, phi, w;
+  u32 loss;
+};
+
+// ------------------------------------------------------------------------------------------------
+// block / grid reduction with a deterministic final pass by the last block to finish
+// ------------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void warp_reduce(double (&v)[NS], unsigned max_mask) {
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double t = __shfl_xor_sync(0xffffffffu, v[s], o);
+      v[s] = ((max_mask >> s) & 1u) ? fmax(v[s], t) : v[s] + t;
+    }
+  }
+}
+
+// Returns true in every thread of the block that finished last; `total` (shared) then holds the
+// grid-wide result of every slot.  partials: [gridDim.x][NS].
+template <int NS>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, double* partials, u32* ticket,
+                                            double* total /* shared, NS */, double* scratch /* shared, 32*NS */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  warp_reduce<NS>(v, max_mask);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) scratch[wid * NS + s] = v[s];
+  }
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    const int s = threadIdx.x;
+    double a = scratch[s];
+    for (int k = 1; k < nw; ++k) a = ((max_mask >> s) & 1u) ? fmax(a, scratch[k * NS + s]) : a + scratch[k * NS + s];
+    partials[(size_t)blockIdx.x * NS + s] = a;
+  }
+  __shared__ u32 s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  // last block: warp w reduces slots w, w+nw, ... ; lanes stride over the blocks in a fixed order
+  for (int s = wid; s < NS; s += nw) {
+    const bool mx = (max_mask >> s) & 1u;
+    double a = mx ? -DBL_MAX : 0.0;
+    for (u32 k = lane; k < gridDim.x; k += 32) {
+      double t = __ldcg(&partials[(size_t)k * NS + s]);
+      a = mx ? fmax(a, t) : a + t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double t = __shfl_xor_sync(0xffffffffu, a, o);
+      a = mx ? fmax(a, t) : a + t;
+    }
+    if (lane == 0) total[s] = a;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+  __syncthreads();
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// element maps (one particle)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double beta_of(double w, double mass) {
+  double g1 = w / mass;
+  return sqrt(g1 * (g1 + 2.0)) / (g1 + 1.0);
+}
+
+// simulation_kernel.cu:87-118 -- a lost particle keeps its pre-drift x,y (H11)
+__device__ __forceinline__ void op_drift(Pt& p, const double* q, u32 elem, double mass) {
+  const double hl = q[0], aper2 = q[1] * q[1], wavelen = q[2];
+  double x = p.x, y = p.y;
+  x += p.xp * hl;
+  y += p.yp * hl;
+  if (aper2 != 0.0 && x * x + y * y > aper2) p.loss = elem;
+  else {
+    p.x = x; p.y = y;
+    p.phi += K_TWOPI * hl / (wavelen * beta_of(p.w, mass));
+  }
+}
+
+// simulation_kernel.cu:142-218 -- two quarter-length thick-lens maps, then the aperture test
+__device__ __forceinline__ void op_quad_half(Pt& p, const double* q, u32 elem, double mass, double charge) {
+  const double length = q[0], wavelen = q[3];
+  double aper2 = q[1]; aper2 *= aper2;
+  const double qg = q[2] * charge;
+  double tx = p.x, ty = p.y;  // what the aperture test sees
+  if (qg == 0) {
+    // the reference stores the drifted x,y but tests the aperture with the OLD values
+    p.x = tx + p.xp * length * 0.5;
+    p.y = ty + p.yp * length * 0.5;
+  } else {
+    double gamma1 = p.w / mass;
+    double bg = sqrt(gamma1 * (gamma1 + 2.0) * (1.0 + p.xp * p.xp + p.yp * p.yp));
+    double absqg = qg > 0.0 ? qg : -qg;
+    double k = sqrt(absqg / (bg * mass) * K_CLIGHT);
+    double inv_k = 1.0 / k;
+    double kds = length * 0.25 * k;
+    double s, c, sh = sinh(kds), ch = cosh(kds);
+    sincos(kds, &s, &c);
+    double sovk = s * inv_k, shovk = sh * inv_k, sk = s * k, shk = sh * k;
+    double x = p.x, xp = p.xp, y = p.y, yp = p.yp, t;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      if (qg > 0.0) {
+        t = c * x + sovk * xp; xp = -sk * x + c * xp; x = t;
+        t = ch * y + shovk * yp; yp = shk * y + ch * yp; y = t;
+      } else {
+        t = ch * x + shovk * xp; xp = shk * x + ch * xp; x = t;
+        t = c * y + sovk * yp; yp = -sk * y + c * yp; y = t;
+      }
+    }
+    p.x = x; p.xp = xp; p.y = y; p.yp = yp;
+    tx = x; ty = y;
+  }
+  if (aper2 != 0 && tx * tx + ty * ty > aper2) p.loss = elem;
+  else p.phi += K_TWOPI * length * 0.5 / (wavelen * beta_of(p.w, mass));
+}
+
+// indices into Op::p for the RF gap (rfgap_parameter.h:4-32)
+enum { G_LEN = 0, G_FREQ, G_CLBL, G_AMP, G_PHREF, G_PHSHIFT, G_EOUT, G_BETAC, G_DG, G_T, G_TP, G_SP,
+       G_FBC, G_FBMIN, G_T0, G_T1, G_T2, G_T3, G_T4, G_T5, G_S1, G_S2, G_S3, G_S4, G_S5,
+       G_DESIGN_W = 25, G_PHI_IN = 26, G_QLEN1 = 27, G_QLEN2 = 28, G_CELLNUM = 29, G_WAVELEN = 30 };
+
+// simulation_kernel.cu:226-288
+__device__ __forceinline__ void op_gap_first(Pt& p, const double* q, bool ccl, double mass) {
+  const double qlen1 = q[G_QLEN1], qlen2 = q[G_QLEN2];
+  const double cell_len = q[G_LEN] + qlen1 * 0.5 + qlen2 * 0.5;
+  const double dd1 = 0.5 * cell_len - q[G_DG] - 0.5 * qlen1;
+  const double xp = p.xp, yp = p.yp, phi = p.phi, w = p.w;
+  p.x = p.x + dd1 * xp;
+  p.y = p.y + dd1 * yp;
+  const double wave_len = K_CLIGHT / q[G_FREQ];
+  if (q[G_AMP] == 0.0) {
+    p.phi += K_TWOPI * dd1 / (wave_len * beta_of(w, mass));
+  } else {
+    double gam = q[G_DESIGN_W] / mass;
+    double beta_in = sqrt((gam + 2.0) * gam) / (gam + 1.0);
+    gam = w / mass;
+    double beta = sqrt((gam + 2.0) * gam) / (gam + 1.0);
+    double dps = q[G_PHREF] - q[G_PHI_IN];
+    if (!ccl) {
+      double d_cell_len = cell_len - q[G_BETAC] * wave_len;
+      double dphi_qlen1 = K_TWOPI * 0.5 * qlen1 / (beta * wave_len);
+      double dphi_clen = 0.0;
+      if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = K_PI * d_cell_len / (beta * wave_len);
+      p.phi = phi + (1.0 - (beta - beta_in) / beta) * (K_PI * q[G_CLBL] + dps) + dphi_clen - dphi_qlen1;
+    } else {
+      double betag = cell_len / (q[G_CLBL] * wave_len);
+      p.phi = phi + (1.0 - (beta - beta_in) * betag / (beta * beta_in)) * (K_PI * q[G_CLBL] + dps);
+    }
+  }
+}
+
+// simulation_kernel.cu:16-73 (polynomial modified Bessel functions)
+__device__ __forceinline__ double bessi0c(double rx) {
+  double ans, y, ax = fabs(rx);
+  if (ax < 3.75) {
+    y = rx / 3.75; y = y * y;
+    ans = 1.0 + y * (3.5156229 + y * (3.0899424 + y * (1.2067492 + y * (0.2659732 + y * (0.360768e-1 + y * 0.45813e-2)))));
+  } else {
+    y = 3.75 / ax;
+    ans = (exp(ax) * rsqrt(ax)) * (0.39894228 + y * (0.1328592e-1 + y * (0.225319e-2 + y * (-0.157565e-2 + y * (0.916281e-2 +
+          y * (-0.2057706e-1 + y * (0.2635537e-1 + y * (-0.1647633e-1 + y * 0.392377e-2))))))));
+  }
+  return ans;
+}
+__device__ __forceinline__ double bessi1c(double rx) {
+  double y, ans, ax = fabs(rx);
+  if (ax < 3.75) {
+    y = rx / 3.75; y = y * y;
+    ans = ax * (0.5 + y * (0.87890594 + y * (0.51498869 + y * (0.15084934 + y * (0.2658733e-1 + y * (0.301532e-2 + y * 0.32411e-3))))));
+  } else {
+    y = 3.75 / ax;
+    ans = 0.2282967e-1 + y * (-0.2895312e-1 + y * (0.1787654e-1 - y * 0.420059e-2));
+    ans = 0.39894228 + y * (-0.3988024e-1 + y * (-0.362018e-2 + y * (0.163801e-2 + y * (-0.1031555e-1 + y * ans))));
+    ans = ans * (exp(ax) * rsqrt(ax));
+  }
+  return rx < 0.0 ? -ans : ans;
+}
+
+// simulation_kernel.cu:290-497
+__device__ __forceinline__ void op_gap_second(Pt& p, const double* q, bool ccl, double mass, double charge) {
+  const double qlen1 = q[G_QLEN1], qlen2 = q[G_QLEN2];
+  const double cell_len = q[G_LEN] + qlen1 * 0.5 + qlen2 * 0.5;
+  const double dd2 = 0.5 * cell_len + q[G_DG] - qlen2 * 0.5;
+  double x = p.x, y = p.y, xp = p.xp, yp = p.yp;
+  const double inv_mass = 1.0 / mass;
+  const double phi = p.phi;
+  double w = p.w;
+  const double gm_in = q[G_DESIGN_W] * inv_mass + 1.0;
+  const double beta_in = sqrt(1.0 - 1.0 / (gm_in * gm_in));
+  double gam = w * inv_mass;
+  const double bg1 = sqrt(gam * (gam + 2.0));
+  double beta = bg1 / (gam + 1.0);
+  // transit-time factors from the 5th-order fits (GetTransitTimeFactors)
+  double t_fac, tp_fac, sp_fac;
+  {
+    const double betag = q[G_FBC];
+    double bb = beta;
+    if (beta > 1.1 * betag) bb = betag;
+    else if (beta < q[G_FBMIN]) bb = q[G_FBMIN];
+    t_fac = q[G_T0] + bb * (q[G_T1] + bb * (q[G_T2] + bb * (q[G_T3] + bb * (q[G_T4] + bb * q[G_T5]))));
+    double coef = bb * bb / (K_TWOPI * betag);
+    tp_fac = coef * (q[G_T1] + bb * (2 * q[G_T2] + bb * (3 * q[G_T3] + bb * (4 * q[G_T4] + 5 * bb * q[G_T5]))));
+    sp_fac = -coef * (q[G_S1] + bb * (2 * q[G_S2] + bb * (3 * q[G_S3] + bb * (4 * q[G_S4] + 5 * bb * q[G_S5]))));
+  }
+  if (q[G_AMP] == 0.0 || (ccl && beta < q[G_FBMIN])) {
+    p.x = x + dd2 * xp;
+    p.y = y + dd2 * yp;
+    p.phi += K_TWOPI * dd2 / (q[G_WAVELEN] * beta_of(w, mass));
+    return;
+  }
+  const double wave_len = K_CLIGHT / q[G_FREQ];
+  const double cl = cell_len / q[G_CLBL];
+  const double betag_ccl = cl / wave_len;
+  const double betag = ccl ? q[G_BETAC] : betag_ccl;
+  const double betag2 = betag * betag;
+  const double gmg = 1.0 / sqrt(1.0 - betag2);
+  const double inv_gmg2 = 1.0 / (gmg * gmg);
+  const double aq = charge > 0.0 ? charge : -charge;
+  const double gm_out = q[G_EOUT] * inv_mass + 1.0;
+  const double beta_out = sqrt(1.0 - 1.0 / (gm_out * gm_out));
+  const double efl = q[G_AMP] * cell_len;
+  const double concomm = aq * efl / (mass * betag2);
+  const double concomm1 = concomm * inv_gmg2 / gmg;
+  const double con1 = K_PI * concomm1;
+  const double con2nex = concomm * inv_gmg2;
+  double con5nex, tw, inv_fkis, inv_gmgcl;
+  if (ccl) {
+    inv_gmgcl = 1.0 / (gmg * betag * wave_len);
+    inv_fkis = betag * wave_len / K_TWOPI;
+    con5nex = concomm * (t_fac * inv_fkis - betag_ccl * wave_len * tp_fac * inv_gmg2);
+    tw = t_fac - K_TWOPI * tp_fac * (beta_in / beta - 1.0) * betag_ccl / beta_in;
+  } else {
+    inv_gmgcl = 1.0 / (gmg * cl);
+    inv_fkis = cl / K_TWOPI;
+    con5nex = concomm * (t_fac * inv_fkis - beta_in * wave_len * tp_fac * inv_gmg2);
+    tw = t_fac;
+  }
+  const double con5nex1 = concomm1 * t_fac;
+  const double con5nex2 = -con2nex * t_fac * inv_fkis;
+  const double fkr = K_TWOPI * inv_gmgcl;
+  double sinps, cosps;
+  sincos(q[G_PHREF], &sinps, &cosps);
+  double phi1, sinp1, cosp1;
+  if (ccl) phi1 = phi + q[G_PHSHIFT] - K_TWOPI * q[G_DG] / (beta * wave_len) + (u32)q[G_CELLNUM] * K_PI;
+  else phi1 = phi + q[G_PHSHIFT];
+  sincos(phi1, &sinp1, &cosp1);
+  const double prome1 = -con1 * (tp_fac * (sinp1 - sinps) + sp_fac * (cosp1 - cosps));
+  sincos(phi1 + prome1, &sinp1, &cosp1);
+
+  const double rs_p = x * x + y * y;
+  const double rrp = x * xp + y * yp;
+  const double ris = sqrt(rs_p);
+  const double fkrris = fkr * ris;
+  const double b0c = bessi0c(fkrris);
+  const double b1c = bessi1c(fkrris);
+  const double b1p = (fkrris != 0.0) ? b0c - b1c / fkrris : 0.5;
+  double bes1covr, rpris = 0.0;
+  if (ris != 0.0) bes1covr = b1c / ris; else bes1covr = fkr * 0.5;
+  const double delte = aq * efl * (tw * b0c * cosp1 + ((tw - K_TWOPI * tp_fac) / gmg * bes1covr + tw / gmg * fkr * b1p -
+                                                      tw * gmg * bes1covr) * rrp * sinp1);
+  w += delte;
+  gam = w * inv_mass;
+  const double bg = sqrt(gam * (gam + 2.0));
+  beta = bg / (gam + 1.0);
+  const double bgr = bg1 / bg;
+  const double onema = 1.0 - (con5nex * bes1covr + con5nex1 * b1p + con5nex2 * bes1covr) * cosp1;
+  const double dovbl = con2nex * bes1covr * tw * sinp1;
+  const double bgrovonema = bgr / onema;
+  xp = -dovbl * x + bgrovonema * xp;
+  x = x * onema + dd2 * xp;
+  yp = -dovbl * y + bgrovonema * yp;
+  y = y * onema + dd2 * yp;
+  if (rs_p > 0.0) rpris = rrp / ris;
+  const double prome = 2.0 * con1 * (-tp_fac * b0c + ris * tw * b1c * inv_gmgcl) * (sinp1 - sinps) -
+                       efl * inv_mass * tw * b1c * rpris * (cosp1 - cosps);
+  double phi_new;
+  if (ccl) {
+    double dps = q[G_PHI_IN] - q[G_PHREF];
+    phi_new = phi + (1.0 - (beta - beta_out) * betag_ccl / (beta * beta_out)) * (K_PI * q[G_CLBL] + dps) + prome;
+  } else {
+    double d_cell_len = cell_len - q[G_BETAC] * wave_len;
+    double dphi_qlen2 = K_TWOPI * 0.5 * qlen2 / (beta * wave_len);
+    double dphi_clen = 0.0;
+    if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = K_PI * d_cell_len / (beta * wave_len);
+    double dps = q[G_PHREF] - q[G_PHI_IN];
+    phi_new = phi + (1.0 - (beta - beta_out) / beta) * (K_PI * q[G_CLBL] + dps) + prome + dphi_clen - dphi_qlen2;
+  }
+  if (w <= 0.0 || x != x || y != y || xp != xp || yp != yp || w != w || phi_new != phi_new) {
+    p.loss = 33333333u;  // the reference also printf()s here; coordinates keep their pre-gap values
+  } else {
+    p.x = x; p.y = y; p.xp = xp; p.yp = yp; p.w = w; p.phi = phi_new;
+  }
+}
+
+// simulation_kernel.cu:603-805.  q: 0 radius 1 angle 2 edge_in 3 edge_out 4 half_gap 5 k1 6 k2 7 field_index
+// 8 kinetic_energy 9 wavelen
+__device__ __forceinline__ void op_dipole(Pt& p, const double* q, bool second, double mass) {
+  double x = p.x, xp = p.xp, y = p.y, yp = p.yp;
+  const double h = 1.0 / q[0];
+  const double hf_g = q[4], k1 = q[5], k2 = q[6], findx = q[7], design_w = q[8];
+  if (!second) {
+    const double b1 = q[2];
+    double c1 = 2.0 * hf_g * k1 * h;
+    double sinb, inv_cosb;
+    sincos(b1, &sinb, &inv_cosb);
+    inv_cosb = 1.0 / inv_cosb;
+    double psi = c1 * (1.0 + sinb * sinb) * inv_cosb * (1.0 - c1 * k2 * sinb * inv_cosb);
+    xp += tan(b1) * h * x;
+    yp -= tan(b1 - psi) * h * y;
+  }
+  const double h2 = h * h;
+  const double dl = 0.5 * q[0] * q[1];
+  const double yk2 = findx * h2;
+  const double yk = sqrt(fabs(yk2));
+  const double inv_yk = 1.0 / yk;
+  const double ykl = yk * dl;
+  const double xk2 = h2 - yk2;
+  const double inv_xk2 = 1.0 / xk2;
+  const double xk = sqrt(fabs(xk2));
+  const double inv_xk = 1.0 / xk;
+  const double xkl = xk * dl;
+  double cxkl = 1.0, sxokx = dl;
+  if (xk2 > 0.0) { cxkl = cos(xkl); sxokx = sin(xkl) * inv_xk; }
+  else if (xk2 < 0.0) { cxkl = cosh(xkl); sxokx = sinh(xkl) * inv_xk; }
+  double cykl = 1.0, syoky = dl;
+  if (yk2 > 0.0) { cykl = cos(ykl); syoky = sin(ykl) * inv_yk; }
+  else if (yk2 < 0.0) { cykl = cosh(ykl); syoky = sinh(ykl) * inv_yk; }
+  const double r11 = cxkl, r12 = sxokx, r21 = -xk2 * sxokx, r22 = cxkl;
+  const double r33 = cykl, r34 = syoky, r43 = -yk2 * syoky, r44 = cykl;
+  const double r26 = h * sxokx, r16 = h * (1.0 - cxkl) * inv_xk2;
+  const double r51 = -r26, r52 = -r16;
+  const double gamma = design_w / mass + 1.0;
+  const double beta2 = 1.0 - 1.0 / (gamma * gamma);
+  const double beta = sqrt(beta2);
+  const double r56 = -h2 * (dl * beta2 - sxokx) * inv_xk2 + dl * (1.0 - h2 * inv_xk2) / (gamma * gamma);
+  const double dpop = gamma / (design_w * (gamma + 1.0)) * (p.w - design_w);
+  p.phi += K_TWOPI * (-(r51 * x + r52 * xp + r56 * dpop) + dl) / (beta * q[9]);
+  const double x_new = r11 * x + r12 * xp + r16 * dpop;
+  const double xp_new = r21 * x + r22 * xp + r26 * dpop;
+  const double y_new = r33 * y + r34 * yp;
+  const double yp_new = r43 * y + r44 * yp;
+  p.x = x_new; p.y = y_new;
+  if (!second) {
+    p.xp = xp_new; p.yp = yp_new;
+  } else {
+    const double b2 = q[3];
+    double c1 = 2.0 * hf_g * k1 * h;
+    double sinb = sin(b2), inv_cosb = 1.0 / cos(b2);
+    double psi = c1 * (1.0 + sinb * sinb) * inv_cosb * (1.0 - c1 * k2 * sinb * inv_cosb);
+    p.xp = xp_new + tan(b2) * h * x_new;
+    p.yp = yp_new - tan(b2 - psi) * h * y_new;
+  }
+}
+
+// simulation_kernel.cu:807-871.  q: 0 w_ref 1 freq 2 voltage 3 phase 4 aperture 5 freq_ratio 6 wavelen
+__device__ __forceinline__ void op_buncher(Pt& p, const double* q, u32 elem, double mass, double charge) {
+  const double wavelen = q[6];
+  const double x = p.x, y = p.y, w = p.w;
+  const double phi = p.phi * q[5];
+  const double r2 = x * x + y * y;
+  const double aper2 = q[4] * q[4];
+  if (aper2 != 0.0 && r2 > aper2) { p.loss = elem; return; }
+  const double h = q[1] * wavelen / K_CLIGHT;
+  const double gm1 = q[0] / mass;
+  const double gm = gm1 + 1.0;
+  const double btgm = sqrt(gm1 * (gm1 + 2.0));
+  const double beta = btgm / gm;
+  const double k = h * K_TWOPI / (btgm * wavelen);
+  const double k2 = k * k;
+  const double aq = charge > 0.0 ? charge : -charge;
+  const double con1 = K_TWOPI * h * q[2] * aq / (beta * wavelen * mass);
+  const double arg = k2 * r2 * 0.25;
+  const double ph = h * phi + q[3];
+  const double dw = aq * q[2] * cos(ph) * (1.0 + arg * (1.0 + arg * (0.25 + arg / 36.0)));
+  const double wb_par = w + 0.5 * dw;
+  const double wf = w + dw;
+  if (wb_par <= 0.0 || wf <= 0.0) { p.loss = elem; return; }
+  double gmtmp = wb_par / mass;
+  const double bav = sqrt(gmtmp * (gmtmp + 2.0)) / (gmtmp + 1.0);
+  gmtmp = w / mass;
+  const double bg = sqrt(gmtmp * (gmtmp + 2.0));
+  gmtmp = wf / mass;
+  const double rbgf = rsqrt(gmtmp * (gmtmp + 2.0));
+  const double del = -con1 * sin(ph) * (1.0 - bav * beta) * (0.5 + arg * (0.25 + arg / 24.0)) / bav;
+  p.xp = (p.xp * bg + del * x) * rbgf;
+  p.yp = (p.yp * bg + del * y) * rbgf;
+  p.w = wf;
+}
+
+// relative phase (beam_kernel.cu:1506-1522)
+__device__ __forceinline__ double rel_phi(double phi, double ref) {
+  double tmp = phi - ref + K_PI;
+  double sign = 1.0;
+  if (tmp < 0) { sign = -1.0; tmp = -tmp; }
+  return sign * (fmod(tmp, K_TWOPI) - K_PI);
+}
+
+struct KickCtx {  // block-uniform inputs of the space-charge kick, staged in shared memory
+  double phimc, xbar, ybar, epsq, phi_ref;
+  double dr, dz, beta, ratio_r, ratio_z, ratio_q, ratio_g;
+  u32 adj_bunch, num_on_mesh, nr, nz;
+};
+
+// space_charge_kernel.cu:573-706
+__device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const double* q, const KickCtx& k, const double2* __restrict__ fld,
+                                           double mass, u32 n_global) {
+  if (!(p.loss == 0 && lloss == 0)) return;
+  const double length = q[0], current = q[1], freq = q[2];
+  const double beta = k.beta;
+  const double phi = rel_phi(p.phi, k.phi_ref);
+  const double gmg = rsqrt(1.0 - beta * beta);
+  const double dr = k.dr * k.ratio_r;
+  const double dzg = k.dz * gmg * k.ratio_z;
+  const double wave_len = K_CLIGHT / freq;
+  const double hl = k.nz * 0.5 * dzg;
+  const double c1 = 5721.67 * current / (freq * 1e6 * (double)n_global * mass);
+  const double c2 = beta * gmg * wave_len / K_TWOPI;
+  const double c3 = length / (beta * gmg);
+  const double xfac = 2.0 / (k.epsq + 1.0);
+  const double yfac = k.epsq * xfac;
+  const double gm = p.w / mass + 1.0;
+  const double bgz = sqrt((gm - 1.0) * (gm + 1.0));
+  double bgx = bgz * p.xp, bgy = bgz * p.yp;
+  double bgzstar = gmg * (bgz - beta * gm);
+  const double xxbar = p.x - k.xbar, yybar = p.y - k.ybar;
+  double r = sqrt(xxbar * xxbar / k.epsq + yybar * yybar * k.epsq);
+  if (r == 0.0) r = 1.0e-8;
+  const double xovr = xxbar * xfac / r, yovr = yybar * yfac / r;
+  double ddz = phi - k.phimc;
+  while (ddz > K_PI || ddz < -K_PI) {
+    if (ddz > 0.0) ddz -= K_TWOPI; else ddz += K_TWOPI;
+  }
+  double z = -c2 * ddz;
+  double cbgr, cbgzs;
+  if (r > k.nr * dr || fabs(z) > hl) {  // off the mesh: point-charge field of the on-mesh charge (H17)
+    z = -c2 * (phi - k.phimc);
+    double d = sqrt(z * z + r * r);
+    double invd3 = 1.0 / (d * d * d);
+    double rod3 = r * invd3, zod3 = z * invd3;
+    const double pl = beta * gmg * wave_len;
+    for (int nb = 1; nb <= (int)k.adj_bunch; ++nb) {
+      int xi = nb;
+      for (int lr = 1; lr <= 2; ++lr) {
+        double s = z + xi * pl;
+        d = sqrt(s * s + r * r);
+        invd3 = 1.0 / (d * d * d);
+        rod3 += r * invd3;
+        zod3 += s * invd3;
+        xi = -xi;
+      }
+    }
+    const double cbgcoef = c1 * c3 * K_PI * 0.5 * k.num_on_mesh;
+    cbgr = cbgcoef * rod3;
+    cbgzs = cbgcoef * zod3;
+  } else {
+    const u32 i = 1 + (int)(r / dr);
+    const double a = r / dr - (i - 1.0), b = 1.0 - a;
+    const u32 j = 1 + (int)((z + hl) / dzg);
+    const double c = (z + hl) / dzg - (j - 1.0), d = 1.0 - c;
+    const u32 l = (j - 1) * (k.nr + 1) + i;
+    u32 m = l + (k.nr + 1);
+    const u32 tbl_sz = (k.nr + 1) * (k.nz + 1);
+    if (m >= tbl_sz) m = tbl_sz - 1;
+    const double er_ratio = k.ratio_q / (k.ratio_r * k.ratio_z * k.ratio_g * k.ratio_g);
+    const double ez_ratio = k.ratio_q / (k.ratio_z * k.ratio_z);
+    const double2 fl = __ldg(&fld[l]), fl1 = __ldg(&fld[l - 1]), fm = __ldg(&fld[m]), fm1 = __ldg(&fld[m - 1]);
+    cbgr = er_ratio * c3 * (d * (a * fl.x + b * fl1.x) + c * (a * fm.x + b * fm1.x));
+    cbgzs = ez_ratio * c3 * (d * (a * fl.y + b * fl1.y) + c * (a * fm.y + b * fm1.y));
+  }
+  bgx += cbgr * xovr;
+  bgy += cbgr * yovr;
+  bgzstar += cbgzs;
+  const double gstar = 1.0 + 0.5 * bgzstar * bgzstar;
+  const double bgzf = gmg * (bgzstar + beta * gstar);
+  if (bgzf <= 0.0) p.loss = 9999u;
+  else {
+    p.xp = bgx / bgzf;
+    p.yp = bgy / bgzf;
+    p.w *= 1.0 + (gm + 1.0) * (bgzf - bgz) / (gm * bgz);
+  }
+}
+
+}  // namespace hps

@@ -1,0 +1,49 @@
+// hps_launch.h -- host-callable wrappers around the kernels in hps_kernels.cu.
+#ifndef HPS_LAUNCH_H
+#define HPS_LAUNCH_H
+
+#include <cuda_runtime.h>
+#include "hps_internal.h"
+
+namespace hps {
+
+struct LaunchCfg {
+  cudaStream_t stream;
+  unsigned grid_pairs;    // grid of the 2-particles-per-thread sweeps
+  unsigned grid_single;   // grid of the 1-particle-per-thread API statistics kernel
+  unsigned grid_deposit;
+  double* partials;       // [max grid][HPS_NSLOT]
+  u32* ticket;
+};
+
+enum StatKind {
+  KS_COUNT_LOSS = 0, KS_COUNT_LLOSS, KS_COUNT_GOOD, KS_MARK_LLOSS, KS_AVG, KS_SIG, KS_AVG_XY, KS_EMIT_T, KS_EMIT_Z,
+  KS_MAX_R_PHI
+};
+struct StatReq {
+  int kind;
+  int var_a, var_b;   // 0..5 = x xp y yp phi w, 6 = relative phase; var_b = -1 when unused
+  int good_only;
+  int out[5];
+  double w_ref;       // w[0] for the emittance normalisation (beam_kernel.cu:1345)
+};
+
+void launch_segment(const LaunchCfg&, const BeamView&, const Op* ops, int nops, int fin_mode, int dirty, int compat,
+                    DevStats*, const ScDev*, const double2* field, const KickParams&);
+void launch_lloss_pass(const LaunchCfg&, const BeamView&, DevStats*, ScDev*);
+void launch_moments(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&, int do_policy);
+cudaError_t launch_deposit(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&);
+cudaError_t launch_field(const LaunchCfg&, DevStats*, ScDev*, const double* bins, double2* field, const KickParams&);
+void launch_stat(const LaunchCfg&, const BeamView&, DevStats*, const StatReq&);
+void launch_set_phi_ref(const LaunchCfg&, const BeamView&, DevStats*, int use_good, double phi0);
+void launch_copy_stat(const LaunchCfg&, DevStats*, int dst, int src);
+void launch_shift(const LaunchCfg&, double* a, double v, u32 n, u32 offset);
+void launch_cut(const LaunchCfg&, const double* a, u32* loss, double lo, double hi, u32 n, u32 offset);
+void launch_rel_phi_out(const LaunchCfg&, const BeamView&, const DevStats*, double* out);
+int segment_occupancy();
+size_t deposit_smem(const KickParams&);
+size_t field_smem(const KickParams&, int threads);
+int field_threads(const KickParams&);
+
+}  // namespace hps
+#endif

@@ -96,7 +96,18 @@ def open_dbs(db_paths: Sequence[str], names: Sequence[str] | None = None) -> tup
     return conn, dbs
 
 
-def load_from_conn(conn: sqlite3.Connection, dbs: Iterable[str]) -> np.ndarray:
+# number of meaningful parameter slots per element type (for printing)
+NPARAM_USED = {DRIFT: 2, QUAD: 3, RFGAP_DTL: 25, RFGAP_CCL: 25, ROTATION: 1, CAPERTURE: 1, RAPERTURE: 4,
+               DIAGNOSTICS: 0, BUNCHER: 4, DIPOLE: 9, SPCH_COMP: 1, STEERER: 2}
+
+_TABLE_OF = {"quad": "quad", "drift": "drift", "dtl_gap": "rf_gap", "ccl_gap": "rf_gap", "rotation": "rotation",
+             "caperture": "caperture", "raperture": "raperture", "diagnostics": "diagnostics",
+             "buncher": "buncher", "dipole": "dipole", "spch_comp": "spch_comp", "steerer": "steerer"}
+
+
+def load_from_conn(conn: sqlite3.Connection, dbs: Iterable[str], write_model_index: bool = False) -> np.ndarray:
+    """`write_model_index=True` also records each element's model index in its table row, as
+    GenerateBeamLine does (init.cpp:68-73) -- only ever used on a private in-memory copy."""
     q = _Db(conn)
     out = []
 
@@ -192,6 +203,8 @@ def load_from_conn(conn: sqlite3.Connection, dbs: Iterable[str]) -> np.ndarray:
                 e["p"][1] = _atof(col("steerer", "bl_v_model"))
             else:
                 continue  # GenerateBeamLine ignores unknown model types
+            if write_model_index:
+                conn.execute(f"update {db}.{_TABLE_OF[mtype]} set model_index = {len(out)} where view_index = {view_index}")
             out.append(e)
     return np.array(out, dtype=ELEM_DTYPE)
 

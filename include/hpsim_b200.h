@@ -106,6 +106,13 @@ int hps_ctx_set_compat(hps_ctx*, int compat_reference);
 int hps_comm_unique_id(void* out128);
 int hps_ctx_comm_init(hps_ctx*, int rank, int nranks, const void* nccl_unique_id);
 
+/* Pinned host staging buffers for hps_beam_upload / hps_beam_download (optional: any host pointer
+ * works, pinned ones copy at full PCIe rate), and the number of kernels this context has launched
+ * so far (bench.py reports the per-step delta as gpu_launches).  No reference counterpart. */
+void* hps_host_alloc(size_t bytes);
+void hps_host_free(void*);
+uint64_t hps_ctx_launch_count(hps_ctx*);
+
 /* ---- beam ---------------------------------------------------------------- */
 /* Replaces Beam::Beam(num, mass, charge, current) + AllocateBeam
  * (reference src/beam/src/beam.cpp:70-147).  With sharding, `n_global` is the

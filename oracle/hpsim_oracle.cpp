@@ -826,9 +826,11 @@ void Deposit(hps_scheff* s, const hps_beam* b, double beta, double freq) {
     if (j1 != jm1) cc = (zz - (j1 - 1 + 0.5) * dzg) / ((jm1 - j1) * dzg);
     double bb = 1.0 - a, d = 1.0 - cc;
     int k = (jm1 - 1) * nx + i;
-    s->bins[k - 1] += a * cc;
-    k += i1 - i;
-    s->bins[k - 1] += bb * cc;
+    if (jm1 <= (int)nz) {  // jm1 == nz+1 (zz/dzg rounding up to nz) writes past the table in the reference
+      s->bins[k - 1] += a * cc;
+      k += i1 - i;
+      s->bins[k - 1] += bb * cc;
+    }
     k = (j1 - 1) * nx + i;
     s->bins[k - 1] += a * d;
     k += i1 - i;
@@ -1150,6 +1152,9 @@ int hps_ctx_comm_init(hps_ctx* c, int, int nranks, const void*) {
   return nranks == 1 ? HPS_OK : fail(c, HPS_ERR_COMM, "the CPU oracle is single-process");
 }
 int hps_ctx_synchronize(hps_ctx*) { return HPS_OK; }
+void* hps_host_alloc(size_t bytes) { return std::malloc(bytes); }
+void hps_host_free(void* p) { std::free(p); }
+uint64_t hps_ctx_launch_count(hps_ctx*) { return 0; }
 // oracle-only: OpenMP thread count (0 = runtime default)
 int hps_oracle_set_threads(hps_ctx* c, int n) {
   c->nthreads = n;

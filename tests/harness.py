@@ -1,0 +1,181 @@
+"""Shared helpers of the test-suite: build/load the CPU oracle, drive either implementation of the
+C ABI through the HPSim mirror, run the reference-CUDA driver (oracle/_ref) and compare beams."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from hpsim_b200 import HPSim, _capi as K, lattice as L  # noqa: E402
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libhpsim_oracle.so")
+REF_DP = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dp")
+REF_SP = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+LATTICE = os.path.join(ROOT, "tests", "golden", "lansce.lat")
+
+# C1 beam recipe
+DC = dict(ax=0.095, bx=47.0, ex=0.00327, ay=-0.102, by=60.0, ey=0.002514, dphi=np.pi, sync_phi=0.0, sync_w=0.7518)
+SEED = 20161201
+PHI_OFFSET = -707.907480574  # rad = -40560.11 deg
+MASS, CHARGE, CURRENT, FREQ, REF_W = 939.294, -1.0, 0.015, 201.25, 0.750
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        src = os.path.join(ROOT, "oracle", "hpsim_oracle.cpp")
+        if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "cpu"])
+        _oracle = K.bind(C.CDLL(ORACLE_SO, mode=C.RTLD_LOCAL))
+        _oracle.hps_oracle_get_threads.restype = C.c_int
+    return _oracle
+
+
+def cuda_lib():
+    return K.load()
+
+
+_lat = None
+
+
+def lattice():
+    global _lat
+    if _lat is None:
+        _lat = L.load(LATTICE)
+    return _lat
+
+
+class Case:
+    """One beam + beamline + (optional) SCHEFF on one implementation."""
+
+    def __init__(self, lib, n=65536, sc=True, nr=32, nz=128, interval=0.025, adj_bunch=3, cutoff_w=0.8, remesh=0.02,
+                 seed=SEED, table=None, make_beam=True):
+        HPSim._use_library(lib)
+        self.lib = lib
+        self.beamline = HPSim.BeamLine(table=lattice() if table is None else table)
+        self.beam = HPSim.Beam(mass=MASS, charge=CHARGE, current=CURRENT, num=n)
+        if make_beam:
+            self.beam.set_dc(DC["ax"], DC["bx"], DC["ex"], DC["ay"], DC["by"], DC["ey"], DC["dphi"], DC["sync_phi"], DC["sync_w"], seed)
+            self.beam.set_frequency(FREQ)
+            self.beam.set_ref_w(REF_W)
+            self.beam.set_ref_phi(PHI_OFFSET)
+            self.beam.translate("phi", PHI_OFFSET)
+            self.beam.save_initial_beam()
+        self.spch = None
+        if sc:
+            self.spch = HPSim.SpaceCharge(nr=nr, nz=nz, interval=interval, adj_bunch=adj_bunch)
+            self.spch.set_adj_bunch_cutoff_w(cutoff_w)
+            self.spch.set_remesh_threshold(remesh)
+        self.sim = HPSim.Simulator(self.beam, self.beamline, self.spch)
+        HPSim._use_library(None)
+
+    def run(self, first, last):
+        self.sim.simulate(first, last)
+        return self.sim.last_run
+
+    def state(self):
+        d = self.beam._arrays()
+        return d
+
+    def moments(self):
+        b = self.beam
+        return dict(loss=b.get_loss_num("t"), lloss=b.get_loss_num("l"),
+                    x_avg=b.get_avg_x(), y_avg=b.get_avg_y(), x_sig=b.get_sig_x(), y_sig=b.get_sig_y(),
+                    w_avg=b.get_avg_w(), w_sig=b.get_sig_w(), phi_avg=b.get_avg_phi(), phi_sig=b.get_sig_phi(),
+                    ex=b.get_emittance_x(), ey=b.get_emittance_y(), ez=b.get_emittance_z())
+
+
+def compare(a, b, rtol):
+    """Per-particle comparison of two beam states; returns a report dict.  Coordinates of particles
+    alive in both are compared with a tolerance relative to the rms extent of each coordinate
+    (phi: relative to its own magnitude is meaningless for an absolute phase of ~1e3 rad)."""
+    rep = {}
+    rep["loss_equal"] = bool(np.array_equal(a["loss"], b["loss"]))
+    rep["lloss_equal"] = bool(np.array_equal(a["lloss"], b["lloss"]))
+    rep["n_loss"] = (int((a["loss"] != 0).sum()), int((b["loss"] != 0).sum()))
+    rep["n_lloss"] = (int((a["lloss"] != 0).sum()), int((b["lloss"] != 0).sum()))
+    rep["loss_mismatch"] = int((a["loss"] != b["loss"]).sum())
+    both = (a["loss"] == 0) & (b["loss"] == 0)
+    worst = 0.0
+    for k in ("x", "xp", "y", "yp", "phi", "w"):
+        va, vb = a[k][both], b[k][both]
+        if len(va) == 0:
+            continue
+        scale = max(np.std(va), 1e-300) if k != "w" else max(np.abs(va).max(), 1e-300)
+        if k == "phi":
+            scale = max(np.std(va), 1.0)
+        err = np.abs(va - vb).max() / scale
+        rep["err_" + k] = float(err)
+        worst = max(worst, err)
+    rep["worst"] = float(worst)
+    rep["ok"] = rep["loss_equal"] and worst <= rtol
+    return rep
+
+
+# ---- reference CUDA driver (Oracle A) -----------------------------------------------------------
+def read_beam_file(path):
+    with open(path, "rb") as f:
+        assert f.read(4) == b"HPSB"
+        ver, n = struct.unpack("<IQ", f.read(12))
+        d = {}
+        for k in ("x", "xp", "y", "yp", "phi", "w"):
+            d[k] = np.frombuffer(f.read(8 * n), dtype=np.float64).copy()
+        d["loss"] = np.frombuffer(f.read(4 * n), dtype=np.uint32).copy()
+        d["lloss"] = np.frombuffer(f.read(4 * n), dtype=np.uint32).copy()
+        rest = f.read()
+        if len(rest) >= 4:
+            (ns,) = struct.unpack("<I", rest[:4])
+            d["stats"] = np.frombuffer(rest[4:4 + 8 * ns], dtype=np.float64).copy()
+    return d
+
+
+def write_beam_file(path, d):
+    n = len(d["x"])
+    with open(path, "wb") as f:
+        f.write(b"HPSB" + struct.pack("<IQ", 1, n))
+        for k in ("x", "xp", "y", "yp", "phi", "w"):
+            f.write(np.ascontiguousarray(d[k], dtype=np.float64).tobytes())
+        f.write(np.ascontiguousarray(d["loss"], dtype=np.uint32).tobytes())
+        f.write(np.ascontiguousarray(d["lloss"], dtype=np.uint32).tobytes())
+        f.write(struct.pack("<I", 0))
+
+
+REF_STATS = ["loss", "lloss", "good", "x_avg", "x_sig", "y_avg", "y_sig", "phi_avg", "phi_sig", "w_avg", "w_sig",
+             "ex", "ey", "ez", "phi_avg_r", "phi_sig_r", "ref_w", "ref_phi", "freq", "current", "design_w"]
+
+
+def run_reference(workdir, n, first, last, sc=True, double=True, nr=32, nz=128, interval=0.025, adj_bunch=3,
+                  cutoff_w=0.8, remesh=0.02, seed=SEED, beam_in=None, design_w=None, freq=FREQ, repeats=1, timeout=900):
+    """Runs oracle/_ref/ref_driver{,_dp} (the reference's own CUDA code) and returns (state, log)."""
+    exe = REF_DP if double else REF_SP
+    os.makedirs(workdir, exist_ok=True)
+    out = os.path.join(workdir, "ref_out.bin")
+    cfg = [f"lattice {LATTICE}", f"n {n}", f"mass {MASS}", f"charge {CHARGE}", f"current {CURRENT}",
+           f"sc {1 if sc else 0}", f"nr {nr}", f"nz {nz}", f"interval {interval}", f"adj_bunch {adj_bunch}",
+           f"adj_bunch_cutoff_w {cutoff_w}", f"remesh_threshold {remesh}", f"first {first}", f"last {last}",
+           f"beam_out {out}", f"repeats {repeats}"]
+    if beam_in is None:
+        cfg += ["gen dc", f"seed {seed}", f"freq {FREQ}", f"ref_w {REF_W}", f"ref_phi {PHI_OFFSET!r}", f"shift_phi {PHI_OFFSET!r}"]
+        for k, v in DC.items():
+            cfg.append(f"{k} {v!r}")
+    else:
+        cfg += [f"beam_in {beam_in}", f"freq {freq}"]
+        if design_w is not None:
+            cfg.append(f"design_w {design_w!r}")
+    path = os.path.join(workdir, "ref.cfg")
+    with open(path, "w") as f:
+        f.write("\n".join(cfg) + "\n")
+    p = subprocess.run([exe, path], capture_output=True, text=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError(f"ref_driver failed ({p.returncode}): {p.stdout[-2000:]} {p.stderr[-2000:]}")
+    return read_beam_file(out), p.stdout
