@@ -26,6 +26,7 @@ from . import lattice as L
 
 _backend = None
 _device = 0
+print_timing = True  # Simulator.simulate prints the reference's "Whole simulation time" line
 _ctx_cache = {}
 
 
@@ -463,7 +464,8 @@ class Simulator:
         sc = self.spch.h if (self.space_charge_on and self.spch is not None) else None
         self._c.check(self._c.lib.hps_simulate(self._c.h, self.beam.h, self.beamline.h, sc, first, last, C.byref(rs)))
         self.last_run = rs.as_dict()
-        print(f"Whole simulation time: {rs.device_ms / 1e3:g} [sec]")  # util/src/timer.cpp:10-19
+        if print_timing:
+            print(f"Whole simulation time: {rs.device_ms / 1e3:g} [sec]")  # util/src/timer.cpp:10-19
         return None
 
 

@@ -37,6 +37,7 @@ UPD_NAMES = [
 ]
 UPD = {n: i for i, n in enumerate(UPD_NAMES)}
 
+PROF_CLASSES = ["segment", "lloss", "moments", "deposit", "field"]
 SC_INTERVAL, SC_ADJ_BUNCH, SC_ADJ_BUNCH_CUTOFF_W, SC_MESH_CUTOFF_W, SC_REMESH_THRESHOLD, SC_FRACTION, SC_NR, SC_NZ = range(8)
 
 
@@ -74,6 +75,8 @@ PROTOTYPES = {
     "hps_host_alloc": (_vp, [C.c_size_t]),
     "hps_host_free": (None, [_vp]),
     "hps_ctx_launch_count": (C.c_uint64, [_vp]),
+    "hps_ctx_set_profile": (C.c_int, [_vp, C.c_int]),
+    "hps_ctx_get_profile": (C.c_int, [_vp, _vp, _vp]),
     "hps_beam_create": (_vp, [_vp, C.c_uint64, C.c_double, C.c_double, C.c_double]),
     "hps_beam_destroy": (None, [_vp]),
     "hps_beam_local_range": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

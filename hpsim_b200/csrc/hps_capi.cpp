@@ -46,6 +46,12 @@ struct hps_ctx {
   size_t ops_cap = 0;
   Comm comm;
   uint64_t launches = 0;
+  // optional per-launch timing (hps_ctx_set_profile): one event between consecutive launches
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_cls;
+  double prof_ms[HPS_PROF_NCLASS] = {0, 0, 0, 0, 0};
+  uint64_t prof_n[HPS_PROF_NCLASS] = {0, 0, 0, 0, 0};
 };
 
 struct hps_beam {
@@ -212,6 +218,31 @@ void UpdateStatForSpaceCharge(hps_beam* b) {
   c->launches += 3;
 }
 
+// profiling: mark() before each launch of class `cls`, finish() after the last one
+void prof_mark(hps_ctx* c, int cls) {
+  if (!c->profile) return;
+  const size_t k = c->prof_cls.size();
+  if (k >= c->prof_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->prof_ev.push_back(e);
+  }
+  cudaEventRecord(c->prof_ev[k], c->stream);
+  c->prof_cls.push_back(cls);
+}
+void prof_finish(hps_ctx* c) {
+  if (!c->profile || c->prof_cls.empty()) return;
+  prof_mark(c, -1);
+  cudaStreamSynchronize(c->stream);
+  for (size_t k = 0; k + 1 < c->prof_cls.size(); ++k) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->prof_ev[k], c->prof_ev[k + 1]);
+    c->prof_ms[c->prof_cls[k]] += ms;
+    c->prof_n[c->prof_cls[k]]++;
+  }
+  c->prof_cls.clear();
+}
+
 int dirty_mask(const Op* ops, u32 n) {
   int d = 0;
   for (u32 i = 0; i < n; ++i) switch (ops[i].type) {
@@ -278,6 +309,7 @@ void hps_ctx_destroy(hps_ctx* c) {
   cudaSetDevice(c->device);
   comm_destroy(c->comm);
   cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_ops); cudaFreeHost(c->h_ops);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -285,6 +317,15 @@ const char* hps_last_error(const hps_ctx* c) { return c ? c->err.c_str() : g_err
 int hps_ctx_set_compat(hps_ctx* c, int v) { c->compat = v; return HPS_OK; }
 int hps_ctx_synchronize(hps_ctx* c) { CK(c, cudaStreamSynchronize(c->stream)); return HPS_OK; }
 uint64_t hps_ctx_launch_count(hps_ctx* c) { return c->launches; }
+int hps_ctx_set_profile(hps_ctx* c, int on) {
+  c->profile = on;
+  for (int k = 0; k < HPS_PROF_NCLASS; ++k) { c->prof_ms[k] = 0.0; c->prof_n[k] = 0; }
+  return HPS_OK;
+}
+int hps_ctx_get_profile(hps_ctx* c, double* ms, uint64_t* n) {
+  for (int k = 0; k < HPS_PROF_NCLASS; ++k) { ms[k] = c->prof_ms[k]; n[k] = c->prof_n[k]; }
+  return HPS_OK;
+}
 
 int hps_comm_unique_id(void* out128) { return comm_unique_id(out128) ? HPS_ERR_COMM : HPS_OK; }
 int hps_ctx_comm_init(hps_ctx* c, int rank, int nranks, const void* id) {
@@ -749,21 +790,27 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
   CK(c, cudaEventRecord(c->ev0, c->stream));
   for (const Segment& s : plan.segs) {
     const int dirty = dirty_mask(plan.ops.data() + s.op_begin, s.op_count);
+    prof_mark(c, HPS_PROF_SEGMENT);
     launch_segment(l, v, c->d_ops + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
                    sc ? sc->field : nullptr, s.kp);
     c->launches++;
     sweeps++;
     if (!s.kick_follows) { extra++; continue; }
     if (sharded) return fail(c, HPS_ERR_COMM, "sharded space-charge kick is not wired up yet");
+    prof_mark(c, HPS_PROF_LLOSS);
     launch_lloss_pass(l, v, b->st, sc->dev);
+    prof_mark(c, HPS_PROF_MOMENTS);
     launch_moments(l, v, b->st, sc->dev, sc->bins, s.kp, 1);
+    prof_mark(c, HPS_PROF_DEPOSIT);
     cudaError_t e = launch_deposit(l, v, b->st, sc->dev, sc->bins, s.kp);
+    prof_mark(c, HPS_PROF_FIELD);
     if (e == cudaSuccess) e = launch_field(l, b->st, sc->dev, sc->bins, sc->field, s.kp);
     if (e != cudaSuccess) return fail(c, HPS_ERR_CUDA, std::string("kick launch: ") + cudaGetErrorString(e));
     c->launches += 4;
   }
   CK(c, cudaEventRecord(c->ev1, c->stream));
   CK(c, cudaGetLastError());
+  prof_finish(c);
   if (out) {
     std::memset(out, 0, sizeof(*out));
     ScDev after;

@@ -112,6 +112,12 @@ int hps_ctx_comm_init(hps_ctx*, int rank, int nranks, const void* nccl_unique_id
 void* hps_host_alloc(size_t bytes);
 void hps_host_free(void*);
 uint64_t hps_ctx_launch_count(hps_ctx*);
+/* Per-kernel-class device timing of hps_simulate (CUDA events between consecutive launches on the
+ * context's stream).  While on, every hps_simulate call ends with a stream synchronisation.
+ * ms[k] / n[k]: accumulated milliseconds and launch count of class k since set_profile(1). */
+enum { HPS_PROF_SEGMENT = 0, HPS_PROF_LLOSS, HPS_PROF_MOMENTS, HPS_PROF_DEPOSIT, HPS_PROF_FIELD, HPS_PROF_NCLASS };
+int hps_ctx_set_profile(hps_ctx*, int on);
+int hps_ctx_get_profile(hps_ctx*, double* ms, uint64_t* n);
 
 /* ---- beam ---------------------------------------------------------------- */
 /* Replaces Beam::Beam(num, mass, charge, current) + AllocateBeam

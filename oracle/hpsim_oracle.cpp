@@ -1155,6 +1155,11 @@ int hps_ctx_synchronize(hps_ctx*) { return HPS_OK; }
 void* hps_host_alloc(size_t bytes) { return std::malloc(bytes); }
 void hps_host_free(void* p) { std::free(p); }
 uint64_t hps_ctx_launch_count(hps_ctx*) { return 0; }
+int hps_ctx_set_profile(hps_ctx*, int) { return HPS_OK; }
+int hps_ctx_get_profile(hps_ctx*, double* ms, uint64_t* n) {
+  for (int k = 0; k < HPS_PROF_NCLASS; ++k) { ms[k] = 0.0; n[k] = 0; }
+  return HPS_OK;
+}
 // oracle-only: OpenMP thread count (0 = runtime default)
 int hps_oracle_set_threads(hps_ctx* c, int n) {
   c->nthreads = n;

@@ -204,8 +204,15 @@ int main(int argc, char** argv) {
 
   std::string first = S(cfg, "first", ""), last = S(cfg, "last", "");
   int repeats = (int)D(cfg, "repeats", 1);
+  // optional untimed lead-in (e.g. the LEBT in front of the timed DTL range); the repeats then
+  // restart from the beam saved at its end
+  const bool lead_in = cfg.count("pre_first") != 0;
+  if (lead_in) {
+    engine.Simulate(S(cfg, "pre_first", ""), S(cfg, "pre_last", ""));
+    beam.SaveIntermediateBeam();
+  }
   for (int r = 0; r < repeats; ++r) {
-    if (r > 0) beam.RestoreInitialBeam();
+    if (r > 0) { if (lead_in) beam.RestoreIntermediateBeam(); else beam.RestoreInitialBeam(); }
     cudaDeviceSynchronize();
     auto t0 = std::chrono::steady_clock::now();
     engine.Simulate(first, last);  // prints "Whole simulation time: X [sec]" itself

@@ -1,0 +1,33 @@
+"""Generates tests/golden/*.npz from the reference's OWN CUDA code (oracle/_ref/ref_driver_dp, the
+unmodified reference sources rebuilt for sm_100 with -DDOUBLE_PRECISION).  Run on a GPU box:
+    gpurun -- 'python tests/make_golden.py && cp tests/golden/*.npz gpurun_out/'
+The fixtures pin the CPU oracle (tests/test_oracle_golden.py) and the CUDA product."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import harness as H  # noqa: E402
+
+CASES = {
+    # name: (n, first, last, sc)
+    "lebt_sc_4k": (4096, "TBDB02", "spch_comp_7", True),
+    "lebt_nosc_4k": (4096, "TBDB02", "spch_comp_7", False),
+    "dtl_sc_4k": (4096, "TBDB02", "04QM30", True),
+    "ccl_nosc_2k": (2048, "TBDB02", "06DT", False),
+}
+
+
+def main():
+    out_dir = os.path.join(H.ROOT, "gpurun_out", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (n, first, last, sc) in CASES.items():
+        st, log = H.run_reference(os.path.join(H.ROOT, "gpurun_out", "golden_work"), n, first, last, sc=sc, double=True)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), n=n, first=first, last=last, sc=sc,
+                            stats=st["stats"], **{k: st[k] for k in ("x", "xp", "y", "yp", "phi", "w", "loss", "lloss")})
+        print(name, "loss", int((st["loss"] != 0).sum()), "lloss", int((st["lloss"] != 0).sum()))
+
+
+if __name__ == "__main__":
+    main()
