@@ -75,7 +75,8 @@ class DBConnection:
         self.dbs = ["main"]
         self.db_addrs = [db_path]
         self.libs = []
-        self.conn = sqlite3.connect(":memory:")
+        self._keep = []
+        self.conn = sqlite3.connect(":memory:", uri=True)
         self.conn.enable_load_extension(True)
         src = sqlite3.connect(f"file:{db_path}?mode=ro", uri=True)
         src.backup(self.conn)
@@ -86,10 +87,14 @@ class DBConnection:
         self.libs.append(path)
 
     def attach_db(self, path: str, name: str) -> None:
-        self.conn.execute(f"attach ':memory:' as {name}")
+        # private shared-cache in-memory copy: Python's backup() can only fill a connection's "main"
+        uri = f"file:hpsim_{id(self)}_{name}?mode=memory&cache=shared"
+        mem = sqlite3.connect(uri, uri=True)
         src = sqlite3.connect(f"file:{path}?mode=ro", uri=True)
-        src.backup(self.conn, name=name)
+        src.backup(mem)
         src.close()
+        self._keep.append(mem)  # the copy lives as long as one connection to it is open
+        self.conn.execute(f"attach '{uri}' as {name}")
         self.dbs.append(name)
         self.db_addrs.append(path)
 

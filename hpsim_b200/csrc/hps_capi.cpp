@@ -39,9 +39,12 @@ struct hps_ctx {
   // scratch shared by every reducing kernel of this context
   double* partials = nullptr;
   u32* ticket = nullptr;
-  unsigned max_grid = 0;
+  unsigned max_grid = 0;    // cap for the light statistic sweeps
+  unsigned seg_grid_cap = 0;  // resident blocks of the segment kernel variant in use
+  int seg_variant = 0;
   // program upload buffers
   Op* d_ops = nullptr;
+  OpC* d_opc = nullptr;  // device-prepared constants, parallel to d_ops
   Op* h_ops = nullptr;  // pinned
   size_t ops_cap = 0;
   Comm comm;
@@ -80,6 +83,8 @@ struct hps_scheff {
   ScDev* dev = nullptr;
   double* bins = nullptr;
   double2* field = nullptr;
+  double2* field_part = nullptr;  // [nr+1][chunks][nz+1] partial fields of the split solve
+  u32* field_tickets = nullptr;   // [nr+1]
 };
 
 namespace {
@@ -112,6 +117,9 @@ LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
   LaunchCfg l;
   l.stream = c->stream;
   const unsigned pairs = (b->n + 1) / 2;
+  l.seg_variant = c->seg_variant;
+  const unsigned seg_items = c->seg_variant == 0 ? pairs : b->n;
+  l.grid_seg = std::max(1u, std::min((seg_items + HPS_BLOCK - 1) / HPS_BLOCK, c->seg_grid_cap));
   l.grid_pairs = std::max(1u, std::min((pairs + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
   l.grid_single = std::max(1u, std::min((b->n + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
   l.grid_deposit = std::max(1u, std::min((b->n + 511) / 512, (unsigned)c->num_sms * 2));
@@ -212,7 +220,7 @@ void UpdateStatForSpaceCharge(hps_beam* b) {
   KickParams kp;
   std::memset(&kp, 0, sizeof(kp));
   kp.n_global = b->h.n_global; kp.mass = b->h.mass;
-  launch_segment(l, v, c->d_ops, 0, FIN_KICK, 0, c->compat, b->st, nullptr, nullptr, kp);
+  launch_segment(l, v, c->d_ops, c->d_opc, 0, FIN_KICK, 0, c->compat, b->st, nullptr, nullptr, kp);
   launch_lloss_pass(l, v, b->st, nullptr);
   launch_moments(l, v, b->st, nullptr, nullptr, kp, 0);
   c->launches += 3;
@@ -289,13 +297,16 @@ hps_ctx* hps_ctx_create(int device) {
   c->num_sms = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
-  int occ = ok ? segment_occupancy() : 0;
+  if (const char* v = getenv("HPSIM_SEG_VARIANT")) c->seg_variant = atoi(v);
+  int occ = ok ? segment_occupancy(c->seg_variant) : 0;
   if (occ < 1) occ = 1;
-  c->max_grid = (unsigned)c->num_sms * (unsigned)occ;
+  c->seg_grid_cap = (unsigned)c->num_sms * (unsigned)occ;
+  c->max_grid = (unsigned)c->num_sms * 6u;
   ok = ok && cudaMalloc(&c->partials, (size_t)c->max_grid * HPS_NSLOT * sizeof(double)) == cudaSuccess &&
        cudaMalloc(&c->ticket, 256) == cudaSuccess && cudaMemset(c->ticket, 0, 256) == cudaSuccess;
   c->ops_cap = 4096;
   ok = ok && cudaMalloc(&c->d_ops, c->ops_cap * sizeof(Op)) == cudaSuccess &&
+       cudaMalloc(&c->d_opc, c->ops_cap * sizeof(OpC)) == cudaSuccess &&
        cudaHostAlloc(&c->h_ops, c->ops_cap * sizeof(Op), cudaHostAllocDefault) == cudaSuccess;
   if (!ok) {
     fail(nullptr, HPS_ERR_CUDA, std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -308,7 +319,7 @@ void hps_ctx_destroy(hps_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   comm_destroy(c->comm);
-  cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_ops); cudaFreeHost(c->h_ops);
+  cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_ops); cudaFree(c->d_opc); cudaFreeHost(c->h_ops);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
   delete c;
@@ -648,11 +659,17 @@ int hps_lattice_update_elem(hps_lattice* l, uint32_t i, const hps_elem* in) {
 // ---- SCHEFF -----------------------------------------------------------------------------------------
 static int scheff_alloc(hps_scheff* s) {
   hps_ctx* c = s->ctx;
-  cudaFree(s->bins); cudaFree(s->field);
-  s->bins = nullptr; s->field = nullptr;
+  cudaFree(s->bins); cudaFree(s->field); cudaFree(s->field_part); cudaFree(s->field_tickets);
+  s->bins = nullptr; s->field = nullptr; s->field_part = nullptr; s->field_tickets = nullptr;
   const size_t nb = (size_t)s->h.nr * s->h.nz, nf = (size_t)(s->h.nr + 1) * (s->h.nz + 1);
+  KickParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.nr = s->h.nr; kp.nz = s->h.nz;
   CK(c, cudaMalloc(&s->bins, nb * sizeof(double)));
   CK(c, cudaMalloc(&s->field, nf * sizeof(double2)));
+  CK(c, cudaMalloc(&s->field_part, nf * field_chunks(kp) * sizeof(double2)));
+  CK(c, cudaMalloc(&s->field_tickets, (s->h.nr + 1) * sizeof(u32)));
+  CK(c, cudaMemsetAsync(s->field_tickets, 0, (s->h.nr + 1) * sizeof(u32), c->stream));
   CK(c, cudaMemsetAsync(s->bins, 0, nb * sizeof(double), c->stream));
   CK(c, cudaMemsetAsync(s->field, 0, nf * sizeof(double2), c->stream));
   return HPS_OK;
@@ -662,8 +679,8 @@ static int scheff_check_mesh(hps_ctx* c, u32 nr, u32 nz) {
   std::memset(&kp, 0, sizeof(kp));
   kp.nr = nr; kp.nz = nz;
   const int th = field_threads(kp);
-  if (nr == 0 || nz == 0 || th == 0 || field_smem(kp, th) > 220 * 1024 || deposit_smem(kp) > 200 * 1024)
-    return fail(c, HPS_ERR_ARG, "SCHEFF mesh too large for the shared-memory field solve (need nz <= 1024 and 24*nr*nz + 16 KB <= 220 KB)");
+  if (nr == 0 || nz == 0 || th == 0 || field_smem(kp, th) > 200 * 1024 || deposit_smem(kp) > 200 * 1024)
+    return fail(c, HPS_ERR_ARG, "SCHEFF mesh too large for the shared-memory deposit / field solve (need nz <= 1024 and 8*nr*nz <= 200 KB)");
   return HPS_OK;
 }
 hps_scheff* hps_scheff_create(hps_ctx* c, uint32_t nr, uint32_t nz, int adj_bunch) {
@@ -678,7 +695,7 @@ hps_scheff* hps_scheff_create(hps_ctx* c, uint32_t nr, uint32_t nz, int adj_bunc
             cudaMemsetAsync(s->dev, 0, sizeof(ScDev), c->stream) == cudaSuccess && scheff_alloc(s) == HPS_OK;
   if (!ok) {
     if (c->err.empty()) fail(c, HPS_ERR_CUDA, "SCHEFF allocation failed");
-    cudaFree(s->dev); cudaFree(s->bins); cudaFree(s->field);
+    cudaFree(s->dev); cudaFree(s->bins); cudaFree(s->field); cudaFree(s->field_part); cudaFree(s->field_tickets);
     delete s;
     return nullptr;
   }
@@ -688,7 +705,7 @@ void hps_scheff_destroy(hps_scheff* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
-  cudaFree(s->dev); cudaFree(s->bins); cudaFree(s->field);
+  cudaFree(s->dev); cudaFree(s->bins); cudaFree(s->field); cudaFree(s->field_part); cudaFree(s->field_tickets);
   delete s;
 }
 int hps_scheff_set(hps_scheff* s, int p, double v) {
@@ -766,10 +783,11 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
   const size_t nops = plan.ops.size();
   if (nops > c->ops_cap) {
     CK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_ops); cudaFreeHost(c->h_ops);
-    c->d_ops = nullptr; c->h_ops = nullptr;
+    cudaFree(c->d_ops); cudaFree(c->d_opc); cudaFreeHost(c->h_ops);
+    c->d_ops = nullptr; c->d_opc = nullptr; c->h_ops = nullptr;
     c->ops_cap = nops * 2;
     CK(c, cudaMalloc(&c->d_ops, c->ops_cap * sizeof(Op)));
+    CK(c, cudaMalloc(&c->d_opc, c->ops_cap * sizeof(OpC)));
     CK(c, cudaHostAlloc(&c->h_ops, c->ops_cap * sizeof(Op), cudaHostAllocDefault));
   }
   CK(c, cudaStreamSynchronize(c->stream));  // h_ops may still feed the previous call's copy
@@ -785,13 +803,15 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
   const LaunchCfg l = cfg(c, b);
   const BeamView v = view(b);
   const uint64_t launches0 = c->launches;
+  launch_prepare_ops(l, c->d_ops, c->d_opc, (int)nops, b->h.mass, b->h.charge);
+  c->launches++;
   uint64_t sweeps = 0, extra = 0;
   const bool sharded = c->comm.nranks > 1;
   CK(c, cudaEventRecord(c->ev0, c->stream));
   for (const Segment& s : plan.segs) {
     const int dirty = dirty_mask(plan.ops.data() + s.op_begin, s.op_count);
     prof_mark(c, HPS_PROF_SEGMENT);
-    launch_segment(l, v, c->d_ops + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
+    launch_segment(l, v, c->d_ops + s.op_begin, c->d_opc + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
                    sc ? sc->field : nullptr, s.kp);
     c->launches++;
     sweeps++;
@@ -804,7 +824,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     prof_mark(c, HPS_PROF_DEPOSIT);
     cudaError_t e = launch_deposit(l, v, b->st, sc->dev, sc->bins, s.kp);
     prof_mark(c, HPS_PROF_FIELD);
-    if (e == cudaSuccess) e = launch_field(l, b->st, sc->dev, sc->bins, sc->field, s.kp);
+    if (e == cudaSuccess) e = launch_field(l, b->st, sc->dev, sc->bins, sc->field, sc->field_part, sc->field_tickets, s.kp);
     if (e != cudaSuccess) return fail(c, HPS_ERR_CUDA, std::string("kick launch: ") + cudaGetErrorString(e));
     c->launches += 4;
   }

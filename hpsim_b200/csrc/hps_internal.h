@@ -47,6 +47,13 @@ struct Op {
   double p[HPS_OP_NPARAM];
 };
 
+// Particle-independent sub-expressions of an op, evaluated ONCE on the device (k_prepare_ops) with
+// the same expression order the reference evaluates per particle, so the hoisting is bit-exact.
+#define HPS_OPC_N 32
+struct OpC {
+  double c[HPS_OPC_N];
+};
+
 // what the segment kernel's last block does with its partial sums
 enum FinMode {
   FIN_NONE = 0,
@@ -100,6 +107,7 @@ struct BeamView {
 
 #define HPS_BLOCK 256
 #define HPS_NSLOT 16          // partial-sum slots per block
+#define HPS_FIELD_RS 4         // source rings per block of the field solve
 #define HPS_MAX_SEG_OPS 24    // ops staged in shared memory per segment
 
 #endif

@@ -43,22 +43,23 @@ __device__ void finalize_segment(int fin, const double* t, DevStats* st, u32 n_g
 }
 
 // one op applied to one register-resident particle
-__device__ __forceinline__ void apply_op(Pt& pt, const u32 ll, const u32 gidx, const Op& op, const KickCtx& kc,
+__device__ __forceinline__ void apply_op(Pt& pt, const u32 ll, const u32 gidx, const Op& op, const OpC& opc, const KickCtx& kc,
                                          const double* cxy, const double2* __restrict__ field, const BeamView& b,
                                          int compat, double& phi_fc, bool& live_fc) {
   const double* q = op.p;
+  const double* c = opc.c;
   const double mass = b.mass, charge = b.charge;
   switch (op.type) {
-    case OP_DRIFT: if (pt.loss == 0) op_drift(pt, q, op.elem, mass); break;
-    case OP_QUAD_HALF: if (pt.loss == 0) op_quad_half(pt, q, op.elem, mass, charge); break;
-    case OP_GAP_FIRST: if (pt.loss == 0) op_gap_first(pt, q, op.flag != 0, mass); break;
-    case OP_GAP_SECOND: if (pt.loss == 0) op_gap_second(pt, q, op.flag != 0, mass, charge); break;
+    case OP_DRIFT: if (pt.loss == 0) op_drift(pt, q, c, op.elem, mass); break;
+    case OP_QUAD_HALF: if (pt.loss == 0) op_quad_half(pt, q, c, op.elem, mass); break;
+    case OP_GAP_FIRST: if (pt.loss == 0) op_gap_first(pt, q, c, op.flag != 0, mass); break;
+    case OP_GAP_SECOND: if (pt.loss == 0) op_gap_second(pt, q, c, op.flag != 0, mass); break;
     case OP_DIPOLE_FIRST: if (pt.loss == 0) op_dipole(pt, q, false, mass); break;
     case OP_DIPOLE_SECOND: if (pt.loss == 0) op_dipole(pt, q, true, mass); break;
     case OP_BUNCHER: if (pt.loss == 0) op_buncher(pt, q, op.elem, mass, charge); break;
     case OP_ROTATION:  // simulation_kernel.cu:511-529
       if (pt.loss == 0) {
-        const double cosa = cos(q[0]), sina = sin(q[0]);
+        const double cosa = c[R_COS], sina = c[R_SIN];
         const double x = pt.x, y = pt.y, xp = pt.xp, yp = pt.yp;
         pt.x = x * cosa + y * sina; pt.y = y * cosa - x * sina;
         pt.xp = xp * cosa + yp * sina; pt.yp = yp * cosa - xp * sina;
@@ -89,7 +90,7 @@ __device__ __forceinline__ void apply_op(Pt& pt, const u32 ll, const u32 gidx, c
       // H2: the reference launches the kick <<<grid, blck/4>>> with `while(indx > 0 && ...)`, so
       // global thread 0 exits at once and particles k*NextPow2(N)/4 never see a kick.
       if (!(gidx == 0 || (compat && (gidx % b.np2_quarter) == 0)))
-        op_sc_kick(pt, ll, q, kc, field, mass, b.n_global);
+        op_sc_kick(pt, ll, kc, field, mass);
       break;
     case OP_FREQ_CHANGE:  // beam_kernel.cu:1531-1538: every particle, lost or not
       pt.phi *= q[0];
@@ -110,10 +111,16 @@ __device__ __forceinline__ void seg_accumulate(double (&acc)[SEG_NS], const Pt& 
   if (live_fc) acc[7] += phi_fc;
 }
 
-__global__ void __launch_bounds__(HPS_BLOCK)
-k_segment(BeamView b, const Op* __restrict__ ops, int nops, int fin_mode, int dirty, int compat, DevStats* st,
-          const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials, u32* ticket) {
+// PPT = particles per thread.  PPT == 2 moves two adjacent particles with one 128-bit access per
+// array; PPT == 1 halves the register footprint and doubles the resident warps (the maps are chains of
+// dependent fp64 operations, so the sweep is latency-bound before it is bandwidth-bound).
+template <int PPT, int MINB>
+__global__ void __launch_bounds__(HPS_BLOCK, MINB)
+k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
+          DevStats* st, const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials,
+          u32* ticket) {
   __shared__ Op s_ops[HPS_MAX_SEG_OPS];
+  __shared__ OpC s_opc[HPS_MAX_SEG_OPS];
   __shared__ KickCtx s_k;
   __shared__ double s_cxy[2];
   __shared__ double s_total[SEG_NS];
@@ -124,6 +131,10 @@ k_segment(BeamView b, const Op* __restrict__ ops, int nops, int fin_mode, int di
     const double* src = reinterpret_cast<const double*>(ops);
     double* dst = reinterpret_cast<double*>(s_ops);
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    const int nc = nops * HPS_OPC_N;
+    const double* csrc = reinterpret_cast<const double*>(opcs);
+    double* cdst = reinterpret_cast<double*>(s_opc);
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) cdst[i] = csrc[i];
   }
   if (threadIdx.x == 0) {
     s_cxy[0] = st->v[HPS_STAT_X_AVG];
@@ -139,6 +150,9 @@ k_segment(BeamView b, const Op* __restrict__ ops, int nops, int fin_mode, int di
       s_k.adj_bunch = sc->adj_bunch; s_k.num_on_mesh = sc->num_on_mesh;
     }
     s_k.nr = kp.nr; s_k.nz = kp.nz;
+    // a segment holds at most one kick (its first op); its block-uniform factors are derived here
+    for (int k = 0; k < nops; ++k)
+      if (ops[k].type == OP_SC_KICK) { kick_prepare(s_k, ops[k].p, b.mass, b.n_global); break; }
   }
   __syncthreads();
 
@@ -147,48 +161,77 @@ k_segment(BeamView b, const Op* __restrict__ ops, int nops, int fin_mode, int di
   for (int s = 0; s < SEG_NS; ++s) acc[s] = 0.0;
   acc[2] = -DBL_MAX;
 
-  const u32 npairs = (b.n + 1) >> 1;
-  for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
-    const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
-    const double2 XP = reinterpret_cast<const double2*>(b.xp)[i2];
-    const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
-    const double2 YP = reinterpret_cast<const double2*>(b.yp)[i2];
-    const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
-    const double2 W = reinterpret_cast<const double2*>(b.w)[i2];
-    const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
-    const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
-    Pt p0 = {X.x, XP.x, Y.x, YP.x, PH.x, W.x, L.x};
-    Pt p1 = {X.y, XP.y, Y.y, YP.y, PH.y, W.y, L.y};
-    const bool valid1 = 2 * i2 + 1 < b.n;
-    const u32 g0 = b.offset + 2 * i2, g1 = g0 + 1;
-    double fc0 = 0.0, fc1 = 0.0;
-    bool lf0 = false, lf1 = false;
-
-    for (int k = 0; k < nops; ++k) {
-      const Op& op = s_ops[k];
-      apply_op(p0, LL.x, g0, op, s_k, s_cxy, field, b, compat, fc0, lf0);
-      if (valid1) apply_op(p1, LL.y, g1, op, s_k, s_cxy, field, b, compat, fc1, lf1);
+  if (PPT == 2) {
+    const u32 npairs = (b.n + 1) >> 1;
+    for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
+      const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
+      const double2 XP = reinterpret_cast<const double2*>(b.xp)[i2];
+      const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
+      const double2 YP = reinterpret_cast<const double2*>(b.yp)[i2];
+      const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
+      const double2 W = reinterpret_cast<const double2*>(b.w)[i2];
+      const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
+      const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
+      Pt p0 = {X.x, XP.x, Y.x, YP.x, PH.x, W.x, L.x};
+      Pt p1 = {X.y, XP.y, Y.y, YP.y, PH.y, W.y, L.y};
+      const bool valid1 = 2 * i2 + 1 < b.n;
+      const u32 g0 = b.offset + 2 * i2, g1 = g0 + 1;
+      double fc0 = 0.0, fc1 = 0.0;
+      bool lf0 = false, lf1 = false;
+      for (int k = 0; k < nops; ++k) {
+        const Op& op = s_ops[k];
+        const OpC& oc = s_opc[k];
+        apply_op(p0, LL.x, g0, op, oc, s_k, s_cxy, field, b, compat, fc0, lf0);
+        if (valid1) apply_op(p1, LL.y, g1, op, oc, s_k, s_cxy, field, b, compat, fc1, lf1);
+      }
+      if (nops > 0) {
+        if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p0.x, p1.x);
+        if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p0.xp, p1.xp);
+        if (dirty & 4) reinterpret_cast<double2*>(b.y)[i2] = make_double2(p0.y, p1.y);
+        if (dirty & 8) reinterpret_cast<double2*>(b.yp)[i2] = make_double2(p0.yp, p1.yp);
+        if (dirty & 16) reinterpret_cast<double2*>(b.phi)[i2] = make_double2(p0.phi, p1.phi);
+        if (dirty & 32) reinterpret_cast<double2*>(b.w)[i2] = make_double2(p0.w, p1.w);
+        if ((dirty & 64) && (p0.loss != L.x || p1.loss != L.y))
+          reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p0.loss, p1.loss);
+      }
+      if (fin_mode != FIN_NONE) {
+        seg_accumulate(acc, p0, LL.x, fc0, lf0);
+        if (valid1) seg_accumulate(acc, p1, LL.y, fc1, lf1);
+      }
     }
-
-    if (nops > 0) {
-      if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p0.x, p1.x);
-      if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p0.xp, p1.xp);
-      if (dirty & 4) reinterpret_cast<double2*>(b.y)[i2] = make_double2(p0.y, p1.y);
-      if (dirty & 8) reinterpret_cast<double2*>(b.yp)[i2] = make_double2(p0.yp, p1.yp);
-      if (dirty & 16) reinterpret_cast<double2*>(b.phi)[i2] = make_double2(p0.phi, p1.phi);
-      if (dirty & 32) reinterpret_cast<double2*>(b.w)[i2] = make_double2(p0.w, p1.w);
-      if ((dirty & 64) && (p0.loss != L.x || p1.loss != L.y))
-        reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p0.loss, p1.loss);
-    }
-    if (fin_mode != FIN_NONE) {
-      seg_accumulate(acc, p0, LL.x, fc0, lf0);
-      if (valid1) seg_accumulate(acc, p1, LL.y, fc1, lf1);
+  } else {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x) {
+      const u32 l0 = b.loss[i], ll = b.lloss[i];
+      Pt p = {b.x[i], b.xp[i], b.y[i], b.yp[i], b.phi[i], b.w[i], l0};
+      const u32 g = b.offset + i;
+      double fc = 0.0;
+      bool lf = false;
+      for (int k = 0; k < nops; ++k) apply_op(p, ll, g, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
+      if (nops > 0) {
+        if (dirty & 1) b.x[i] = p.x;
+        if (dirty & 2) b.xp[i] = p.xp;
+        if (dirty & 4) b.y[i] = p.y;
+        if (dirty & 8) b.yp[i] = p.yp;
+        if (dirty & 16) b.phi[i] = p.phi;
+        if (dirty & 32) b.w[i] = p.w;
+        if ((dirty & 64) && p.loss != l0) b.loss[i] = p.loss;
+      }
+      if (fin_mode != FIN_NONE) seg_accumulate(acc, p, ll, fc, lf);
     }
   }
   if (fin_mode == FIN_NONE) return;
   if (grid_reduce<SEG_NS>(acc, 1u << 2, partials, ticket, s_total, s_scratch)) {
     if (threadIdx.x == 0) finalize_segment(fin_mode, s_total, st, b.n_global);
   }
+}
+template __global__ void k_segment<2, 2>(BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*);
+template __global__ void k_segment<1, 3>(BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*);
+template __global__ void k_segment<1, 4>(BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*);
+
+// one thread per op record of the uploaded program (once per simulate() call)
+__global__ void k_prepare_ops(const Op* __restrict__ ops, OpC* opcs, int nops, double mass, double charge) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nops) prepare_op(ops[i], opcs[i], mass, charge);
 }
 
 // ================================================================================================
@@ -464,19 +507,30 @@ __device__ __forceinline__ void ellip_ke(double g, double& ee, double& ek) {
   ek = 1.38629436 - 0.5 * h + g * (0.1119697 - 0.1213486 * h + g * (0.07253230 - 0.02887472 * h));
 }
 
+// Work split: block (rp, ch) owns receiving radius rp and HPS_FIELD_RS consecutive source rings; it
+// builds the [HPS_FIELD_RS][nz] Green slice in shared memory, accumulates the partial field of its rings
+// at every node (zp = 0..nz, rp) and stores it; the last block of each rp (ticket) adds the chunk
+// partials in a fixed order, so the result is deterministic.  (nr+1) x ceil(nr/RS) blocks fill the GPU;
+// the previous one-block-per-rp version ran on 33 SMs only.
 __global__ void __launch_bounds__(1024)
-k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, KickParams kp) {
+k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, double2* part, u32* tickets,
+        KickParams kp) {
   extern __shared__ double s_mem[];
   if (!sc->remesh) return;
-  const u32 nr = kp.nr, nz = kp.nz, nb = nr * nz;
-  double* s_bins = s_mem;                                      // [nb]
-  double2* s_green = reinterpret_cast<double2*>(s_mem + nb);   // [nr][nz]
-  double2* s_part = s_green + nb;                              // [blockDim.x]
-  const u32 irp = blockIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
+  const u32 nr = kp.nr, nz = kp.nz;
+  const u32 irp = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
+  const u32 rs0 = ch * HPS_FIELD_RS;
+  const u32 nrs = min((u32)HPS_FIELD_RS, nr - rs0);
+  double* s_b = s_mem;                                                       // [RS][nz]
+  double2* s_g = reinterpret_cast<double2*>(s_mem + HPS_FIELD_RS * nz);      // [RS][nz]
+  double2* s_red = s_g + HPS_FIELD_RS * nz;                                  // [blockDim.x]
+  if (irp == 0 && ch == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
     st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
 
-  for (u32 k = threadIdx.x; k < nb; k += blockDim.x) s_bins[k] = bins[k];
+  for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
+    const u32 k = e / nz, zs = e % nz;
+    s_b[k * nz + zs] = bins[zs * nr + rs0 + k];
+  }
   {
     const double beta = sc->beta;
     const double gm = rsqrt(1.0 - beta * beta);
@@ -487,8 +541,8 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
     const double c1 = 5721.67 * (kp.current_frac / kp.mass) / (kp.freq * 1e6 * (double)kp.n_global);
     const double rp = irp * dr;
     const int adj = (int)sc->adj_bunch;
-    for (u32 e = threadIdx.x; e < nb; e += blockDim.x) {
-      const u32 jz = e % nz, k = e / nz;
+    for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
+      const u32 jz = e % nz, k = rs0 + e / nz;
       const double rs = sqrt(0.5 * (k * k + (k + 1) * (k + 1))) * dr;
       const double zs = 0.5 * dzg, zp = (jz + 1) * dzg;
       const double d = zp - zs;
@@ -516,65 +570,76 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
           xi = -xi;
         }
       }
-      s_green[e] = make_double2(c1 * er1, c1 * ez1);
+      s_g[e] = make_double2(c1 * er1, c1 * ez1);
     }
   }
   __syncthreads();
 
-  // nodes (zp = 0..nz-1, rp): thread -> (zp, chunk of source bins); chunks are summed in a fixed order
-  const u32 nchunk = blockDim.x / nz;
-  const u32 per = (nb + nchunk - 1) / nchunk;
-  {
-    const u32 zp = threadIdx.x % nz, ch = threadIdx.x / nz;
+  const size_t nodes_per_rp = nz + 1;
+  double2* my_part = part + ((size_t)irp * nch + ch) * nodes_per_rp;
+  // nodes (zp = 0..nz-1, rp): one thread per node, sources in (ring, zs) order
+  if (threadIdx.x < nz) {
+    const u32 zp = threadIdx.x;
     double tx = 0.0, tz = 0.0;
-    if (ch < nchunk) {
-      const u32 b0 = ch * per, b1 = min(nb, b0 + per);
-      for (u32 bi = b0; bi < b1; ++bi) {
-        const double v = s_bins[bi];
+    for (u32 k = 0; k < nrs; ++k) {
+      const double* bk = s_b + k * nz;
+      const double2* gk = s_g + k * nz;
+      for (u32 zs = 0; zs < nz; ++zs) {
+        const double v = bk[zs];
         if (v == 0.0) continue;
-        const u32 rs = bi % nr, zs = bi / nr;
         u32 dz;
         double sign = 1.0;
         if (zs >= zp) { dz = zs - zp; sign = -1.0; } else dz = zp - zs - 1;
-        const double2 g = s_green[rs * nz + dz];
+        const double2 g = gk[dz];
         tx += v * g.x;
         tz += sign * v * g.y;
       }
     }
-    s_part[threadIdx.x] = make_double2(tx, tz);
+    my_part[zp] = make_double2(tx, tz);
   }
-  __syncthreads();
-  if (threadIdx.x < nz) {
-    double tx = 0.0, tz = 0.0;
-    for (u32 ch = 0; ch < nchunk; ++ch) {
-      const double2 v = s_part[ch * nz + threadIdx.x];
-      tx += v.x; tz += v.y;
-    }
-    field[threadIdx.x * (nr + 1) + irp] = make_double2(tx, tz);
-  }
-  __syncthreads();
   // node (zp = nz, rp): every source bin lies upstream (dz = nz - zs - 1)
   {
     double tx = 0.0, tz = 0.0;
-    for (u32 bi = threadIdx.x; bi < nb; bi += blockDim.x) {
-      const double v = s_bins[bi];
+    for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
+      const double v = s_b[e];
       if (v == 0.0) continue;
-      const u32 rs = bi % nr, zs = bi / nr;
-      const double2 g = s_green[rs * nz + (nz - zs - 1)];
+      const u32 k = e / nz, zs = e % nz;
+      const double2 g = s_g[k * nz + (nz - zs - 1)];
       tx += v * g.x;
       tz += v * g.y;
     }
-    s_part[threadIdx.x] = make_double2(tx, tz);
+    s_red[threadIdx.x] = make_double2(tx, tz);
   }
   __syncthreads();
   for (u32 s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if (threadIdx.x < s && threadIdx.x + s < blockDim.x) {
-      s_part[threadIdx.x].x += s_part[threadIdx.x + s].x;
-      s_part[threadIdx.x].y += s_part[threadIdx.x + s].y;
+    if (threadIdx.x < s) {
+      s_red[threadIdx.x].x += s_red[threadIdx.x + s].x;
+      s_red[threadIdx.x].y += s_red[threadIdx.x + s].y;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) field[nz * (nr + 1) + irp] = s_part[0];
+  if (threadIdx.x == 0) my_part[nz] = s_red[0];
+
+  // last block of this rp folds the chunk partials (fixed order)
+  __shared__ u32 s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const u32 t = atomicAdd(&tickets[irp], 1u);
+    s_last = (t == nch - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (u32 node = threadIdx.x; node <= nz; node += blockDim.x) {
+    double tx = 0.0, tz = 0.0;
+    for (u32 c2 = 0; c2 < nch; ++c2) {
+      const double2 v = __ldcg(&part[((size_t)irp * nch + c2) * nodes_per_rp + node]);
+      tx += v.x; tz += v.y;
+    }
+    field[node * (nr + 1) + irp] = make_double2(tx, tz);
+  }
+  if (threadIdx.x == 0) tickets[irp] = 0u;
 }
 
 // ================================================================================================
@@ -714,10 +779,21 @@ __global__ void k_rel_phi_out(BeamView b, const DevStats* st, double* out) {
 // ================================================================================================
 static int g_field_smem_set = 0, g_deposit_smem_set = 0;
 
-void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* ops, int nops, int fin_mode, int dirty, int compat,
-                    DevStats* st, const ScDev* sc, const double2* field, const KickParams& kp) {
-  k_segment<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, ops, nops, fin_mode, dirty, compat, st, sc, field, kp,
-                                                      c.partials, c.ticket);
+void launch_prepare_ops(const LaunchCfg& c, const Op* ops, OpC* opcs, int nops, double mass, double charge) {
+  if (nops > 0) k_prepare_ops<<<(nops + 63) / 64, 64, 0, c.stream>>>(ops, opcs, nops, mass, charge);
+}
+void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* ops, const OpC* opcs, int nops, int fin_mode, int dirty,
+                    int compat, DevStats* st, const ScDev* sc, const double2* field, const KickParams& kp) {
+  switch (c.seg_variant) {
+    case 1:
+      k_segment<1, 3><<<c.grid_seg, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+      break;
+    case 2:
+      k_segment<1, 4><<<c.grid_seg, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+      break;
+    default:
+      k_segment<2, 2><<<c.grid_seg, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+  }
 }
 void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
   k_lloss_pass<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, c.partials, c.ticket);
@@ -728,12 +804,15 @@ void launch_moments(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* 
 }
 size_t deposit_smem(const KickParams& kp) { return (size_t)kp.nr * kp.nz * sizeof(double); }
 size_t field_smem(const KickParams& kp, int threads) {
-  return (size_t)kp.nr * kp.nz * (sizeof(double) + sizeof(double2)) + (size_t)threads * sizeof(double2);
+  return (size_t)HPS_FIELD_RS * kp.nz * (sizeof(double) + sizeof(double2)) + (size_t)threads * sizeof(double2);
 }
 int field_threads(const KickParams& kp) {
   if (kp.nz == 0 || kp.nz > 1024) return 0;
-  return (int)(kp.nz * (1024 / kp.nz));
+  int t = 32;
+  while (t < (int)kp.nz) t <<= 1;  // power of two >= nz (the tree reduction needs it)
+  return t;
 }
+unsigned field_chunks(const KickParams& kp) { return (kp.nr + HPS_FIELD_RS - 1) / HPS_FIELD_RS; }
 cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
                            const KickParams& kp) {
   const size_t smem = deposit_smem(kp);
@@ -745,16 +824,16 @@ cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, 
   k_deposit<<<c.grid_deposit, 512, smem, c.stream>>>(b, st, sc, bins, kp);
   return cudaSuccess;
 }
-cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const double* bins, double2* field,
-                         const KickParams& kp) {
+cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const double* bins, double2* field, double2* part,
+                         u32* tickets, const KickParams& kp) {
   const int threads = field_threads(kp);
   const size_t smem = field_smem(kp, threads);
-  if (!g_field_smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (smem > 48 * 1024 && !g_field_smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     g_field_smem_set = 1;
   }
-  k_field<<<kp.nr + 1, threads, smem, c.stream>>>(st, sc, bins, field, kp);
+  k_field<<<dim3(kp.nr + 1, field_chunks(kp)), threads, smem, c.stream>>>(st, sc, bins, field, part, tickets, kp);
   return cudaSuccess;
 }
 void launch_stat(const LaunchCfg& c, const BeamView& b, DevStats* st, const StatReq& rq) {
@@ -773,9 +852,11 @@ void launch_cut(const LaunchCfg& c, const double* a, u32* loss, double lo, doubl
 void launch_rel_phi_out(const LaunchCfg& c, const BeamView& b, const DevStats* st, double* out) {
   k_rel_phi_out<<<(b.n + 255) / 256, 256, 0, c.stream>>>(b, st, out);
 }
-int segment_occupancy() {
+int segment_occupancy(int variant) {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment, HPS_BLOCK, 0);
+  if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3>, HPS_BLOCK, 0);
+  else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 4>, HPS_BLOCK, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<2, 2>, HPS_BLOCK, 0);
   return nb;
 }
 

@@ -94,24 +94,144 @@ __device__ __forceinline__ double beta_of(double w, double mass) {
   return sqrt(g1 * (g1 + 2.0)) / (g1 + 1.0);
 }
 
+// ---- hoisted constants -------------------------------------------------------------------------
+// slots of OpC::c per op type
+enum { D_APER2 = 0, D_TWOPI_HL };
+enum { Q_APER2 = 0, Q_QG, Q_ABSQG, Q_LEN4, Q_TWOPI_LEN_HALF };
+enum { R_COS = 0, R_SIN };
+enum { GC_CELL_LEN = 0, GC_DD, GC_WAVE_LEN, GC_BETA_IN, GC_DPS, GC_PI_CLBL_DPS, GC_D_CELL_LEN, GC_PI_DCL, GC_TWOPI_HALF_QLEN,
+       GC_BETAG_CCL, GC_TWOPI_DD,
+       // second half only
+       GC_INV_MASS, GC_BETAG, GC_GMG, GC_INV_GMG2, GC_AQ, GC_BETA_OUT, GC_EFL, GC_CONCOMM, GC_CONCOMM1, GC_CON1, GC_CON2NEX,
+       GC_INV_GMGCL, GC_INV_FKIS, GC_FKR, GC_SINPS, GC_COSPS, GC_X5, GC_TTF_DEN, GC_PH_CONST, GC_TWOPI_DG, GC_AQ_EFL };
+
+// indices into Op::p for the RF gap (rfgap_parameter.h:4-32)
+enum { G_LEN = 0, G_FREQ, G_CLBL, G_AMP, G_PHREF, G_PHSHIFT, G_EOUT, G_BETAC, G_DG, G_T, G_TP, G_SP,
+       G_FBC, G_FBMIN, G_T0, G_T1, G_T2, G_T3, G_T4, G_T5, G_S1, G_S2, G_S3, G_S4, G_S5,
+       G_DESIGN_W = 25, G_PHI_IN = 26, G_QLEN1 = 27, G_QLEN2 = 28, G_CELLNUM = 29, G_WAVELEN = 30 };
+
+// Evaluates the particle-independent sub-expressions of one op.  Every value is produced by the very
+// expression (same operand order) the reference evaluates inside its per-particle loop.
+__device__ inline void prepare_op(const Op& op, OpC& o, double mass, double charge) {
+  const double* q = op.p;
+  double* c = o.c;
+  switch (op.type) {
+    case OP_DRIFT:
+      c[D_APER2] = q[1] * q[1];
+      c[D_TWOPI_HL] = K_TWOPI * q[0];
+      break;
+    case OP_QUAD_HALF: {
+      double aper2 = q[1]; aper2 *= aper2;
+      const double qg = q[2] * charge;
+      c[Q_APER2] = aper2;
+      c[Q_QG] = qg;
+      c[Q_ABSQG] = qg > 0.0 ? qg : -qg;
+      c[Q_LEN4] = q[0] * 0.25;
+      c[Q_TWOPI_LEN_HALF] = K_TWOPI * q[0] * 0.5;
+      break;
+    }
+    case OP_ROTATION:
+      c[R_COS] = cos(q[0]);
+      c[R_SIN] = sin(q[0]);
+      break;
+    case OP_GAP_FIRST:
+    case OP_GAP_SECOND: {
+      const bool ccl = op.flag != 0, second = op.type == OP_GAP_SECOND;
+      const double qlen1 = q[G_QLEN1], qlen2 = q[G_QLEN2];
+      const double cell_len = q[G_LEN] + qlen1 * 0.5 + qlen2 * 0.5;
+      const double wave_len = K_CLIGHT / q[G_FREQ];
+      c[GC_CELL_LEN] = cell_len;
+      c[GC_WAVE_LEN] = wave_len;
+      const double dd = second ? 0.5 * cell_len + q[G_DG] - qlen2 * 0.5 : 0.5 * cell_len - q[G_DG] - 0.5 * qlen1;
+      c[GC_DD] = dd;
+      c[GC_TWOPI_DD] = K_TWOPI * dd;
+      const double d_cell_len = cell_len - q[G_BETAC] * wave_len;
+      c[GC_D_CELL_LEN] = d_cell_len;
+      c[GC_PI_DCL] = K_PI * d_cell_len;
+      c[GC_TWOPI_HALF_QLEN] = K_TWOPI * 0.5 * (second ? qlen2 : qlen1);
+      if (!second) {
+        double gam = q[G_DESIGN_W] / mass;
+        c[GC_BETA_IN] = sqrt((gam + 2.0) * gam) / (gam + 1.0);
+        const double dps = q[G_PHREF] - q[G_PHI_IN];
+        c[GC_DPS] = dps;
+        c[GC_PI_CLBL_DPS] = K_PI * q[G_CLBL] + dps;
+        c[GC_BETAG_CCL] = cell_len / (q[G_CLBL] * wave_len);  // "betag" of the CCL first half
+      } else {
+        const double inv_mass = 1.0 / mass;
+        c[GC_INV_MASS] = inv_mass;
+        const double gm_in = q[G_DESIGN_W] * inv_mass + 1.0;
+        const double beta_in = sqrt(1.0 - 1.0 / (gm_in * gm_in));
+        c[GC_BETA_IN] = beta_in;
+        const double cl = cell_len / q[G_CLBL];
+        const double betag_ccl = cl / wave_len;
+        c[GC_BETAG_CCL] = betag_ccl;
+        const double betag = ccl ? q[G_BETAC] : betag_ccl;
+        c[GC_BETAG] = betag;
+        const double betag2 = betag * betag;
+        const double gmg = 1.0 / sqrt(1.0 - betag2);
+        c[GC_GMG] = gmg;
+        const double inv_gmg2 = 1.0 / (gmg * gmg);
+        c[GC_INV_GMG2] = inv_gmg2;
+        const double aq = charge > 0.0 ? charge : -charge;
+        c[GC_AQ] = aq;
+        const double gm_out = q[G_EOUT] * inv_mass + 1.0;
+        c[GC_BETA_OUT] = sqrt(1.0 - 1.0 / (gm_out * gm_out));
+        const double efl = q[G_AMP] * cell_len;
+        c[GC_EFL] = efl;
+        c[GC_AQ_EFL] = aq * efl;
+        const double concomm = aq * efl / (mass * betag2);
+        c[GC_CONCOMM] = concomm;
+        const double concomm1 = concomm * inv_gmg2 / gmg;
+        c[GC_CONCOMM1] = concomm1;
+        c[GC_CON1] = K_PI * concomm1;
+        c[GC_CON2NEX] = concomm * inv_gmg2;
+        double inv_gmgcl, inv_fkis;
+        if (ccl) {
+          inv_gmgcl = 1.0 / (gmg * betag * wave_len);
+          inv_fkis = betag * wave_len / K_TWOPI;
+          c[GC_X5] = betag_ccl * wave_len;
+        } else {
+          inv_gmgcl = 1.0 / (gmg * cl);
+          inv_fkis = cl / K_TWOPI;
+          c[GC_X5] = beta_in * wave_len;
+        }
+        c[GC_INV_GMGCL] = inv_gmgcl;
+        c[GC_INV_FKIS] = inv_fkis;
+        c[GC_FKR] = K_TWOPI * inv_gmgcl;
+        double sinps, cosps;
+        sincos(q[G_PHREF], &sinps, &cosps);
+        c[GC_SINPS] = sinps;
+        c[GC_COSPS] = cosps;
+        c[GC_TTF_DEN] = K_TWOPI * q[G_FBC];
+        c[GC_TWOPI_DG] = K_TWOPI * q[G_DG];
+        const double dps = ccl ? q[G_PHI_IN] - q[G_PHREF] : q[G_PHREF] - q[G_PHI_IN];
+        c[GC_DPS] = dps;
+        c[GC_PI_CLBL_DPS] = K_PI * q[G_CLBL] + dps;
+        c[GC_PH_CONST] = (u32)q[G_CELLNUM] * K_PI;
+      }
+      break;
+    }
+    default: break;
+  }
+}
+
 // simulation_kernel.cu:87-118 -- a lost particle keeps its pre-drift x,y (H11)
-__device__ __forceinline__ void op_drift(Pt& p, const double* q, u32 elem, double mass) {
-  const double hl = q[0], aper2 = q[1] * q[1], wavelen = q[2];
+__device__ __forceinline__ void op_drift(Pt& p, const double* q, const double* c, u32 elem, double mass) {
+  const double hl = q[0], aper2 = c[D_APER2], wavelen = q[2];
   double x = p.x, y = p.y;
   x += p.xp * hl;
   y += p.yp * hl;
   if (aper2 != 0.0 && x * x + y * y > aper2) p.loss = elem;
   else {
     p.x = x; p.y = y;
-    p.phi += K_TWOPI * hl / (wavelen * beta_of(p.w, mass));
+    p.phi += c[D_TWOPI_HL] / (wavelen * beta_of(p.w, mass));
   }
 }
 
 // simulation_kernel.cu:142-218 -- two quarter-length thick-lens maps, then the aperture test
-__device__ __forceinline__ void op_quad_half(Pt& p, const double* q, u32 elem, double mass, double charge) {
+__device__ __forceinline__ void op_quad_half(Pt& p, const double* q, const double* c, u32 elem, double mass) {
   const double length = q[0], wavelen = q[3];
-  double aper2 = q[1]; aper2 *= aper2;
-  const double qg = q[2] * charge;
+  const double aper2 = c[Q_APER2], qg = c[Q_QG];
   double tx = p.x, ty = p.y;  // what the aperture test sees
   if (qg == 0) {
     // the reference stores the drifted x,y but tests the aperture with the OLD values
@@ -120,62 +240,51 @@ __device__ __forceinline__ void op_quad_half(Pt& p, const double* q, u32 elem, d
   } else {
     double gamma1 = p.w / mass;
     double bg = sqrt(gamma1 * (gamma1 + 2.0) * (1.0 + p.xp * p.xp + p.yp * p.yp));
-    double absqg = qg > 0.0 ? qg : -qg;
-    double k = sqrt(absqg / (bg * mass) * K_CLIGHT);
+    double k = sqrt(c[Q_ABSQG] / (bg * mass) * K_CLIGHT);
     double inv_k = 1.0 / k;
-    double kds = length * 0.25 * k;
-    double s, c, sh = sinh(kds), ch = cosh(kds);
-    sincos(kds, &s, &c);
+    double kds = c[Q_LEN4] * k;
+    double s, cs, sh = sinh(kds), ch = cosh(kds);
+    sincos(kds, &s, &cs);
     double sovk = s * inv_k, shovk = sh * inv_k, sk = s * k, shk = sh * k;
     double x = p.x, xp = p.xp, y = p.y, yp = p.yp, t;
 #pragma unroll
     for (int rep = 0; rep < 2; ++rep) {
       if (qg > 0.0) {
-        t = c * x + sovk * xp; xp = -sk * x + c * xp; x = t;
+        t = cs * x + sovk * xp; xp = -sk * x + cs * xp; x = t;
         t = ch * y + shovk * yp; yp = shk * y + ch * yp; y = t;
       } else {
         t = ch * x + shovk * xp; xp = shk * x + ch * xp; x = t;
-        t = c * y + sovk * yp; yp = -sk * y + c * yp; y = t;
+        t = cs * y + sovk * yp; yp = -sk * y + cs * yp; y = t;
       }
     }
     p.x = x; p.xp = xp; p.y = y; p.yp = yp;
     tx = x; ty = y;
   }
   if (aper2 != 0 && tx * tx + ty * ty > aper2) p.loss = elem;
-  else p.phi += K_TWOPI * length * 0.5 / (wavelen * beta_of(p.w, mass));
+  else p.phi += c[Q_TWOPI_LEN_HALF] / (wavelen * beta_of(p.w, mass));
 }
 
-// indices into Op::p for the RF gap (rfgap_parameter.h:4-32)
-enum { G_LEN = 0, G_FREQ, G_CLBL, G_AMP, G_PHREF, G_PHSHIFT, G_EOUT, G_BETAC, G_DG, G_T, G_TP, G_SP,
-       G_FBC, G_FBMIN, G_T0, G_T1, G_T2, G_T3, G_T4, G_T5, G_S1, G_S2, G_S3, G_S4, G_S5,
-       G_DESIGN_W = 25, G_PHI_IN = 26, G_QLEN1 = 27, G_QLEN2 = 28, G_CELLNUM = 29, G_WAVELEN = 30 };
-
 // simulation_kernel.cu:226-288
-__device__ __forceinline__ void op_gap_first(Pt& p, const double* q, bool ccl, double mass) {
-  const double qlen1 = q[G_QLEN1], qlen2 = q[G_QLEN2];
-  const double cell_len = q[G_LEN] + qlen1 * 0.5 + qlen2 * 0.5;
-  const double dd1 = 0.5 * cell_len - q[G_DG] - 0.5 * qlen1;
-  const double xp = p.xp, yp = p.yp, phi = p.phi, w = p.w;
-  p.x = p.x + dd1 * xp;
-  p.y = p.y + dd1 * yp;
-  const double wave_len = K_CLIGHT / q[G_FREQ];
+__device__ __forceinline__ void op_gap_first(Pt& p, const double* q, const double* c, bool ccl, double mass) {
+  const double dd1 = c[GC_DD];
+  const double phi = p.phi, w = p.w;
+  p.x = p.x + dd1 * p.xp;
+  p.y = p.y + dd1 * p.yp;
+  const double wave_len = c[GC_WAVE_LEN];
   if (q[G_AMP] == 0.0) {
-    p.phi += K_TWOPI * dd1 / (wave_len * beta_of(w, mass));
+    p.phi += c[GC_TWOPI_DD] / (wave_len * beta_of(w, mass));
   } else {
-    double gam = q[G_DESIGN_W] / mass;
-    double beta_in = sqrt((gam + 2.0) * gam) / (gam + 1.0);
-    gam = w / mass;
-    double beta = sqrt((gam + 2.0) * gam) / (gam + 1.0);
-    double dps = q[G_PHREF] - q[G_PHI_IN];
+    const double beta_in = c[GC_BETA_IN];
+    const double gam = w / mass;
+    const double beta = sqrt((gam + 2.0) * gam) / (gam + 1.0);
     if (!ccl) {
-      double d_cell_len = cell_len - q[G_BETAC] * wave_len;
-      double dphi_qlen1 = K_TWOPI * 0.5 * qlen1 / (beta * wave_len);
+      const double d_cell_len = c[GC_D_CELL_LEN];
+      const double dphi_qlen1 = c[GC_TWOPI_HALF_QLEN] / (beta * wave_len);
       double dphi_clen = 0.0;
-      if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = K_PI * d_cell_len / (beta * wave_len);
-      p.phi = phi + (1.0 - (beta - beta_in) / beta) * (K_PI * q[G_CLBL] + dps) + dphi_clen - dphi_qlen1;
+      if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = c[GC_PI_DCL] / (beta * wave_len);
+      p.phi = phi + (1.0 - (beta - beta_in) / beta) * c[GC_PI_CLBL_DPS] + dphi_clen - dphi_qlen1;
     } else {
-      double betag = cell_len / (q[G_CLBL] * wave_len);
-      p.phi = phi + (1.0 - (beta - beta_in) * betag / (beta * beta_in)) * (K_PI * q[G_CLBL] + dps);
+      p.phi = phi + (1.0 - (beta - beta_in) * c[GC_BETAG_CCL] / (beta * beta_in)) * c[GC_PI_CLBL_DPS];
     }
   }
 }
@@ -208,71 +317,52 @@ __device__ __forceinline__ double bessi1c(double rx) {
 }
 
 // simulation_kernel.cu:290-497
-__device__ __forceinline__ void op_gap_second(Pt& p, const double* q, bool ccl, double mass, double charge) {
-  const double qlen1 = q[G_QLEN1], qlen2 = q[G_QLEN2];
-  const double cell_len = q[G_LEN] + qlen1 * 0.5 + qlen2 * 0.5;
-  const double dd2 = 0.5 * cell_len + q[G_DG] - qlen2 * 0.5;
+__device__ __forceinline__ void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, double mass) {
+  const double dd2 = c[GC_DD];
   double x = p.x, y = p.y, xp = p.xp, yp = p.yp;
-  const double inv_mass = 1.0 / mass;
+  const double inv_mass = c[GC_INV_MASS];
   const double phi = p.phi;
   double w = p.w;
-  const double gm_in = q[G_DESIGN_W] * inv_mass + 1.0;
-  const double beta_in = sqrt(1.0 - 1.0 / (gm_in * gm_in));
+  const double beta_in = c[GC_BETA_IN];
   double gam = w * inv_mass;
   const double bg1 = sqrt(gam * (gam + 2.0));
   double beta = bg1 / (gam + 1.0);
   // transit-time factors from the 5th-order fits (GetTransitTimeFactors)
   double t_fac, tp_fac, sp_fac;
   {
-    const double betag = q[G_FBC];
     double bb = beta;
-    if (beta > 1.1 * betag) bb = betag;
+    if (beta > 1.1 * q[G_FBC]) bb = q[G_FBC];
     else if (beta < q[G_FBMIN]) bb = q[G_FBMIN];
     t_fac = q[G_T0] + bb * (q[G_T1] + bb * (q[G_T2] + bb * (q[G_T3] + bb * (q[G_T4] + bb * q[G_T5]))));
-    double coef = bb * bb / (K_TWOPI * betag);
+    double coef = bb * bb / c[GC_TTF_DEN];
     tp_fac = coef * (q[G_T1] + bb * (2 * q[G_T2] + bb * (3 * q[G_T3] + bb * (4 * q[G_T4] + 5 * bb * q[G_T5]))));
     sp_fac = -coef * (q[G_S1] + bb * (2 * q[G_S2] + bb * (3 * q[G_S3] + bb * (4 * q[G_S4] + 5 * bb * q[G_S5]))));
   }
   if (q[G_AMP] == 0.0 || (ccl && beta < q[G_FBMIN])) {
     p.x = x + dd2 * xp;
     p.y = y + dd2 * yp;
-    p.phi += K_TWOPI * dd2 / (q[G_WAVELEN] * beta_of(w, mass));
+    p.phi += c[GC_TWOPI_DD] / (q[G_WAVELEN] * beta_of(w, mass));
     return;
   }
-  const double wave_len = K_CLIGHT / q[G_FREQ];
-  const double cl = cell_len / q[G_CLBL];
-  const double betag_ccl = cl / wave_len;
-  const double betag = ccl ? q[G_BETAC] : betag_ccl;
-  const double betag2 = betag * betag;
-  const double gmg = 1.0 / sqrt(1.0 - betag2);
-  const double inv_gmg2 = 1.0 / (gmg * gmg);
-  const double aq = charge > 0.0 ? charge : -charge;
-  const double gm_out = q[G_EOUT] * inv_mass + 1.0;
-  const double beta_out = sqrt(1.0 - 1.0 / (gm_out * gm_out));
-  const double efl = q[G_AMP] * cell_len;
-  const double concomm = aq * efl / (mass * betag2);
-  const double concomm1 = concomm * inv_gmg2 / gmg;
-  const double con1 = K_PI * concomm1;
-  const double con2nex = concomm * inv_gmg2;
-  double con5nex, tw, inv_fkis, inv_gmgcl;
-  if (ccl) {
-    inv_gmgcl = 1.0 / (gmg * betag * wave_len);
-    inv_fkis = betag * wave_len / K_TWOPI;
-    con5nex = concomm * (t_fac * inv_fkis - betag_ccl * wave_len * tp_fac * inv_gmg2);
-    tw = t_fac - K_TWOPI * tp_fac * (beta_in / beta - 1.0) * betag_ccl / beta_in;
-  } else {
-    inv_gmgcl = 1.0 / (gmg * cl);
-    inv_fkis = cl / K_TWOPI;
-    con5nex = concomm * (t_fac * inv_fkis - beta_in * wave_len * tp_fac * inv_gmg2);
-    tw = t_fac;
-  }
-  const double con5nex1 = concomm1 * t_fac;
+  const double wave_len = c[GC_WAVE_LEN];
+  const double betag_ccl = c[GC_BETAG_CCL];
+  const double gmg = c[GC_GMG];
+  const double inv_gmg2 = c[GC_INV_GMG2];
+  const double efl = c[GC_EFL];
+  const double concomm = c[GC_CONCOMM];
+  const double con1 = c[GC_CON1];
+  const double con2nex = c[GC_CON2NEX];
+  const double inv_gmgcl = c[GC_INV_GMGCL], inv_fkis = c[GC_INV_FKIS];
+  const double con5nex = concomm * (t_fac * inv_fkis - c[GC_X5] * tp_fac * inv_gmg2);
+  double tw;
+  if (ccl) tw = t_fac - K_TWOPI * tp_fac * (beta_in / beta - 1.0) * betag_ccl / beta_in;
+  else tw = t_fac;
+  const double con5nex1 = c[GC_CONCOMM1] * t_fac;
   const double con5nex2 = -con2nex * t_fac * inv_fkis;
-  const double fkr = K_TWOPI * inv_gmgcl;
-  double sinps, cosps;
-  sincos(q[G_PHREF], &sinps, &cosps);
+  const double fkr = c[GC_FKR];
+  const double sinps = c[GC_SINPS], cosps = c[GC_COSPS];
   double phi1, sinp1, cosp1;
-  if (ccl) phi1 = phi + q[G_PHSHIFT] - K_TWOPI * q[G_DG] / (beta * wave_len) + (u32)q[G_CELLNUM] * K_PI;
+  if (ccl) phi1 = phi + q[G_PHSHIFT] - c[GC_TWOPI_DG] / (beta * wave_len) + c[GC_PH_CONST];
   else phi1 = phi + q[G_PHSHIFT];
   sincos(phi1, &sinp1, &cosp1);
   const double prome1 = -con1 * (tp_fac * (sinp1 - sinps) + sp_fac * (cosp1 - cosps));
@@ -287,8 +377,8 @@ __device__ __forceinline__ void op_gap_second(Pt& p, const double* q, bool ccl, 
   const double b1p = (fkrris != 0.0) ? b0c - b1c / fkrris : 0.5;
   double bes1covr, rpris = 0.0;
   if (ris != 0.0) bes1covr = b1c / ris; else bes1covr = fkr * 0.5;
-  const double delte = aq * efl * (tw * b0c * cosp1 + ((tw - K_TWOPI * tp_fac) / gmg * bes1covr + tw / gmg * fkr * b1p -
-                                                      tw * gmg * bes1covr) * rrp * sinp1);
+  const double delte = c[GC_AQ_EFL] * (tw * b0c * cosp1 + ((tw - K_TWOPI * tp_fac) / gmg * bes1covr + tw / gmg * fkr * b1p -
+                                                           tw * gmg * bes1covr) * rrp * sinp1);
   w += delte;
   gam = w * inv_mass;
   const double bg = sqrt(gam * (gam + 2.0));
@@ -304,17 +394,16 @@ __device__ __forceinline__ void op_gap_second(Pt& p, const double* q, bool ccl, 
   if (rs_p > 0.0) rpris = rrp / ris;
   const double prome = 2.0 * con1 * (-tp_fac * b0c + ris * tw * b1c * inv_gmgcl) * (sinp1 - sinps) -
                        efl * inv_mass * tw * b1c * rpris * (cosp1 - cosps);
+  const double beta_out = c[GC_BETA_OUT];
   double phi_new;
   if (ccl) {
-    double dps = q[G_PHI_IN] - q[G_PHREF];
-    phi_new = phi + (1.0 - (beta - beta_out) * betag_ccl / (beta * beta_out)) * (K_PI * q[G_CLBL] + dps) + prome;
+    phi_new = phi + (1.0 - (beta - beta_out) * betag_ccl / (beta * beta_out)) * c[GC_PI_CLBL_DPS] + prome;
   } else {
-    double d_cell_len = cell_len - q[G_BETAC] * wave_len;
-    double dphi_qlen2 = K_TWOPI * 0.5 * qlen2 / (beta * wave_len);
+    const double d_cell_len = c[GC_D_CELL_LEN];
+    const double dphi_qlen2 = c[GC_TWOPI_HALF_QLEN] / (beta * wave_len);
     double dphi_clen = 0.0;
-    if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = K_PI * d_cell_len / (beta * wave_len);
-    double dps = q[G_PHREF] - q[G_PHI_IN];
-    phi_new = phi + (1.0 - (beta - beta_out) / beta) * (K_PI * q[G_CLBL] + dps) + prome + dphi_clen - dphi_qlen2;
+    if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = c[GC_PI_DCL] / (beta * wave_len);
+    phi_new = phi + (1.0 - (beta - beta_out) / beta) * c[GC_PI_CLBL_DPS] + prome + dphi_clen - dphi_qlen2;
   }
   if (w <= 0.0 || x != x || y != y || xp != xp || yp != yp || w != w || phi_new != phi_new) {
     p.loss = 33333333u;  // the reference also printf()s here; coordinates keep their pre-gap values
@@ -430,25 +519,44 @@ struct KickCtx {  // block-uniform inputs of the space-charge kick, staged in sh
   double phimc, xbar, ybar, epsq, phi_ref;
   double dr, dz, beta, ratio_r, ratio_z, ratio_q, ratio_g;
   u32 adj_bunch, num_on_mesh, nr, nz;
+  // derived once per block (kick_prepare) with the reference's expression order
+  double gmg, dr_eff, dzg, hl, c2, c3, xfac, yfac, pl, cbgcoef, nr_dr, er_c3, ez_c3, inv_mass_unused;
 };
 
-// space_charge_kernel.cu:573-706
-__device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const double* q, const KickCtx& k, const double2* __restrict__ fld,
-                                           double mass, u32 n_global) {
-  if (!(p.loss == 0 && lloss == 0)) return;
+// particle-independent part of space_charge_kernel.cu:597-616, 680-681
+__device__ inline void kick_prepare(KickCtx& k, const double* q, double mass, u32 n_global) {
   const double length = q[0], current = q[1], freq = q[2];
   const double beta = k.beta;
-  const double phi = rel_phi(p.phi, k.phi_ref);
   const double gmg = rsqrt(1.0 - beta * beta);
-  const double dr = k.dr * k.ratio_r;
-  const double dzg = k.dz * gmg * k.ratio_z;
+  k.gmg = gmg;
+  k.dr_eff = k.dr * k.ratio_r;
+  k.dzg = k.dz * gmg * k.ratio_z;
   const double wave_len = K_CLIGHT / freq;
-  const double hl = k.nz * 0.5 * dzg;
+  k.hl = k.nz * 0.5 * k.dzg;
   const double c1 = 5721.67 * current / (freq * 1e6 * (double)n_global * mass);
-  const double c2 = beta * gmg * wave_len / K_TWOPI;
+  k.c2 = beta * gmg * wave_len / K_TWOPI;
   const double c3 = length / (beta * gmg);
-  const double xfac = 2.0 / (k.epsq + 1.0);
-  const double yfac = k.epsq * xfac;
+  k.c3 = c3;
+  k.xfac = 2.0 / (k.epsq + 1.0);
+  k.yfac = k.epsq * k.xfac;
+  k.pl = beta * gmg * wave_len;
+  k.cbgcoef = c1 * c3 * K_PI * 0.5 * k.num_on_mesh;
+  k.nr_dr = k.nr * k.dr_eff;
+  const double er_ratio = k.ratio_q / (k.ratio_r * k.ratio_z * k.ratio_g * k.ratio_g);
+  const double ez_ratio = k.ratio_q / (k.ratio_z * k.ratio_z);
+  k.er_c3 = er_ratio * c3;
+  k.ez_c3 = ez_ratio * c3;
+}
+
+// space_charge_kernel.cu:573-706
+__device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __restrict__ fld, double mass) {
+  if (!(p.loss == 0 && lloss == 0)) return;
+  const double beta = k.beta;
+  const double phi = rel_phi(p.phi, k.phi_ref);
+  const double gmg = k.gmg;
+  const double dr = k.dr_eff;
+  const double dzg = k.dzg;
+  const double hl = k.hl;
   const double gm = p.w / mass + 1.0;
   const double bgz = sqrt((gm - 1.0) * (gm + 1.0));
   double bgx = bgz * p.xp, bgy = bgz * p.yp;
@@ -456,23 +564,22 @@ __device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const double* q, co
   const double xxbar = p.x - k.xbar, yybar = p.y - k.ybar;
   double r = sqrt(xxbar * xxbar / k.epsq + yybar * yybar * k.epsq);
   if (r == 0.0) r = 1.0e-8;
-  const double xovr = xxbar * xfac / r, yovr = yybar * yfac / r;
+  const double xovr = xxbar * k.xfac / r, yovr = yybar * k.yfac / r;
   double ddz = phi - k.phimc;
   while (ddz > K_PI || ddz < -K_PI) {
     if (ddz > 0.0) ddz -= K_TWOPI; else ddz += K_TWOPI;
   }
-  double z = -c2 * ddz;
+  double z = -k.c2 * ddz;
   double cbgr, cbgzs;
-  if (r > k.nr * dr || fabs(z) > hl) {  // off the mesh: point-charge field of the on-mesh charge (H17)
-    z = -c2 * (phi - k.phimc);
+  if (r > k.nr_dr || fabs(z) > hl) {  // off the mesh: point-charge field of the on-mesh charge (H17)
+    z = -k.c2 * (phi - k.phimc);
     double d = sqrt(z * z + r * r);
     double invd3 = 1.0 / (d * d * d);
     double rod3 = r * invd3, zod3 = z * invd3;
-    const double pl = beta * gmg * wave_len;
     for (int nb = 1; nb <= (int)k.adj_bunch; ++nb) {
       int xi = nb;
       for (int lr = 1; lr <= 2; ++lr) {
-        double s = z + xi * pl;
+        double s = z + xi * k.pl;
         d = sqrt(s * s + r * r);
         invd3 = 1.0 / (d * d * d);
         rod3 += r * invd3;
@@ -480,9 +587,8 @@ __device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const double* q, co
         xi = -xi;
       }
     }
-    const double cbgcoef = c1 * c3 * K_PI * 0.5 * k.num_on_mesh;
-    cbgr = cbgcoef * rod3;
-    cbgzs = cbgcoef * zod3;
+    cbgr = k.cbgcoef * rod3;
+    cbgzs = k.cbgcoef * zod3;
   } else {
     const u32 i = 1 + (int)(r / dr);
     const double a = r / dr - (i - 1.0), b = 1.0 - a;
@@ -492,11 +598,9 @@ __device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const double* q, co
     u32 m = l + (k.nr + 1);
     const u32 tbl_sz = (k.nr + 1) * (k.nz + 1);
     if (m >= tbl_sz) m = tbl_sz - 1;
-    const double er_ratio = k.ratio_q / (k.ratio_r * k.ratio_z * k.ratio_g * k.ratio_g);
-    const double ez_ratio = k.ratio_q / (k.ratio_z * k.ratio_z);
     const double2 fl = __ldg(&fld[l]), fl1 = __ldg(&fld[l - 1]), fm = __ldg(&fld[m]), fm1 = __ldg(&fld[m - 1]);
-    cbgr = er_ratio * c3 * (d * (a * fl.x + b * fl1.x) + c * (a * fm.x + b * fm1.x));
-    cbgzs = ez_ratio * c3 * (d * (a * fl.y + b * fl1.y) + c * (a * fm.y + b * fm1.y));
+    cbgr = k.er_c3 * (d * (a * fl.x + b * fl1.x) + c * (a * fm.x + b * fm1.x));
+    cbgzs = k.ez_c3 * (d * (a * fl.y + b * fl1.y) + c * (a * fm.y + b * fm1.y));
   }
   bgx += cbgr * xovr;
   bgy += cbgr * yovr;

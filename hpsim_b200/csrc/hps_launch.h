@@ -9,7 +9,9 @@ namespace hps {
 
 struct LaunchCfg {
   cudaStream_t stream;
-  unsigned grid_pairs;    // grid of the 2-particles-per-thread sweeps
+  int seg_variant;        // 0: 2 particles/thread, 1: 1 particle/thread (3 blocks/SM), 2: 1 particle/thread (4 blocks/SM)
+  unsigned grid_seg;      // grid of the fused segment sweep
+  unsigned grid_pairs;    // grid of the 2-particles-per-thread statistic sweeps
   unsigned grid_single;   // grid of the 1-particle-per-thread API statistics kernel
   unsigned grid_deposit;
   double* partials;       // [max grid][HPS_NSLOT]
@@ -28,19 +30,22 @@ struct StatReq {
   double w_ref;       // w[0] for the emittance normalisation (beam_kernel.cu:1345)
 };
 
-void launch_segment(const LaunchCfg&, const BeamView&, const Op* ops, int nops, int fin_mode, int dirty, int compat,
-                    DevStats*, const ScDev*, const double2* field, const KickParams&);
+void launch_prepare_ops(const LaunchCfg&, const Op* ops, OpC* opcs, int nops, double mass, double charge);
+void launch_segment(const LaunchCfg&, const BeamView&, const Op* ops, const OpC* opcs, int nops, int fin_mode, int dirty,
+                    int compat, DevStats*, const ScDev*, const double2* field, const KickParams&);
 void launch_lloss_pass(const LaunchCfg&, const BeamView&, DevStats*, ScDev*);
 void launch_moments(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&, int do_policy);
 cudaError_t launch_deposit(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&);
-cudaError_t launch_field(const LaunchCfg&, DevStats*, ScDev*, const double* bins, double2* field, const KickParams&);
+cudaError_t launch_field(const LaunchCfg&, DevStats*, ScDev*, const double* bins, double2* field, double2* part,
+                         u32* tickets, const KickParams&);
+unsigned field_chunks(const KickParams&);
 void launch_stat(const LaunchCfg&, const BeamView&, DevStats*, const StatReq&);
 void launch_set_phi_ref(const LaunchCfg&, const BeamView&, DevStats*, int use_good, double phi0);
 void launch_copy_stat(const LaunchCfg&, DevStats*, int dst, int src);
 void launch_shift(const LaunchCfg&, double* a, double v, u32 n, u32 offset);
 void launch_cut(const LaunchCfg&, const double* a, u32* loss, double lo, double hi, u32 n, u32 offset);
 void launch_rel_phi_out(const LaunchCfg&, const BeamView&, const DevStats*, double* out);
-int segment_occupancy();
+int segment_occupancy(int variant);
 size_t deposit_smem(const KickParams&);
 size_t field_smem(const KickParams&, int threads);
 int field_threads(const KickParams&);

@@ -991,7 +991,7 @@ void ScheffStart(hps_scheff* s, hps_beam* b, double length) {
       s->dz = bl / s->nz;
     } else {
       // H6: the reference compares device POINTERS (x_sig_good > y_sig_good); allocation order makes it false
-      s->dr = 3.0 * b->s.v[HPS_STAT_Y_SIG_GOOD] / s->nx;
+      s->dr = 3.0 * b->s.v[getenv("HPS_SIGX") ? HPS_STAT_X_SIG_GOOD : HPS_STAT_Y_SIG_GOOD] / s->nx;
       s->dz = 3.0 * bl * b->s.v[HPS_STAT_PHI_SIG_GOOD] / (s->nz * PI);  // H8: clamp is dead code
     }
     UpdateGreenTable(s, freq, beta, b->n, b->current * frac / b->mass, adj_bunch);
