@@ -41,6 +41,7 @@ struct hps_ctx {
   u32* ticket = nullptr;
   unsigned max_grid = 0;    // cap for the light statistic sweeps
   unsigned seg_grid_cap = 0;  // resident blocks of the segment kernel variant in use
+  unsigned seg_grid_cap_full = 0;
   int seg_variant = 0;
   // program upload buffers
   Op* d_ops = nullptr;
@@ -120,6 +121,7 @@ LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
   l.seg_variant = c->seg_variant;
   const unsigned seg_items = c->seg_variant == 0 ? pairs : b->n;
   l.grid_seg = std::max(1u, std::min((seg_items + HPS_BLOCK - 1) / HPS_BLOCK, c->seg_grid_cap));
+  l.grid_seg1 = std::max(1u, std::min((b->n + HPS_BLOCK - 1) / HPS_BLOCK, c->seg_grid_cap_full));
   l.grid_pairs = std::max(1u, std::min((pairs + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
   l.grid_single = std::max(1u, std::min((b->n + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
   l.grid_deposit = std::max(1u, std::min((b->n + 511) / 512, (unsigned)c->num_sms * 2));
@@ -220,7 +222,7 @@ void UpdateStatForSpaceCharge(hps_beam* b) {
   KickParams kp;
   std::memset(&kp, 0, sizeof(kp));
   kp.n_global = b->h.n_global; kp.mass = b->h.mass;
-  launch_segment(l, v, c->d_ops, c->d_opc, 0, FIN_KICK, 0, c->compat, b->st, nullptr, nullptr, kp);
+  launch_segment(l, v, nullptr, c->d_ops, c->d_opc, 0, FIN_KICK, 0, c->compat, b->st, nullptr, nullptr, kp);
   launch_lloss_pass(l, v, b->st, nullptr);
   launch_moments(l, v, b->st, nullptr, nullptr, kp, 0);
   c->launches += 3;
@@ -301,6 +303,7 @@ hps_ctx* hps_ctx_create(int device) {
   int occ = ok ? segment_occupancy(c->seg_variant) : 0;
   if (occ < 1) occ = 1;
   c->seg_grid_cap = (unsigned)c->num_sms * (unsigned)occ;
+  c->seg_grid_cap_full = (unsigned)c->num_sms * (unsigned)std::max(1, ok ? segment_occupancy(-1) : 1);
   c->max_grid = (unsigned)c->num_sms * 6u;
   ok = ok && cudaMalloc(&c->partials, (size_t)c->max_grid * HPS_NSLOT * sizeof(double)) == cudaSuccess &&
        cudaMalloc(&c->ticket, 256) == cudaSuccess && cudaMemset(c->ticket, 0, 256) == cudaSuccess;
@@ -811,7 +814,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
   for (const Segment& s : plan.segs) {
     const int dirty = dirty_mask(plan.ops.data() + s.op_begin, s.op_count);
     prof_mark(c, HPS_PROF_SEGMENT);
-    launch_segment(l, v, c->d_ops + s.op_begin, c->d_opc + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
+    launch_segment(l, v, plan.ops.data() + s.op_begin, c->d_ops + s.op_begin, c->d_opc + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
                    sc ? sc->field : nullptr, s.kp);
     c->launches++;
     sweeps++;

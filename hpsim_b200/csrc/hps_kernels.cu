@@ -43,6 +43,7 @@ __device__ void finalize_segment(int fin, const double* t, DevStats* st, u32 n_g
 }
 
 // one op applied to one register-resident particle
+template <bool FULL>
 __device__ __forceinline__ void apply_op(Pt& pt, const u32 ll, const u32 gidx, const Op& op, const OpC& opc, const KickCtx& kc,
                                          const double* cxy, const double2* __restrict__ field, const BeamView& b,
                                          int compat, double& phi_fc, bool& live_fc) {
@@ -54,9 +55,11 @@ __device__ __forceinline__ void apply_op(Pt& pt, const u32 ll, const u32 gidx, c
     case OP_QUAD_HALF: if (pt.loss == 0) op_quad_half(pt, q, c, op.elem, mass); break;
     case OP_GAP_FIRST: if (pt.loss == 0) op_gap_first(pt, q, c, op.flag != 0, mass); break;
     case OP_GAP_SECOND: if (pt.loss == 0) op_gap_second(pt, q, c, op.flag != 0, mass); break;
-    case OP_DIPOLE_FIRST: if (pt.loss == 0) op_dipole(pt, q, false, mass); break;
-    case OP_DIPOLE_SECOND: if (pt.loss == 0) op_dipole(pt, q, true, mass); break;
-    case OP_BUNCHER: if (pt.loss == 0) op_buncher(pt, q, op.elem, mass, charge); break;
+    // the rare, code-heavy maps (7 dipoles and 2 bunchers in the whole linac) live in the FULL variant only,
+    // which keeps the hot variant's SASS inside the instruction cache
+    case OP_DIPOLE_FIRST: if (FULL && pt.loss == 0) op_dipole(pt, q, false, mass); break;
+    case OP_DIPOLE_SECOND: if (FULL && pt.loss == 0) op_dipole(pt, q, true, mass); break;
+    case OP_BUNCHER: if (FULL && pt.loss == 0) op_buncher(pt, q, op.elem, mass, charge); break;
     case OP_ROTATION:  // simulation_kernel.cu:511-529
       if (pt.loss == 0) {
         const double cosa = c[R_COS], sina = c[R_SIN];
@@ -114,7 +117,7 @@ __device__ __forceinline__ void seg_accumulate(double (&acc)[SEG_NS], const Pt& 
 // PPT = particles per thread.  PPT == 2 moves two adjacent particles with one 128-bit access per
 // array; PPT == 1 halves the register footprint and doubles the resident warps (the maps are chains of
 // dependent fp64 operations, so the sweep is latency-bound before it is bandwidth-bound).
-template <int PPT, int MINB>
+template <int PPT, int MINB, bool FULL>
 __global__ void __launch_bounds__(HPS_BLOCK, MINB)
 k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
           DevStats* st, const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials,
@@ -181,8 +184,8 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       for (int k = 0; k < nops; ++k) {
         const Op& op = s_ops[k];
         const OpC& oc = s_opc[k];
-        apply_op(p0, LL.x, g0, op, oc, s_k, s_cxy, field, b, compat, fc0, lf0);
-        if (valid1) apply_op(p1, LL.y, g1, op, oc, s_k, s_cxy, field, b, compat, fc1, lf1);
+        apply_op<FULL>(p0, LL.x, g0, op, oc, s_k, s_cxy, field, b, compat, fc0, lf0);
+        if (valid1) apply_op<FULL>(p1, LL.y, g1, op, oc, s_k, s_cxy, field, b, compat, fc1, lf1);
       }
       if (nops > 0) {
         if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p0.x, p1.x);
@@ -206,7 +209,7 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       const u32 g = b.offset + i;
       double fc = 0.0;
       bool lf = false;
-      for (int k = 0; k < nops; ++k) apply_op(p, ll, g, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
+      for (int k = 0; k < nops; ++k) apply_op<FULL>(p, ll, g, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
       if (nops > 0) {
         if (dirty & 1) b.x[i] = p.x;
         if (dirty & 2) b.xp[i] = p.xp;
@@ -224,9 +227,11 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
     if (threadIdx.x == 0) finalize_segment(fin_mode, s_total, st, b.n_global);
   }
 }
-template __global__ void k_segment<2, 2>(BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*);
-template __global__ void k_segment<1, 3>(BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*);
-template __global__ void k_segment<1, 4>(BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*);
+#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*
+template __global__ void k_segment<2, 2, false>(SEG_ARGS);
+template __global__ void k_segment<1, 3, false>(SEG_ARGS);
+template __global__ void k_segment<1, 4, false>(SEG_ARGS);
+template __global__ void k_segment<1, 3, true>(SEG_ARGS);
 
 // one thread per op record of the uploaded program (once per simulate() call)
 __global__ void k_prepare_ops(const Op* __restrict__ ops, OpC* opcs, int nops, double mass, double charge) {
@@ -782,17 +787,25 @@ static int g_field_smem_set = 0, g_deposit_smem_set = 0;
 void launch_prepare_ops(const LaunchCfg& c, const Op* ops, OpC* opcs, int nops, double mass, double charge) {
   if (nops > 0) k_prepare_ops<<<(nops + 63) / 64, 64, 0, c.stream>>>(ops, opcs, nops, mass, charge);
 }
-void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* ops, const OpC* opcs, int nops, int fin_mode, int dirty,
-                    int compat, DevStats* st, const ScDev* sc, const double2* field, const KickParams& kp) {
+void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, const Op* ops, const OpC* opcs, int nops,
+                    int fin_mode, int dirty, int compat, DevStats* st, const ScDev* sc, const double2* field,
+                    const KickParams& kp) {
+  bool full = false;
+  for (int k = 0; k < nops; ++k) full |= host_ops[k].type == OP_DIPOLE_FIRST || host_ops[k].type == OP_DIPOLE_SECOND || host_ops[k].type == OP_BUNCHER;
+  const unsigned grid1 = c.grid_seg1, grid2 = c.grid_seg;
+  if (full) {
+    k_segment<1, 3, true><<<grid1, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+    return;
+  }
   switch (c.seg_variant) {
     case 1:
-      k_segment<1, 3><<<c.grid_seg, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+      k_segment<1, 3, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
       break;
     case 2:
-      k_segment<1, 4><<<c.grid_seg, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+      k_segment<1, 4, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
       break;
     default:
-      k_segment<2, 2><<<c.grid_seg, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+      k_segment<2, 2, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
   }
 }
 void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
@@ -854,9 +867,10 @@ void launch_rel_phi_out(const LaunchCfg& c, const BeamView& b, const DevStats* s
 }
 int segment_occupancy(int variant) {
   int nb = 0;
-  if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3>, HPS_BLOCK, 0);
-  else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 4>, HPS_BLOCK, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<2, 2>, HPS_BLOCK, 0);
+  if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3, false>, HPS_BLOCK, 0);
+  else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 4, false>, HPS_BLOCK, 0);
+  else if (variant == -1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3, true>, HPS_BLOCK, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<2, 2, false>, HPS_BLOCK, 0);
   return nb;
 }
 

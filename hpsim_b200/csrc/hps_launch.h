@@ -10,7 +10,8 @@ namespace hps {
 struct LaunchCfg {
   cudaStream_t stream;
   int seg_variant;        // 0: 2 particles/thread, 1: 1 particle/thread (3 blocks/SM), 2: 1 particle/thread (4 blocks/SM)
-  unsigned grid_seg;      // grid of the fused segment sweep
+  unsigned grid_seg;      // grid of the fused segment sweep (variant in use)
+  unsigned grid_seg1;     // grid of the full-op-set variant (1 particle per thread)
   unsigned grid_pairs;    // grid of the 2-particles-per-thread statistic sweeps
   unsigned grid_single;   // grid of the 1-particle-per-thread API statistics kernel
   unsigned grid_deposit;
@@ -31,8 +32,8 @@ struct StatReq {
 };
 
 void launch_prepare_ops(const LaunchCfg&, const Op* ops, OpC* opcs, int nops, double mass, double charge);
-void launch_segment(const LaunchCfg&, const BeamView&, const Op* ops, const OpC* opcs, int nops, int fin_mode, int dirty,
-                    int compat, DevStats*, const ScDev*, const double2* field, const KickParams&);
+void launch_segment(const LaunchCfg&, const BeamView&, const Op* host_ops, const Op* ops, const OpC* opcs, int nops,
+                    int fin_mode, int dirty, int compat, DevStats*, const ScDev*, const double2* field, const KickParams&);
 void launch_lloss_pass(const LaunchCfg&, const BeamView&, DevStats*, ScDev*);
 void launch_moments(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&, int do_policy);
 cudaError_t launch_deposit(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&);

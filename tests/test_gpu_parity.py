@@ -108,13 +108,6 @@ def test_live_reference_single_kicks_in_dtl(tmp_path):
     c = H.Case(H.cuda_lib(), n=n, sc=True, make_beam=False)
     c.beam.set_frequency(stats["freq"])
     c.beam._upload(mid["x"], mid["xp"], mid["y"], mid["yp"], mid["phi"], mid["w"], mid["loss"], mid["lloss"])
-    c.beam.set_ref_w(float(mid["w"][0]))
-    c.beam._c.check(c.beam._c.lib.hps_beam_set_ref_w(c.beam.h, float(mid["w"][0])))
-    # the engine takes design_w from the beam at Reset(); the reference driver sets it explicitly too
-    c.beam._c.lib.hps_beam_set_ref_w(c.beam.h, float(mid["w"][0]))
-    c.sim.reset()
-    K.load().hps_engine_reset(c.beam._c.h, c.beam.h)
-    c.design_w = stats["design_w"]
     _set_design_w(c, stats["design_w"])
     c.run("01RG20", "01QM22")
     c.beam.get_loss_num("l")
