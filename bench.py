@@ -14,9 +14,10 @@ One step = restore the intermediate beam + one simulate(01QM00U, 04QM30).
           events between consecutive launches in one extra profiled step
   cpu_baseline : the CPU oracle (oracle/, OpenMP, all host cores) on a bounded sample
 
-N > 1 (torchrun): weak scaling -- every rank tracks its own 1 Mi-particle beam (scan-style
-replicas, BASELINE configs[4]) unless --sharded is given, in which case one beam of N x 1 Mi
-particles is particle-sharded with NCCL reductions per kick.
+N > 1 (torchrun): weak scaling -- ONE beam of N x 1 Mi particles, particle-sharded over the N GPUs
+(contiguous index blocks); every kick exchanges three small moment vectors and the 32 KB charge mesh
+between the ranks inside the reducing kernels (peer stores over NVLink; NCCL all-gather as fallback).
+--replicas instead tracks one independent 1 Mi-particle beam per GPU (scan style, BASELINE configs[4]).
 `--impl reference` runs the reference's own CUDA code (oracle/_ref/ref_driver, sm_100 rebuild of
 the unmodified sources) on the same workload; the reference has no CPU implementation.
 """
@@ -97,8 +98,8 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_dp was not built (reference sources absent at build time)"}))
         return
     n = N_PER_GPU
-    work = os.path.join(ROOT, "gpurun_out", "bench_ref")
-    os.makedirs(work, exist_ok=True)
+    import tempfile
+    work = tempfile.mkdtemp(prefix="hpsim_bench_ref_")  # the 59 MB beam dump must not land in gpurun_out/
     reps = args.steps + args.warmup
     cfg = [f"lattice {H.LATTICE}", f"n {n}", f"mass {H.MASS}", f"charge {H.CHARGE}", f"current {H.CURRENT}", "sc 1",
            "nr 32", "nz 128", "interval 0.025", "adj_bunch 3", "adj_bunch_cutoff_w 0.8", "remesh_threshold 0.02",
@@ -158,9 +159,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--particles", type=int, default=N_PER_GPU)
-    ap.add_argument("--sharded", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N>1: one independent beam per GPU (scan style) instead of one sharded beam")
     ap.add_argument("--ref-float", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -178,7 +180,13 @@ def main():
     HPSim.print_timing = False
     lib = K.load()
     n = args.particles
-    case = H.Case(lib, n=n, sc=True)
+    sharded = world > 1 and not args.replicas
+    xr_mode = "single"
+    if sharded:  # one beam of world x n particles, particle-sharded; per-kick exchanges over NVLink
+        ids = [HPSim.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        xr_mode = HPSim.init_sharding(rank, world, ids[0])
+    case = H.Case(lib, n=n * world if sharded else n, sc=True)
     ctx = case.beam._c
     nel = case.beamline.index(RANGE[1]) - case.beamline.index(RANGE[0]) + 1
 
@@ -216,6 +224,21 @@ def main():
 
     first, last = case.beamline.index(RANGE[0]), case.beamline.index(RANGE[1])
 
+    def timed(step_fn, steps):
+        """Per-step CUDA-event time on the context's stream; L2 flushed (384 MB memset) before each
+        step, outside the event pair; the step's own host-side submission overlaps its execution."""
+        total = 0.0
+        for _ in range(steps):
+            ctx.check(lib.hps_ctx_flush_l2(ctx.h))
+            barrier()
+            ctx.check(lib.hps_ctx_event_record(ctx.h, 0))
+            step_fn()
+            ctx.check(lib.hps_ctx_event_record(ctx.h, 1))
+            ms = C.c_double()
+            ctx.check(lib.hps_ctx_event_elapsed(ctx.h, 0, 1, C.byref(ms)))
+            total += ms.value * 1e-3
+        return total
+
     # ---- device-resident timing
     for _ in range(args.warmup):
         step_resident()
@@ -223,30 +246,25 @@ def main():
     l0 = lib.hps_ctx_launch_count(ctx.h)
     sampler = ClockSampler(local)
     sampler.start()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_resident()
-    barrier()
-    dt = time.perf_counter() - t0
+    dt = timed(step_resident, args.steps)
     launches = lib.hps_ctx_launch_count(ctx.h) - l0
-    # ---- end-to-end timing (host buffers)
-    for k in order:  # the download of a warm-up step must not clobber the input
-        pass
-    e2e_in = {k: pinned[k][1].copy() for k in order}
-    for _ in range(max(1, args.warmup // 2)):
-        for k in order:
-            pinned[k][1][:] = e2e_in[k]
-        step_e2e()
-    barrier()
-    te = 0.0
-    for _ in range(args.steps):
-        for k in order:
-            pinned[k][1][:] = e2e_in[k]
-        barrier()
-        t1 = time.perf_counter()
-        step_e2e()
-        barrier()
-        te += time.perf_counter() - t1
+    # ---- end-to-end timing (host buffers; upload + simulate + download inside the event pair)
+    te = None
+    if not args.no_e2e:
+        e2e_in = {k: pinned[k][1].copy() for k in order}
+
+        def e2e_once():
+            step_e2e()
+
+        for _ in range(max(1, args.warmup // 2)):
+            for k in order:  # the download of the previous step must not become this step's input
+                pinned[k][1][:] = e2e_in[k]
+            step_e2e()
+        te = 0.0
+        for _ in range(args.steps):
+            for k in order:
+                pinned[k][1][:] = e2e_in[k]
+            te += timed(e2e_once, 1)
     clocks = sampler.summary()
 
     # ---- one profiled step for the roofline of the dominant kernel
@@ -262,14 +280,14 @@ def main():
 
     if dist is not None:
         import torch
-        t = torch.tensor([dt, te], dtype=torch.float64)
+        t = torch.tensor([dt, te if te is not None else 0.0], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, te = float(t[0]), float(t[1])
+        dt, te = float(t[0]), (float(t[1]) if te is not None else None)
     if rank != 0:
         return
     total_particles = n * world
     value = total_particles * nel * args.steps / dt
-    e2e = total_particles * nel * args.steps / te
+    e2e = total_particles * nel * args.steps / te if te else None
     peak, peak_kind = peaks()
     seg = prof["segment"]
     seg_us = 1e3 * seg["ms"] / max(1, seg["launches"])
@@ -282,11 +300,16 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2: DTL tanks 1-4 (01QM00U->04QM30, 349 elements, %d SC kicks), %d particles/GPU, SCHEFF 32x128, "
                                "interval 0.025 m, adj_bunch 3; input = C1 DC beam tracked TBDB02->spch_comp_7 (untimed)" % (run["kicks"], n),
-                   "parallelism": "1 beam per GPU (replicas)" if world > 1 else "single GPU",
-                   "l2": "working set 56 B x %d = %.0f MB per sweep; < 126 MB L2 at 1 Mi particles (stated, not flushed)" % (n, 56 * n / 1e6),
+                   "parallelism": ("single GPU" if world == 1 else
+                                   "one beam of %d particles sharded over %d GPUs (contiguous index blocks); per kick 3 moment "
+                                   "exchanges + the 32 KB r-z mesh, mode=%s" % (n * world, world, xr_mode) if sharded else
+                                   "1 independent beam per GPU (replicas, no communication)"),
+                   "l2": "L2 flushed (384 MB memset) before every timed step; inside a step the %.0f MB beam is swept ~%d times "
+                         "and largely stays in the 126 MB L2 -- that is the workload" % (56 * n / 1e6, run["sweeps"] + 2 * run["kicks"]),
+                   "timing": "CUDA events on the context's stream around each step, summed over steps; max over ranks",
                    "run": run},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                "ms_per_step": 1e3 * te / args.steps},
+                "ms_per_step": 1e3 * te / args.steps if te else None},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_segment", "achieved": achieved, "peak": peak, "unit": "GB/s",

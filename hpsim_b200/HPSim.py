@@ -33,8 +33,7 @@ _ctx_cache = {}
 def _use_library(cdll):
     """Test hook: route this module through another implementation of the same C ABI."""
     global _backend
-    _backend = cdll
-    _ctx_cache.clear()
+    _backend = cdll  # contexts are cached per (library, device), so nothing has to be dropped here
 
 
 def _lib():
@@ -65,6 +64,23 @@ def set_gpu(gpu_id: int) -> None:
     """SetGPU (reference src/beamline/src/init.cpp:12-18): objects created afterwards live on this device."""
     global _device
     _device = int(gpu_id)
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id made on rank 0; the caller distributes it (no reference counterpart)."""
+    buf = C.create_string_buffer(128)
+    lib = _lib()
+    if lib.hps_comm_unique_id(buf) != K.OK:
+        raise K.HpsError(K.ERR_COMM, "cannot create an NCCL unique id")
+    return buf.raw
+
+
+def init_sharding(rank: int, nranks: int, unique_id: bytes) -> str:
+    """Particle-shard every Beam created afterwards over `nranks` processes (one GPU each, SPMD:
+    all ranks must issue the same HPSim calls in the same order).  Returns the exchange mode."""
+    c = _ctx()
+    c.check(c.lib.hps_ctx_comm_init(c.h, int(rank), int(nranks), C.create_string_buffer(unique_id, 128)))
+    return {0: "single", 1: "p2p", 2: "nccl"}[c.lib.hps_ctx_comm_mode(c.h)]
 
 
 # ------------------------------------------------------------------------------------------- DB

@@ -71,12 +71,16 @@ PROTOTYPES = {
     "hps_ctx_set_compat": (C.c_int, [_vp, C.c_int]),
     "hps_comm_unique_id": (C.c_int, [_vp]),
     "hps_ctx_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "hps_ctx_comm_mode": (C.c_int, [_vp]),
     "hps_ctx_synchronize": (C.c_int, [_vp]),
     "hps_host_alloc": (_vp, [C.c_size_t]),
     "hps_host_free": (None, [_vp]),
     "hps_ctx_launch_count": (C.c_uint64, [_vp]),
     "hps_ctx_set_profile": (C.c_int, [_vp, C.c_int]),
     "hps_ctx_get_profile": (C.c_int, [_vp, _vp, _vp]),
+    "hps_ctx_event_record": (C.c_int, [_vp, C.c_int]),
+    "hps_ctx_event_elapsed": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+    "hps_ctx_flush_l2": (C.c_int, [_vp]),
     "hps_beam_create": (_vp, [_vp, C.c_uint64, C.c_double, C.c_double, C.c_double]),
     "hps_beam_destroy": (None, [_vp]),
     "hps_beam_local_range": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

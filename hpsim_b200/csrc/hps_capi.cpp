@@ -49,6 +49,10 @@ struct hps_ctx {
   Op* h_ops = nullptr;  // pinned
   size_t ops_cap = 0;
   Comm comm;
+  // cross-rank exchange state of a particle-sharded beam (hps_ctx_comm_init)
+  XrView xr;
+  XrBox* xr_box = nullptr;
+  void* xr_mapped[HPS_XR_MAXR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   // optional per-launch timing (hps_ctx_set_profile): one event between consecutive launches
   int profile = 0;
@@ -56,6 +60,10 @@ struct hps_ctx {
   std::vector<int> prof_cls;
   double prof_ms[HPS_PROF_NCLASS] = {0, 0, 0, 0, 0};
   uint64_t prof_n[HPS_PROF_NCLASS] = {0, 0, 0, 0, 0};
+  // caller-visible timing events and the L2-flush scratch (bench.py)
+  cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  char* flush_buf = nullptr;
+  size_t flush_bytes = 0;
 };
 
 struct hps_beam {
@@ -127,7 +135,25 @@ LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
   l.grid_deposit = std::max(1u, std::min((b->n + 511) / 512, (unsigned)c->num_sms * 2));
   l.partials = c->partials;
   l.ticket = c->ticket;
+  l.xr = c->xr;
   return l;
+}
+
+// XR_NCCL: all-gather the partial vector the reducing kernel left in xr.send, then finish on the device
+int xr_after_reduce(hps_ctx* c, const LaunchCfg& l, int kind, int fin_mode, int do_policy, const StatReq* rq,
+                    const KickParams* kp, const BeamView& v, DevStats* st, ScDev* sc, double* bins) {
+  if (c->xr.mode != XR_NCCL) return HPS_OK;
+  if (comm_allgather(c->comm, c->xr.send, c->xr.recv, HPS_XR_NS * sizeof(double), c->stream))
+    return fail(c, HPS_ERR_COMM, "ncclAllGather of a reduction's partials failed");
+  FinReq f;
+  std::memset(&f, 0, sizeof(f));
+  f.kind = kind; f.fin_mode = fin_mode; f.do_policy = do_policy;
+  f.ns = reduce_slots(kind); f.max_mask = reduce_max_mask(kind);
+  if (rq) f.rq = *rq;
+  if (kp) f.kp = *kp;
+  launch_xr_finalize(l, f, v, st, sc, bins);
+  c->launches++;
+  return HPS_OK;
 }
 
 void carve(hps_beam* b, char* slab, double* c[6], u32** loss, u32** lloss) {
@@ -145,8 +171,11 @@ StatReq req(int kind, int a = 0, int bvar = -1, int good = 0, int out0 = 0) {
   return r;
 }
 void stat(hps_beam* b, const StatReq& r) {
-  launch_stat(cfg(b->ctx, b), view(b), b->st, r);
+  const LaunchCfg l = cfg(b->ctx, b);
+  const BeamView v = view(b);
+  launch_stat(l, v, b->st, r);
   b->ctx->launches++;
+  xr_after_reduce(b->ctx, l, FK_STAT, 0, 0, &r, nullptr, v, b->st, nullptr, nullptr);
 }
 void UpdateLoss(hps_beam* b) { stat(b, req(KS_COUNT_LOSS)); }
 void UpdateGoodParticleCount(hps_beam* b) { stat(b, req(KS_COUNT_GOOD, 0, -1, 1)); }
@@ -223,8 +252,11 @@ void UpdateStatForSpaceCharge(hps_beam* b) {
   std::memset(&kp, 0, sizeof(kp));
   kp.n_global = b->h.n_global; kp.mass = b->h.mass;
   launch_segment(l, v, nullptr, c->d_ops, c->d_opc, 0, FIN_KICK, 0, c->compat, b->st, nullptr, nullptr, kp);
+  xr_after_reduce(c, l, FK_SEGMENT, FIN_KICK, 0, nullptr, nullptr, v, b->st, nullptr, nullptr);
   launch_lloss_pass(l, v, b->st, nullptr);
+  xr_after_reduce(c, l, FK_LLOSS, 0, 0, nullptr, nullptr, v, b->st, nullptr, nullptr);
   launch_moments(l, v, b->st, nullptr, nullptr, kp, 0);
+  xr_after_reduce(c, l, FK_MOMENTS, 0, 0, nullptr, &kp, v, b->st, nullptr, nullptr);
   c->launches += 3;
 }
 
@@ -299,6 +331,8 @@ hps_ctx* hps_ctx_create(int device) {
   c->num_sms = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+  std::memset(&c->xr, 0, sizeof(c->xr));
+  c->xr.nranks = 1;
   if (const char* v = getenv("HPSIM_SEG_VARIANT")) c->seg_variant = atoi(v);
   int occ = ok ? segment_occupancy(c->seg_variant) : 0;
   if (occ < 1) occ = 1;
@@ -321,9 +355,14 @@ hps_ctx* hps_ctx_create(int device) {
 void hps_ctx_destroy(hps_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  for (void* p : c->xr_mapped) if (p) cudaIpcCloseMemHandle(p);
+  if (c->xr.seq) cudaFree(c->xr.seq);
+  cudaFree(c->xr_box); cudaFree(c->xr.bins_gather);
   comm_destroy(c->comm);
   cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_ops); cudaFree(c->d_opc); cudaFreeHost(c->h_ops);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->user_ev) if (e) cudaEventDestroy(e);
+  cudaFree(c->flush_buf);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -341,14 +380,93 @@ int hps_ctx_get_profile(hps_ctx* c, double* ms, uint64_t* n) {
   return HPS_OK;
 }
 
+int hps_ctx_event_record(hps_ctx* c, int slot) {
+  if (slot < 0 || slot >= 8) return fail(c, HPS_ERR_ARG, "event slot out of range");
+  cudaSetDevice(c->device);
+  if (!c->user_ev[slot]) CK(c, cudaEventCreate(&c->user_ev[slot]));
+  CK(c, cudaEventRecord(c->user_ev[slot], c->stream));
+  return HPS_OK;
+}
+int hps_ctx_event_elapsed(hps_ctx* c, int a, int b, double* ms) {
+  if (a < 0 || a >= 8 || b < 0 || b >= 8 || !c->user_ev[a] || !c->user_ev[b]) return fail(c, HPS_ERR_ARG, "event slot not recorded");
+  CK(c, cudaEventSynchronize(c->user_ev[b]));
+  float f = 0.f;
+  CK(c, cudaEventElapsedTime(&f, c->user_ev[a], c->user_ev[b]));
+  if (ms) *ms = f;
+  return HPS_OK;
+}
+int hps_ctx_flush_l2(hps_ctx* c) {
+  cudaSetDevice(c->device);
+  if (!c->flush_buf) {
+    c->flush_bytes = (size_t)384 << 20;  // 3x the 126 MB L2
+    CK(c, cudaMalloc(&c->flush_buf, c->flush_bytes));
+  }
+  CK(c, cudaMemsetAsync(c->flush_buf, 0x5a, c->flush_bytes, c->stream));
+  return HPS_OK;
+}
+
 int hps_comm_unique_id(void* out128) { return comm_unique_id(out128) ? HPS_ERR_COMM : HPS_OK; }
 int hps_ctx_comm_init(hps_ctx* c, int rank, int nranks, const void* id) {
   if (nranks <= 1) return HPS_OK;
+  if (nranks > HPS_XR_MAXR) return fail(c, HPS_ERR_ARG, "at most 8 ranks (one NVSwitch domain)");
+  if (c->comm.nranks > 1) return fail(c, HPS_ERR_STATE, "communicator already initialised");
   cudaSetDevice(c->device);
   std::string err;
   if (comm_init(c->comm, rank, nranks, id, &err)) return fail(c, HPS_ERR_COMM, err);
+  // exchange buffers: this rank's box, the NCCL staging vectors, the error word
+  XrView& x = c->xr;
+  std::memset(&x, 0, sizeof(x));
+  x.rank = rank; x.nranks = nranks;
+  char* misc = nullptr;  // [seq 2 x u64][err u32 + pad][send NS][recv R*NS]
+  const size_t misc_bytes = 32 + (size_t)(1 + nranks) * HPS_XR_NS * sizeof(double);
+  CK(c, cudaMalloc(&c->xr_box, sizeof(XrBox)));
+  CK(c, cudaMemset(c->xr_box, 0, sizeof(XrBox)));
+  CK(c, cudaMalloc(&misc, misc_bytes));
+  CK(c, cudaMemset(misc, 0, misc_bytes));
+  CK(c, cudaMalloc(&x.bins_gather, (size_t)nranks * HPS_XR_BINS_CAP * sizeof(double)));
+  x.seq = reinterpret_cast<unsigned long long*>(misc);
+  x.err = reinterpret_cast<u32*>(misc + 16);
+  x.send = reinterpret_cast<double*>(misc + 32);
+  x.recv = x.send + HPS_XR_NS;
+  CK(c, cudaDeviceSynchronize());
+  // map every peer's box (CUDA IPC; NVLink / NVSwitch peer access).  HPSIM_XR=nccl keeps to NCCL.
+  const char* want = getenv("HPSIM_XR");
+  bool p2p = !(want && std::strcmp(want, "nccl") == 0);
+  double ok = 1.0;
+  std::vector<cudaIpcMemHandle_t> handles(nranks);
+  if (p2p) {
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, c->xr_box) != cudaSuccess) { ok = 0.0; std::memset(&mine, 0, sizeof(mine)); cudaGetLastError(); }
+    char* d_h = nullptr;
+    CK(c, cudaMalloc(&d_h, (size_t)(nranks + 1) * sizeof(mine)));
+    CK(c, cudaMemcpyAsync(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+    if (comm_allgather(c->comm, d_h, d_h + sizeof(mine), sizeof(mine), c->stream))
+      return fail(c, HPS_ERR_COMM, "all-gather of the IPC handles failed");
+    CK(c, cudaMemcpyAsync(handles.data(), d_h + sizeof(mine), (size_t)nranks * sizeof(mine), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_h);
+    for (int r = 0; r < nranks && ok == 1.0; ++r) {
+      if (r == rank) { x.peer[r] = c->xr_box; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0.0; cudaGetLastError(); break; }
+      c->xr_mapped[r] = p;
+      x.peer[r] = reinterpret_cast<XrBox*>(p);
+    }
+    // every rank must have mapped every box, or all fall back to NCCL together
+    double* d_ok = x.send;
+    CK(c, cudaMemcpyAsync(d_ok, &ok, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (comm_allreduce_sum_f64(c->comm, d_ok, 1, c->stream)) return fail(c, HPS_ERR_COMM, "all-reduce failed");
+    double all_ok = 0.0;
+    CK(c, cudaMemcpyAsync(&all_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemsetAsync(x.send, 0, sizeof(double), c->stream));
+    p2p = all_ok == (double)nranks;
+  }
+  x.mode = p2p ? XR_P2P : XR_NCCL;
+  if (!p2p) x.peer[rank] = c->xr_box;
   return HPS_OK;
 }
+int hps_ctx_comm_mode(hps_ctx* c) { return c->xr.mode; }
 
 void* hps_host_alloc(size_t bytes) {
   void* p = nullptr;
@@ -580,8 +698,6 @@ int hps_beam_cut(hps_beam* b, int coord, double lo, double hi) {  // beam.cpp:15
 
 int hps_beam_update(hps_beam* b, int id) {
   cudaSetDevice(b->ctx->device);
-  if (b->ctx->comm.nranks > 1 && id != HPS_UPD_REL_PHI && id != HPS_UPD_REL_PHI_GOOD)
-    return fail(b->ctx, HPS_ERR_COMM, "hps_beam_update on a sharded beam is not supported in this round");
   switch (id) {
     case HPS_UPD_LOSS: UpdateLoss(b); break;
     case HPS_UPD_LLOSS: UpdateLongitudinalLoss(b); break;
@@ -668,12 +784,12 @@ static int scheff_alloc(hps_scheff* s) {
   KickParams kp;
   std::memset(&kp, 0, sizeof(kp));
   kp.nr = s->h.nr; kp.nz = s->h.nz;
-  CK(c, cudaMalloc(&s->bins, nb * sizeof(double)));
+  CK(c, cudaMalloc(&s->bins, (nb + 2) * sizeof(double)));  // + on-mesh count, max |phi| (sharded hand-off)
   CK(c, cudaMalloc(&s->field, nf * sizeof(double2)));
   CK(c, cudaMalloc(&s->field_part, nf * field_chunks(kp) * sizeof(double2)));
   CK(c, cudaMalloc(&s->field_tickets, (s->h.nr + 1) * sizeof(u32)));
   CK(c, cudaMemsetAsync(s->field_tickets, 0, (s->h.nr + 1) * sizeof(u32), c->stream));
-  CK(c, cudaMemsetAsync(s->bins, 0, nb * sizeof(double), c->stream));
+  CK(c, cudaMemsetAsync(s->bins, 0, (nb + 2) * sizeof(double), c->stream));
   CK(c, cudaMemsetAsync(s->field, 0, nf * sizeof(double2), c->stream));
   return HPS_OK;
 }
@@ -809,7 +925,6 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
   launch_prepare_ops(l, c->d_ops, c->d_opc, (int)nops, b->h.mass, b->h.charge);
   c->launches++;
   uint64_t sweeps = 0, extra = 0;
-  const bool sharded = c->comm.nranks > 1;
   CK(c, cudaEventRecord(c->ev0, c->stream));
   for (const Segment& s : plan.segs) {
     const int dirty = dirty_mask(plan.ops.data() + s.op_begin, s.op_count);
@@ -818,14 +933,28 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
                    sc ? sc->field : nullptr, s.kp);
     c->launches++;
     sweeps++;
+    if (s.fin_mode != FIN_NONE) {
+      int rc = xr_after_reduce(c, l, FK_SEGMENT, s.fin_mode, 0, nullptr, nullptr, v, b->st, sc ? sc->dev : nullptr, nullptr);
+      if (rc) return rc;
+    }
     if (!s.kick_follows) { extra++; continue; }
-    if (sharded) return fail(c, HPS_ERR_COMM, "sharded space-charge kick is not wired up yet");
     prof_mark(c, HPS_PROF_LLOSS);
     launch_lloss_pass(l, v, b->st, sc->dev);
+    int rc = xr_after_reduce(c, l, FK_LLOSS, 0, 0, nullptr, nullptr, v, b->st, sc->dev, nullptr);
+    if (rc) return rc;
     prof_mark(c, HPS_PROF_MOMENTS);
     launch_moments(l, v, b->st, sc->dev, sc->bins, s.kp, 1);
+    rc = xr_after_reduce(c, l, FK_MOMENTS, 0, 1, nullptr, &s.kp, v, b->st, sc->dev, sc->bins);
+    if (rc) return rc;
     prof_mark(c, HPS_PROF_DEPOSIT);
     cudaError_t e = launch_deposit(l, v, b->st, sc->dev, sc->bins, s.kp);
+    if (e == cudaSuccess && c->xr.mode == XR_NCCL) {
+      // the rank-local mesh is all-gathered on every kick (the remesh decision lives on the device);
+      // k_field folds the copies in rank order when it runs
+      const size_t bytes = ((size_t)s.kp.nr * s.kp.nz + 2) * sizeof(double);
+      if (comm_allgather(c->comm, sc->bins, c->xr.bins_gather, bytes, c->stream))
+        return fail(c, HPS_ERR_COMM, "ncclAllGather of the charge mesh failed");
+    }
     prof_mark(c, HPS_PROF_FIELD);
     if (e == cudaSuccess) e = launch_field(l, b->st, sc->dev, sc->bins, sc->field, sc->field_part, sc->field_tickets, s.kp);
     if (e != cudaSuccess) return fail(c, HPS_ERR_CUDA, std::string("kick launch: ") + cudaGetErrorString(e));
@@ -852,6 +981,11 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     out->extra_sweeps = extra;
     out->launches = c->launches - launches0;
     out->device_ms = ms;
+    if (c->xr.mode == XR_P2P) {
+      u32 xerr = 0;
+      CK(c, cudaMemcpy(&xerr, c->xr.err, sizeof(u32), cudaMemcpyDeviceToHost));
+      if (xerr) return fail(c, HPS_ERR_COMM, "a peer rank did not answer a cross-rank exchange within 20 s");
+    }
   }
   return HPS_OK;
 }

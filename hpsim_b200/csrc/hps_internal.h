@@ -105,6 +105,32 @@ struct BeamView {
   double mass, charge;
 };
 
+// ---- cross-rank exchange ("xr") for particle-sharded beams -------------------------
+// Every rank owns one XrBox in its own HBM; all ranks map every box (CUDA IPC over NVLink/NVSwitch).
+// A reduction's last block stores its rank-local partial vector into slot [rank] of EVERY peer's box,
+// publishes a sequence number, waits for the R slots of its own box and folds them in rank order --
+// so all ranks obtain bit-identical totals and every device-side decision stays rank-consistent.
+// Two parity buffers suffice: a rank can run at most one exchange ahead of its slowest peer.
+#define HPS_XR_MAXR 8
+#define HPS_XR_NS 16            // doubles per small-reduction slot (>= every kernel's NS)
+#define HPS_XR_BINS_CAP 25608   // nr*nz + 2 (count, max|phi|) doubles; 8*nr*nz <= 200 KB
+struct XrBox {
+  unsigned long long flag[2][HPS_XR_MAXR];       // sequence number of the data in data[parity][rank]
+  double data[2][HPS_XR_MAXR][HPS_XR_NS];
+  unsigned long long bflag[2][HPS_XR_MAXR];      // same for the charge mesh
+  double bins[2][HPS_XR_MAXR][HPS_XR_BINS_CAP];
+};
+enum XrMode { XR_NONE = 0, XR_P2P = 1, XR_NCCL = 2 };
+struct XrView {
+  int rank, nranks, mode;
+  XrBox* peer[HPS_XR_MAXR];      // XR_P2P: peer[r] = rank r's box mapped here (peer[rank] = own box)
+  unsigned long long* seq;       // device counter of small exchanges issued by this rank
+  double* send;                  // XR_NCCL: [HPS_XR_NS] partial vector handed to ncclAllGather
+  double* recv;                  //          [nranks][HPS_XR_NS] gathered vectors
+  double* bins_gather;           // XR_NCCL: [nranks][nb+2] gathered charge meshes
+  u32* err;                      // set non-zero when a peer did not answer in time
+};
+
 #define HPS_BLOCK 256
 #define HPS_NSLOT 16          // partial-sum slots per block
 #define HPS_FIELD_RS 4         // source rings per block of the field solve

@@ -121,7 +121,7 @@ template <int PPT, int MINB, bool FULL>
 __global__ void __launch_bounds__(HPS_BLOCK, MINB)
 k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
           DevStats* st, const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials,
-          u32* ticket) {
+          u32* ticket, const XrView xr) {
   __shared__ Op s_ops[HPS_MAX_SEG_OPS];
   __shared__ OpC s_opc[HPS_MAX_SEG_OPS];
   __shared__ KickCtx s_k;
@@ -223,11 +223,11 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
     }
   }
   if (fin_mode == FIN_NONE) return;
-  if (grid_reduce<SEG_NS>(acc, 1u << 2, partials, ticket, s_total, s_scratch)) {
+  if (grid_reduce<SEG_NS>(acc, 1u << 2, partials, ticket, s_total, s_scratch, xr)) {
     if (threadIdx.x == 0) finalize_segment(fin_mode, s_total, st, b.n_global);
   }
 }
-#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*
+#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*, const XrView
 template __global__ void k_segment<2, 2, false>(SEG_ARGS);
 template __global__ void k_segment<1, 3, false>(SEG_ARGS);
 template __global__ void k_segment<1, 4, false>(SEG_ARGS);
@@ -244,8 +244,17 @@ __global__ void k_prepare_ops(const Op* __restrict__ ops, OpC* opcs, int nops, d
 // ================================================================================================
 // Beam::UpdateLongitudinalLoss steps 3-4 + the recount of UpdateStatForSpaceCharge
 // (beam.cpp:776-782, 1007-1009; beam_kernel.cu:1549-1559).  slots: 0 n_good 1 sum phi good 2 n_lloss
+__device__ void finalize_lloss(const double* t, DevStats* st, ScDev* sc) {
+  const u32 ng = (u32)t[0];
+  st->num_good = ng;
+  st->v[HPS_STAT_PHI_AVG_GOOD] = ng > 0 ? t[1] / ng : -99999;
+  st->num_lloss = (u32)t[2];
+  st->need_lloss_pass = 0;
+  if (sc) sc->n_lloss_pass++;
+}
+
 __global__ void __launch_bounds__(HPS_BLOCK)
-k_lloss_pass(BeamView b, DevStats* st, ScDev* sc, double* partials, u32* ticket) {
+k_lloss_pass(BeamView b, DevStats* st, ScDev* sc, double* partials, u32* ticket, const XrView xr) {
   __shared__ double s_total[LL_NS];
   __shared__ double s_scratch[(HPS_BLOCK / 32) * LL_NS];
   if (st->need_lloss_pass == 0) return;
@@ -268,15 +277,8 @@ k_lloss_pass(BeamView b, DevStats* st, ScDev* sc, double* partials, u32* ticket)
       if (LL.y != 0) acc[2] += 1.0;
     }
   }
-  if (grid_reduce<LL_NS>(acc, 0u, partials, ticket, s_total, s_scratch)) {
-    if (threadIdx.x == 0) {
-      const u32 ng = (u32)s_total[0];
-      st->num_good = ng;
-      st->v[HPS_STAT_PHI_AVG_GOOD] = ng > 0 ? s_total[1] / ng : -99999;
-      st->num_lloss = (u32)s_total[2];
-      st->need_lloss_pass = 0;
-      if (sc) sc->n_lloss_pass++;
-    }
+  if (grid_reduce<LL_NS>(acc, 0u, partials, ticket, s_total, s_scratch, xr)) {
+    if (threadIdx.x == 0) finalize_lloss(s_total, st, sc);
   }
 }
 
@@ -336,9 +338,31 @@ __device__ void scheff_policy(DevStats* st, ScDev* sc, const KickParams& kp, dou
   }
 }
 
+// beam.cpp:1010-1015; finalisers beam_kernel.cu:1396-1446.  H4: surv uses the stale num_loss.
+__device__ void finalize_moments(const double* t, double ref, u32 n_global, DevStats* st, ScDev* sc, const KickParams& kp,
+                                 int do_policy) {
+  const double surv = (double)(u32)(n_global - st->num_loss);
+  const u32 ng = st->num_good;
+  st->phi_r_ref = ref;
+  st->v[HPS_STAT_PHI_AVG_R] = t[0] / surv;
+  {
+    const double avg = t[1] / ng, avg2 = t[2] / ng;
+    st->v[HPS_STAT_PHI_SIG_GOOD] = sqrt(avg2 - avg * avg);
+  }
+  {
+    const double xavg = t[3] / surv, x2avg = t[4] / surv, yavg = t[5] / surv, y2avg = t[6] / surv;
+    st->v[HPS_STAT_X_AVG_GOOD] = xavg;
+    st->v[HPS_STAT_X_SIG_GOOD] = sqrt(x2avg - xavg * xavg);
+    st->v[HPS_STAT_Y_AVG_GOOD] = yavg;
+    st->v[HPS_STAT_Y_SIG_GOOD] = sqrt(y2avg - yavg * yavg);
+  }
+  st->v[HPS_STAT_W_AVG_GOOD] = ng > 0 ? t[7] / ng : -99999;
+  if (do_policy) scheff_policy(st, sc, kp, t[8]);
+}
+
 __global__ void __launch_bounds__(HPS_BLOCK)
 k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, double* partials,
-          u32* ticket) {
+          u32* ticket, const XrView xr) {
   __shared__ double s_total[MOM_NS];
   __shared__ double s_scratch[(HPS_BLOCK / 32) * MOM_NS];
   const double ref = st->v[HPS_STAT_PHI_AVG_GOOD];
@@ -372,28 +396,8 @@ k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int 
       }
     }
   }
-  if (!grid_reduce<MOM_NS>(acc, 1u << 8, partials, ticket, s_total, s_scratch)) return;
-  if (threadIdx.x == 0) {
-    const double* t = s_total;
-    // beam.cpp:1010-1015; finalisers beam_kernel.cu:1396-1446.  H4: surv uses the stale num_loss.
-    const double surv = (double)(u32)(b.n_global - st->num_loss);
-    const u32 ng = st->num_good;
-    st->phi_r_ref = ref;
-    st->v[HPS_STAT_PHI_AVG_R] = t[0] / surv;
-    {
-      const double avg = t[1] / ng, avg2 = t[2] / ng;
-      st->v[HPS_STAT_PHI_SIG_GOOD] = sqrt(avg2 - avg * avg);
-    }
-    {
-      const double xavg = t[3] / surv, x2avg = t[4] / surv, yavg = t[5] / surv, y2avg = t[6] / surv;
-      st->v[HPS_STAT_X_AVG_GOOD] = xavg;
-      st->v[HPS_STAT_X_SIG_GOOD] = sqrt(x2avg - xavg * xavg);
-      st->v[HPS_STAT_Y_AVG_GOOD] = yavg;
-      st->v[HPS_STAT_Y_SIG_GOOD] = sqrt(y2avg - yavg * yavg);
-    }
-    st->v[HPS_STAT_W_AVG_GOOD] = ng > 0 ? t[7] / ng : -99999;
-    if (do_policy) scheff_policy(st, sc, kp, t[8]);
-  }
+  if (!grid_reduce<MOM_NS>(acc, 1u << 8, partials, ticket, s_total, s_scratch, xr)) return;
+  if (threadIdx.x == 0) finalize_moments(s_total, ref, b.n_global, st, sc, kp, do_policy);
   __syncthreads();
   if (do_policy && sc->remesh) {  // ResetBinTbl (space_charge.cu:92-105)
     const u32 nb = kp.nr * kp.nz;
@@ -408,7 +412,7 @@ k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int 
 // table; here each block accumulates a private fp64 copy in shared memory and flushes its non-zero
 // bins once.
 __global__ void __launch_bounds__(512)
-k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp) {
+k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, u32* ticket, const XrView xr) {
   extern __shared__ double s_bins[];
   if (!sc->remesh) return;
   const int nx = (int)kp.nr, nz = (int)kp.nz;
@@ -498,6 +502,37 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp) {
     if (cnt) atomicAdd(&sc->num_on_mesh, cnt);
     atomicMax(&sc->abs_phi_max_bits, (unsigned long long)__double_as_longlong(pmax));
   }
+  if (xr.nranks <= 1) return;
+  // Sharded beam: the rank's last block hands the rank-local mesh (+ on-mesh count, max |phi|) to every
+  // peer; k_field folds the R meshes in rank order.  XR_P2P: stores into the peers' boxes over NVLink,
+  // sequence number = this context's mesh hand-off counter xr.seq[1].  XR_NCCL: the two scalars are appended and the host all-gathers.
+  __shared__ u32 s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double cnt_d = (double)__ldcg(&sc->num_on_mesh);
+  const double pmax_d = __longlong_as_double((long long)__ldcg(&sc->abs_phi_max_bits));
+  if (xr.mode == XR_P2P) {
+    __shared__ unsigned long long s_seq;
+    if (threadIdx.x == 0) { s_seq = xr.seq[1] + 1ull; xr.seq[1] = s_seq; }  // k_field reads it back
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const int par = (int)(seq & 1ull);
+    for (u32 k = threadIdx.x; k < nb + 2; k += blockDim.x) {
+      const double v = k < nb ? __ldcg(&bins[k]) : (k == nb ? cnt_d : pmax_d);
+      for (int p = 0; p < xr.nranks; ++p) *(volatile double*)&xr.peer[p]->bins[par][xr.rank][k] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < xr.nranks) st_release_sys(&xr.peer[threadIdx.x]->bflag[par][xr.rank], seq);
+  } else if (threadIdx.x == 0) {
+    bins[nb] = cnt_d;
+    bins[nb + 1] = pmax_d;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // ================================================================================================
@@ -519,7 +554,7 @@ __device__ __forceinline__ void ellip_ke(double g, double& ee, double& ek) {
 // the previous one-block-per-rp version ran on 33 SMs only.
 __global__ void __launch_bounds__(1024)
 k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, double2* part, u32* tickets,
-        KickParams kp) {
+        KickParams kp, const XrView xr) {
   extern __shared__ double s_mem[];
   if (!sc->remesh) return;
   const u32 nr = kp.nr, nz = kp.nz;
@@ -529,12 +564,43 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
   double* s_b = s_mem;                                                       // [RS][nz]
   double2* s_g = reinterpret_cast<double2*>(s_mem + HPS_FIELD_RS * nz);      // [RS][nz]
   double2* s_red = s_g + HPS_FIELD_RS * nz;                                  // [blockDim.x]
-  if (irp == 0 && ch == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
-    st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
-
-  for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
-    const u32 k = e / nz, zs = e % nz;
-    s_b[k * nz + zs] = bins[zs * nr + rs0 + k];
+  if (xr.nranks <= 1) {
+    if (irp == 0 && ch == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
+      st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
+    for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
+      const u32 k = e / nz, zs = e % nz;
+      s_b[k * nz + zs] = bins[zs * nr + rs0 + k];
+    }
+  } else {
+    // sharded beam: fold the R rank-local meshes in rank order (bit-identical on every rank)
+    const u32 nb = nr * nz;
+    const double* slot[HPS_XR_MAXR];
+    if (xr.mode == XR_P2P) {
+      const unsigned long long seq = xr.seq[1];  // advanced by this rank's k_deposit just before
+      const int par = (int)(seq & 1ull);
+      const XrBox* own = xr.peer[xr.rank];
+      if ((int)threadIdx.x < xr.nranks) xr_wait(&own->bflag[par][threadIdx.x], seq, xr.err);
+      __syncthreads();
+      for (int r = 0; r < xr.nranks; ++r) slot[r] = own->bins[par][r];
+    } else {
+      for (int r = 0; r < xr.nranks; ++r) slot[r] = xr.bins_gather + (size_t)r * (nb + 2);
+    }
+    for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
+      const u32 k = e / nz, zs = e % nz;
+      double a = *(const volatile double*)&slot[0][zs * nr + rs0 + k];
+      for (int r = 1; r < xr.nranks; ++r) a += *(const volatile double*)&slot[r][zs * nr + rs0 + k];
+      s_b[k * nz + zs] = a;
+    }
+    if (irp == 0 && ch == 0 && threadIdx.x == 0) {
+      u32 cnt = 0;
+      double pm = 0.0;
+      for (int r = 0; r < xr.nranks; ++r) {
+        cnt += (u32)*(const volatile double*)&slot[r][nb];
+        pm = fmax(pm, *(const volatile double*)&slot[r][nb + 1]);
+      }
+      sc->num_on_mesh = cnt;
+      if (sc->adj_bunch != 0) st->v[HPS_STAT_ABS_PHI_MAX] = pm;
+    }
   }
   {
     const double beta = sc->beta;
@@ -662,49 +728,7 @@ __device__ __forceinline__ double pick(const BeamView& b, int var, u32 i, double
   }
 }
 
-// slots: 0 count(filter passes) 1 sum a 2 sum a^2 3 sum b 4 sum b^2 5 sum ab 6 MAX 7 MAX
-__global__ void __launch_bounds__(HPS_BLOCK)
-k_stat(BeamView b, DevStats* st, StatReq rq, double* partials, u32* ticket) {
-  __shared__ double s_total[STAT_NS];
-  __shared__ double s_scratch[(HPS_BLOCK / 32) * STAT_NS];
-  const double phi_ref = st->phi_r_ref;
-  const double xa = st->v[HPS_STAT_X_AVG], ya = st->v[HPS_STAT_Y_AVG], pa = st->v[HPS_STAT_PHI_AVG_R];
-  const double thr = st->v[HPS_STAT_PHI_AVG_GOOD] + K_TWOPI + K_PI;
-  double acc[STAT_NS];
-#pragma unroll
-  for (int s = 0; s < STAT_NS; ++s) acc[s] = 0.0;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x) {
-    const u32 l = b.loss[i];
-    u32 ll = b.lloss[i];
-    if (rq.kind == KS_MARK_LLOSS) {  // beam_kernel.cu:1549-1559
-      if (b.phi[i] > thr && ll != 1u) { ll = 1u; b.lloss[i] = 1u; }
-      if (ll != 0) acc[0] += 1.0;
-      continue;
-    }
-    if (rq.kind == KS_COUNT_LOSS) { if (l != 0) acc[0] += 1.0; continue; }
-    if (rq.kind == KS_COUNT_LLOSS) { if (ll != 0) acc[0] += 1.0; continue; }
-    const bool pass = rq.good_only ? (l + ll == 0) : (l == 0);
-    if (!pass) continue;
-    acc[0] += 1.0;
-    if (rq.kind == KS_COUNT_GOOD) continue;
-    if (rq.kind == KS_MAX_R_PHI) {  // beam_kernel.cu:792-932
-      const double tx = b.x[i] - xa, ty = b.y[i] - ya;
-      double tp = rel_phi(b.phi[i], phi_ref) - pa;
-      tp = tp > 0.0 ? tp : -tp;
-      acc[6] = fmax(acc[6], tx * tx + ty * ty);
-      acc[7] = fmax(acc[7], tp);
-      continue;
-    }
-    const double a = pick(b, rq.var_a, i, phi_ref);
-    acc[1] += a; acc[2] += a * a;
-    if (rq.var_b >= 0) {
-      const double c = pick(b, rq.var_b, i, phi_ref);
-      acc[3] += c; acc[4] += c * c; acc[5] += a * c;
-    }
-  }
-  if (!grid_reduce<STAT_NS>(acc, (1u << 6) | (1u << 7), partials, ticket, s_total, s_scratch)) return;
-  if (threadIdx.x != 0) return;
-  const double* t = s_total;
+__device__ void finalize_stat(const double* t, const BeamView& b, DevStats* st, const StatReq& rq) {
   const double surv = (double)(u32)(b.n_global - st->num_loss);
   switch (rq.kind) {
     case KS_COUNT_LOSS: st->num_loss = (u32)t[0]; break;
@@ -753,6 +777,85 @@ k_stat(BeamView b, DevStats* st, StatReq rq, double* partials, u32* ticket) {
   }
 }
 
+// slots: 0 count(filter passes) 1 sum a 2 sum a^2 3 sum b 4 sum b^2 5 sum ab 6 MAX 7 MAX
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_stat(BeamView b, DevStats* st, StatReq rq, double* partials, u32* ticket, const XrView xr) {
+  __shared__ double s_total[STAT_NS];
+  __shared__ double s_scratch[(HPS_BLOCK / 32) * STAT_NS];
+  const double phi_ref = st->phi_r_ref;
+  const double xa = st->v[HPS_STAT_X_AVG], ya = st->v[HPS_STAT_Y_AVG], pa = st->v[HPS_STAT_PHI_AVG_R];
+  const double thr = st->v[HPS_STAT_PHI_AVG_GOOD] + K_TWOPI + K_PI;
+  double acc[STAT_NS];
+#pragma unroll
+  for (int s = 0; s < STAT_NS; ++s) acc[s] = 0.0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x) {
+    const u32 l = b.loss[i];
+    u32 ll = b.lloss[i];
+    if (rq.kind == KS_MARK_LLOSS) {  // beam_kernel.cu:1549-1559
+      if (b.phi[i] > thr && ll != 1u) { ll = 1u; b.lloss[i] = 1u; }
+      if (ll != 0) acc[0] += 1.0;
+      continue;
+    }
+    if (rq.kind == KS_COUNT_LOSS) { if (l != 0) acc[0] += 1.0; continue; }
+    if (rq.kind == KS_COUNT_LLOSS) { if (ll != 0) acc[0] += 1.0; continue; }
+    const bool pass = rq.good_only ? (l + ll == 0) : (l == 0);
+    if (!pass) continue;
+    acc[0] += 1.0;
+    if (rq.kind == KS_COUNT_GOOD) continue;
+    if (rq.kind == KS_MAX_R_PHI) {  // beam_kernel.cu:792-932
+      const double tx = b.x[i] - xa, ty = b.y[i] - ya;
+      double tp = rel_phi(b.phi[i], phi_ref) - pa;
+      tp = tp > 0.0 ? tp : -tp;
+      acc[6] = fmax(acc[6], tx * tx + ty * ty);
+      acc[7] = fmax(acc[7], tp);
+      continue;
+    }
+    const double a = pick(b, rq.var_a, i, phi_ref);
+    acc[1] += a; acc[2] += a * a;
+    if (rq.var_b >= 0) {
+      const double c = pick(b, rq.var_b, i, phi_ref);
+      acc[3] += c; acc[4] += c * c; acc[5] += a * c;
+    }
+  }
+  if (!grid_reduce<STAT_NS>(acc, (1u << 6) | (1u << 7), partials, ticket, s_total, s_scratch, xr)) return;
+  if (threadIdx.x == 0) finalize_stat(s_total, b, st, rq);
+}
+
+// ================================================================================================
+// XR_NCCL only: fold the all-gathered rank partials in rank order and run the finaliser that the
+// XR_P2P / single-GPU path runs inside the reducing kernel's last block
+// ================================================================================================
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_xr_finalize(const XrView xr, FinReq f, BeamView b, DevStats* st, ScDev* sc, double* bins) {
+  __shared__ double s_t[HPS_XR_NS];
+  if (f.kind == FK_LLOSS && st->need_lloss_pass == 0) return;  // k_lloss_pass did not run either
+  if ((int)threadIdx.x < f.ns) {
+    const int s = threadIdx.x;
+    const bool mx = (f.max_mask >> s) & 1u;
+    double a = xr.recv[s];
+    for (int r = 1; r < xr.nranks; ++r) {
+      const double t = xr.recv[r * HPS_XR_NS + s];
+      a = mx ? fmax(a, t) : a + t;
+    }
+    s_t[s] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    switch (f.kind) {
+      case FK_SEGMENT: finalize_segment(f.fin_mode, s_t, st, b.n_global); break;
+      case FK_LLOSS: finalize_lloss(s_t, st, sc); break;
+      case FK_MOMENTS: finalize_moments(s_t, st->v[HPS_STAT_PHI_AVG_GOOD], b.n_global, st, sc, f.kp, f.do_policy); break;
+      case FK_STAT: finalize_stat(s_t, b, st, f.rq); break;
+      default: break;
+    }
+  }
+  __syncthreads();
+  if (f.kind == FK_MOMENTS && f.do_policy && sc->remesh) {
+    const u32 nb = f.kp.nr * f.kp.nz;
+    for (u32 k = threadIdx.x; k < nb; k += blockDim.x) bins[k] = 0.0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------
@@ -794,26 +897,26 @@ void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, c
   for (int k = 0; k < nops; ++k) full |= host_ops[k].type == OP_DIPOLE_FIRST || host_ops[k].type == OP_DIPOLE_SECOND || host_ops[k].type == OP_BUNCHER;
   const unsigned grid1 = c.grid_seg1, grid2 = c.grid_seg;
   if (full) {
-    k_segment<1, 3, true><<<grid1, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+    k_segment<1, 3, true><<<grid1, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr);
     return;
   }
   switch (c.seg_variant) {
     case 1:
-      k_segment<1, 3, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+      k_segment<1, 3, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr);
       break;
     case 2:
-      k_segment<1, 4, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+      k_segment<1, 4, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr);
       break;
     default:
-      k_segment<2, 2, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket);
+      k_segment<2, 2, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr);
   }
 }
 void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
-  k_lloss_pass<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, c.partials, c.ticket);
+  k_lloss_pass<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, c.partials, c.ticket, c.xr);
 }
 void launch_moments(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins, const KickParams& kp,
                     int do_policy) {
-  k_moments<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, bins, kp, do_policy, c.partials, c.ticket);
+  k_moments<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, bins, kp, do_policy, c.partials, c.ticket, c.xr);
 }
 size_t deposit_smem(const KickParams& kp) { return (size_t)kp.nr * kp.nz * sizeof(double); }
 size_t field_smem(const KickParams& kp, int threads) {
@@ -834,7 +937,7 @@ cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, 
     if (e != cudaSuccess) return e;
     g_deposit_smem_set = 1;
   }
-  k_deposit<<<c.grid_deposit, 512, smem, c.stream>>>(b, st, sc, bins, kp);
+  k_deposit<<<c.grid_deposit, 512, smem, c.stream>>>(b, st, sc, bins, kp, c.ticket + 1, c.xr);
   return cudaSuccess;
 }
 cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const double* bins, double2* field, double2* part,
@@ -846,11 +949,30 @@ cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const doub
     if (e != cudaSuccess) return e;
     g_field_smem_set = 1;
   }
-  k_field<<<dim3(kp.nr + 1, field_chunks(kp)), threads, smem, c.stream>>>(st, sc, bins, field, part, tickets, kp);
+  k_field<<<dim3(kp.nr + 1, field_chunks(kp)), threads, smem, c.stream>>>(st, sc, bins, field, part, tickets, kp, c.xr);
   return cudaSuccess;
 }
 void launch_stat(const LaunchCfg& c, const BeamView& b, DevStats* st, const StatReq& rq) {
-  k_stat<<<c.grid_single, HPS_BLOCK, 0, c.stream>>>(b, st, rq, c.partials, c.ticket);
+  k_stat<<<c.grid_single, HPS_BLOCK, 0, c.stream>>>(b, st, rq, c.partials, c.ticket, c.xr);
+}
+void launch_xr_finalize(const LaunchCfg& c, const FinReq& f, const BeamView& b, DevStats* st, ScDev* sc, double* bins) {
+  k_xr_finalize<<<1, HPS_BLOCK, 0, c.stream>>>(c.xr, f, b, st, sc, bins);
+}
+int reduce_slots(int kind) {
+  switch (kind) {
+    case FK_SEGMENT: return SEG_NS;
+    case FK_LLOSS: return LL_NS;
+    case FK_MOMENTS: return MOM_NS;
+    default: return STAT_NS;
+  }
+}
+unsigned reduce_max_mask(int kind) {
+  switch (kind) {
+    case FK_SEGMENT: return 1u << 2;
+    case FK_MOMENTS: return 1u << 8;
+    case FK_STAT: return (1u << 6) | (1u << 7);
+    default: return 0u;
+  }
 }
 void launch_set_phi_ref(const LaunchCfg& c, const BeamView& b, DevStats* st, int use_good, double phi0) {
   k_set_phi_ref<<<1, 1, 0, c.stream>>>(b, st, use_good, phi0);

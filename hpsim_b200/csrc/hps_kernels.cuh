@@ -38,11 +38,72 @@ __device__ __forceinline__ void warp_reduce(double (&v)[NS], unsigned max_mask) 
   }
 }
 
-// Returns true in every thread of the block that finished last; `total` (shared) then holds the
-// grid-wide result of every slot.  partials: [gridDim.x][NS].
+// ---- cross-rank exchange over peer memory (XrBox, hps_internal.h) ------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define HPS_XR_TIMEOUT_NS 20000000000ull  // a peer that stays silent this long is reported, not waited for
+
+// Spins until flag == seq (written by a peer GPU through NVLink into this rank's box).
+__device__ __forceinline__ void xr_wait(const unsigned long long* flag, unsigned long long seq, u32* err) {
+  if (ld_acquire_sys(flag) == seq) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) != seq) {
+    if (global_ns() - t0 > HPS_XR_TIMEOUT_NS) { *err = 1u; return; }
+  }
+}
+
+// All threads of ONE block (the rank's last block) call this with the rank-local totals in shared
+// memory; on return total[] holds the fold over all ranks in rank order (bit-identical everywhere).
+__device__ __forceinline__ void xr_exchange_p2p(double* total, int ns, unsigned max_mask, const XrView& xr) {
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) { s_seq = *xr.seq + 1ull; *xr.seq = s_seq; }
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int par = (int)(seq & 1ull);
+  for (int t = threadIdx.x; t < xr.nranks * ns; t += blockDim.x) {
+    const int p = t / ns, s = t - p * ns;
+    *(volatile double*)&xr.peer[p]->data[par][xr.rank][s] = total[s];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < xr.nranks) {
+    st_release_sys(&xr.peer[threadIdx.x]->flag[par][xr.rank], seq);
+    xr_wait(&xr.peer[xr.rank]->flag[par][threadIdx.x], seq, xr.err);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < ns) {
+    const int s = threadIdx.x;
+    const bool mx = (max_mask >> s) & 1u;
+    const XrBox* own = xr.peer[xr.rank];
+    double a = *(const volatile double*)&own->data[par][0][s];
+    for (int r = 1; r < xr.nranks; ++r) {
+      const double t = *(const volatile double*)&own->data[par][r][s];
+      a = mx ? fmax(a, t) : a + t;
+    }
+    total[s] = a;
+  }
+  __syncthreads();
+}
+
+// Returns true in every thread of the block that finished last AND owns the final totals; `total`
+// (shared) then holds the result of every slot over the whole (possibly sharded) beam.
+// partials: [gridDim.x][NS].  XR_NCCL: the last block only hands its totals to xr.send and returns
+// false; the host then enqueues an all-gather and k_xr_finalize.
 template <int NS>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, double* partials, u32* ticket,
-                                            double* total /* shared, NS */, double* scratch /* shared, 32*NS */) {
+                                            double* total /* shared, NS */, double* scratch /* shared, 32*NS */,
+                                            const XrView& xr) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   warp_reduce<NS>(v, max_mask);
   if (lane == 0) {
@@ -83,6 +144,11 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, 
   }
   if (threadIdx.x == 0) *ticket = 0u;
   __syncthreads();
+  if (xr.mode == XR_P2P) xr_exchange_p2p(total, NS, max_mask, xr);
+  else if (xr.mode == XR_NCCL) {
+    if (threadIdx.x < NS) xr.send[threadIdx.x] = total[threadIdx.x];
+    return false;
+  }
   return true;
 }
 

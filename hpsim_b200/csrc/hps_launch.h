@@ -16,7 +16,8 @@ struct LaunchCfg {
   unsigned grid_single;   // grid of the 1-particle-per-thread API statistics kernel
   unsigned grid_deposit;
   double* partials;       // [max grid][HPS_NSLOT]
-  u32* ticket;
+  u32* ticket;            // [0] reductions, [1] deposit hand-off (sharded beams)
+  XrView xr;              // cross-rank exchange of a particle-sharded beam (mode XR_NONE otherwise)
 };
 
 enum StatKind {
@@ -30,6 +31,18 @@ struct StatReq {
   int out[5];
   double w_ref;       // w[0] for the emittance normalisation (beam_kernel.cu:1345)
 };
+
+// XR_NCCL: what k_xr_finalize has to finish after the all-gather of a reducing kernel's partials
+enum FinKind { FK_SEGMENT = 0, FK_LLOSS, FK_MOMENTS, FK_STAT };
+struct FinReq {
+  int kind, fin_mode, do_policy, ns;
+  unsigned max_mask;
+  StatReq rq;
+  KickParams kp;
+};
+void launch_xr_finalize(const LaunchCfg&, const FinReq&, const BeamView&, DevStats*, ScDev*, double* bins);
+int reduce_slots(int kind);
+unsigned reduce_max_mask(int kind);
 
 void launch_prepare_ops(const LaunchCfg&, const Op* ops, OpC* opcs, int nops, double mass, double charge);
 void launch_segment(const LaunchCfg&, const BeamView&, const Op* host_ops, const Op* ops, const OpC* opcs, int nops,

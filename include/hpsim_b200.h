@@ -105,6 +105,9 @@ int hps_ctx_set_compat(hps_ctx*, int compat_reference);
  * (bench.py uses torch.distributed for that and nothing else). */
 int hps_comm_unique_id(void* out128);
 int hps_ctx_comm_init(hps_ctx*, int rank, int nranks, const void* nccl_unique_id);
+/* 0 = single rank, 1 = in-kernel exchange over peer memory (CUDA IPC, NVLink), 2 = NCCL all-gather
+ * between kernels (fallback when the peer mapping is unavailable, or HPSIM_XR=nccl). */
+int hps_ctx_comm_mode(hps_ctx*);
 
 /* Pinned host staging buffers for hps_beam_upload / hps_beam_download (optional: any host pointer
  * works, pinned ones copy at full PCIe rate), and the number of kernels this context has launched
@@ -118,6 +121,12 @@ uint64_t hps_ctx_launch_count(hps_ctx*);
 enum { HPS_PROF_SEGMENT = 0, HPS_PROF_LLOSS, HPS_PROF_MOMENTS, HPS_PROF_DEPOSIT, HPS_PROF_FIELD, HPS_PROF_NCLASS };
 int hps_ctx_set_profile(hps_ctx*, int on);
 int hps_ctx_get_profile(hps_ctx*, double* ms, uint64_t* n);
+/* Device timing for callers (bench.py): record CUDA event `slot` (0..7) on the context's stream;
+ * elapsed() synchronises on event b and returns the milliseconds between two recorded slots.
+ * hps_ctx_flush_l2 overwrites a scratch buffer larger than the 126 MB L2 on the same stream. */
+int hps_ctx_event_record(hps_ctx*, int slot);
+int hps_ctx_event_elapsed(hps_ctx*, int slot_a, int slot_b, double* ms);
+int hps_ctx_flush_l2(hps_ctx*);
 
 /* ---- beam ---------------------------------------------------------------- */
 /* Replaces Beam::Beam(num, mass, charge, current) + AllocateBeam

@@ -1151,11 +1151,15 @@ int hps_comm_unique_id(void*) { return HPS_ERR_COMM; }
 int hps_ctx_comm_init(hps_ctx* c, int, int nranks, const void*) {
   return nranks == 1 ? HPS_OK : fail(c, HPS_ERR_COMM, "the CPU oracle is single-process");
 }
+int hps_ctx_comm_mode(hps_ctx*) { return 0; }
 int hps_ctx_synchronize(hps_ctx*) { return HPS_OK; }
 void* hps_host_alloc(size_t bytes) { return std::malloc(bytes); }
 void hps_host_free(void* p) { std::free(p); }
 uint64_t hps_ctx_launch_count(hps_ctx*) { return 0; }
 int hps_ctx_set_profile(hps_ctx*, int) { return HPS_OK; }
+int hps_ctx_event_record(hps_ctx*, int) { return HPS_OK; }
+int hps_ctx_event_elapsed(hps_ctx*, int, int, double* ms) { if (ms) *ms = 0.0; return HPS_OK; }
+int hps_ctx_flush_l2(hps_ctx*) { return HPS_OK; }
 int hps_ctx_get_profile(hps_ctx*, double* ms, uint64_t* n) {
   for (int k = 0; k < HPS_PROF_NCLASS; ++k) { ms[k] = 0.0; n[k] = 0; }
   return HPS_OK;
