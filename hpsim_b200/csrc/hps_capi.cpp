@@ -132,7 +132,7 @@ LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
   l.grid_seg1 = std::max(1u, std::min((b->n + HPS_BLOCK - 1) / HPS_BLOCK, c->seg_grid_cap_full));
   l.grid_pairs = std::max(1u, std::min((pairs + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
   l.grid_single = std::max(1u, std::min((b->n + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
-  l.grid_deposit = std::max(1u, std::min((b->n + 511) / 512, (unsigned)c->num_sms * 2));
+  l.grid_deposit = std::max(1u, std::min((pairs + 511) / 512, (unsigned)c->num_sms * 2));
   l.partials = c->partials;
   l.ticket = c->ticket;
   l.xr = c->xr;
@@ -255,7 +255,7 @@ void UpdateStatForSpaceCharge(hps_beam* b) {
   xr_after_reduce(c, l, FK_SEGMENT, FIN_KICK, 0, nullptr, nullptr, v, b->st, nullptr, nullptr);
   launch_lloss_pass(l, v, b->st, nullptr);
   xr_after_reduce(c, l, FK_LLOSS, 0, 0, nullptr, nullptr, v, b->st, nullptr, nullptr);
-  launch_moments(l, v, b->st, nullptr, nullptr, kp, 0);
+  launch_moments(l, v, b->st, nullptr, nullptr, kp, 0, 0);
   xr_after_reduce(c, l, FK_MOMENTS, 0, 0, nullptr, &kp, v, b->st, nullptr, nullptr);
   c->launches += 3;
 }
@@ -338,8 +338,9 @@ hps_ctx* hps_ctx_create(int device) {
   if (occ < 1) occ = 1;
   c->seg_grid_cap = (unsigned)c->num_sms * (unsigned)occ;
   c->seg_grid_cap_full = (unsigned)c->num_sms * (unsigned)std::max(1, ok ? segment_occupancy(-1) : 1);
-  c->max_grid = (unsigned)c->num_sms * 6u;
-  ok = ok && cudaMalloc(&c->partials, (size_t)c->max_grid * HPS_NSLOT * sizeof(double)) == cudaSuccess &&
+  // the pair sweeps (K2/K3) hold a grid barrier: every block must be resident
+  c->max_grid = (unsigned)c->num_sms * (unsigned)std::max(1, std::min(4, ok ? moments_occupancy() : 1));
+  ok = ok && cudaMalloc(&c->partials, (size_t)c->num_sms * 8 * HPS_NSLOT * sizeof(double)) == cudaSuccess &&
        cudaMalloc(&c->ticket, 256) == cudaSuccess && cudaMemset(c->ticket, 0, 256) == cudaSuccess;
   c->ops_cap = 4096;
   ok = ok && cudaMalloc(&c->d_ops, c->ops_cap * sizeof(Op)) == cudaSuccess &&
@@ -870,6 +871,14 @@ int hps_scheff_download_tables(hps_scheff* s, double* bins, double* field, doubl
   ScDev h;
   CK(c, cudaMemcpyAsync(&h, s->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  if (bins) {  // the device mesh is 64-bit fixed point (k_deposit): scale 2^-38
+    const size_t nb = (size_t)s->h.nr * s->h.nz;
+    for (size_t k = 0; k < nb; ++k) {
+      long long q;
+      std::memcpy(&q, &bins[k], sizeof(q));
+      bins[k] = (double)q / 274877906944.0;
+    }
+  }
   if (dr_dz) { dr_dz[0] = h.dr; dr_dz[1] = h.dz; }
   return HPS_OK;
 }
@@ -938,12 +947,17 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
       if (rc) return rc;
     }
     if (!s.kick_follows) { extra++; continue; }
-    prof_mark(c, HPS_PROF_LLOSS);
-    launch_lloss_pass(l, v, b->st, sc->dev);
-    int rc = xr_after_reduce(c, l, FK_LLOSS, 0, 0, nullptr, nullptr, v, b->st, sc->dev, nullptr);
-    if (rc) return rc;
+    int rc = HPS_OK;
+    const int merged = c->xr.mode != XR_NCCL;  // K2 rides inside K3 (grid barrier) unless its finaliser is a separate kernel
+    if (!merged) {
+      prof_mark(c, HPS_PROF_LLOSS);
+      launch_lloss_pass(l, v, b->st, sc->dev);
+      c->launches++;
+      rc = xr_after_reduce(c, l, FK_LLOSS, 0, 0, nullptr, nullptr, v, b->st, sc->dev, nullptr);
+      if (rc) return rc;
+    }
     prof_mark(c, HPS_PROF_MOMENTS);
-    launch_moments(l, v, b->st, sc->dev, sc->bins, s.kp, 1);
+    launch_moments(l, v, b->st, sc->dev, sc->bins, s.kp, 1, merged);
     rc = xr_after_reduce(c, l, FK_MOMENTS, 0, 1, nullptr, &s.kp, v, b->st, sc->dev, sc->bins);
     if (rc) return rc;
     prof_mark(c, HPS_PROF_DEPOSIT);
@@ -958,7 +972,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     prof_mark(c, HPS_PROF_FIELD);
     if (e == cudaSuccess) e = launch_field(l, b->st, sc->dev, sc->bins, sc->field, sc->field_part, sc->field_tickets, s.kp);
     if (e != cudaSuccess) return fail(c, HPS_ERR_CUDA, std::string("kick launch: ") + cudaGetErrorString(e));
-    c->launches += 4;
+    c->launches += 3;
   }
   CK(c, cudaEventRecord(c->ev1, c->stream));
   CK(c, cudaGetLastError());

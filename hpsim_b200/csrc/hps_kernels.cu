@@ -1,4 +1,5 @@
 // hps_kernels.cu -- __global__ kernels + their launch wrappers (see hps_launch.h).
+#include <algorithm>
 #include "hps_kernels.cuh"
 #include "hps_launch.h"
 
@@ -121,13 +122,13 @@ template <int PPT, int MINB, bool FULL>
 __global__ void __launch_bounds__(HPS_BLOCK, MINB)
 k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
           DevStats* st, const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials,
-          u32* ticket, const XrView xr) {
+          u32* ticket, const __grid_constant__ XrView xr) {
   __shared__ Op s_ops[HPS_MAX_SEG_OPS];
   __shared__ OpC s_opc[HPS_MAX_SEG_OPS];
   __shared__ KickCtx s_k;
   __shared__ double s_cxy[2];
   __shared__ double s_total[SEG_NS];
-  __shared__ double s_scratch[(HPS_BLOCK / 32) * SEG_NS];
+  __shared__ double s_scratch[HPS_BLOCK];
 
   {  // stage the segment's op records (block-uniform) in shared memory
     const int nw = nops * (int)(sizeof(Op) / sizeof(double));
@@ -227,7 +228,7 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
     if (threadIdx.x == 0) finalize_segment(fin_mode, s_total, st, b.n_global);
   }
 }
-#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*, const XrView
+#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*, const __grid_constant__ XrView
 template __global__ void k_segment<2, 2, false>(SEG_ARGS);
 template __global__ void k_segment<1, 3, false>(SEG_ARGS);
 template __global__ void k_segment<1, 4, false>(SEG_ARGS);
@@ -253,11 +254,9 @@ __device__ void finalize_lloss(const double* t, DevStats* st, ScDev* sc) {
   if (sc) sc->n_lloss_pass++;
 }
 
-__global__ void __launch_bounds__(HPS_BLOCK)
-k_lloss_pass(BeamView b, DevStats* st, ScDev* sc, double* partials, u32* ticket, const XrView xr) {
-  __shared__ double s_total[LL_NS];
-  __shared__ double s_scratch[(HPS_BLOCK / 32) * LL_NS];
-  if (st->need_lloss_pass == 0) return;
+// the sweep of the longitudinal-loss pass; every thread of the grid calls it
+__device__ __forceinline__ void lloss_sweep(const BeamView& b, DevStats* st, ScDev* sc, double* partials, u32* ticket,
+                                            double* s_total, double* s_scratch, const XrView& xr) {
   const double thr = st->v[HPS_STAT_PHI_AVG_GOOD] + K_TWOPI + K_PI;
   double acc[LL_NS] = {0.0, 0.0, 0.0, 0.0};
   const u32 npairs = (b.n + 1) >> 1;
@@ -280,6 +279,34 @@ k_lloss_pass(BeamView b, DevStats* st, ScDev* sc, double* partials, u32* ticket,
   if (grid_reduce<LL_NS>(acc, 0u, partials, ticket, s_total, s_scratch, xr)) {
     if (threadIdx.x == 0) finalize_lloss(s_total, st, sc);
   }
+}
+
+// stand-alone form: the Beam::Update* API path and XR_NCCL (whose finaliser is a separate kernel)
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_lloss_pass(BeamView b, DevStats* st, ScDev* sc, double* partials, u32* ticket, const __grid_constant__ XrView xr) {
+  __shared__ double s_total[LL_NS];
+  __shared__ double s_scratch[HPS_BLOCK];
+  if (st->need_lloss_pass == 0) return;
+  lloss_sweep(b, st, sc, partials, ticket, s_total, s_scratch, xr);
+}
+
+// Barrier over the whole grid (all blocks are co-resident: the launch wrappers cap the grid at the
+// kernel's occupancy x SM count).  bar[0] = arrivals, bar[1] = generation.
+__device__ __forceinline__ void grid_barrier(u32* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const u32 gen = *(volatile u32*)&bar[1];
+    __threadfence();
+    if (atomicAdd(&bar[0], 1u) == gridDim.x - 1) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
+    } else {
+      while (*(volatile u32*)&bar[1] == gen) {}
+    }
+    __threadfence();
+  }
+  __syncthreads();
 }
 
 // ================================================================================================
@@ -361,11 +388,18 @@ __device__ void finalize_moments(const double* t, double ref, u32 n_global, DevS
 }
 
 __global__ void __launch_bounds__(HPS_BLOCK)
-k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, double* partials,
-          u32* ticket, const XrView xr) {
+k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, int with_lloss, double* partials,
+          u32* ticket, const __grid_constant__ XrView xr) {
   __shared__ double s_total[MOM_NS];
-  __shared__ double s_scratch[(HPS_BLOCK / 32) * MOM_NS];
-  const double ref = st->v[HPS_STAT_PHI_AVG_GOOD];
+  __shared__ double s_scratch[HPS_BLOCK];
+  // with_lloss: the longitudinal-loss pass (K2) runs in front of the moments inside this launch when K1
+  // asked for it -- the common "nothing to mark" case then costs nothing instead of an empty kernel.  The
+  // flag only changes in K1's finaliser, so every block sees the same value for the whole launch.
+  if (with_lloss && *(volatile u32*)&st->need_lloss_pass != 0u) {
+    lloss_sweep(b, st, sc, partials, ticket, s_total, s_scratch, xr);
+    grid_barrier(ticket + 2);
+  }
+  const double ref = *(volatile double*)&st->v[HPS_STAT_PHI_AVG_GOOD];
   const double xa = st->v[HPS_STAT_X_AVG], ya = st->v[HPS_STAT_Y_AVG];
   double acc[MOM_NS];
 #pragma unroll
@@ -406,92 +440,136 @@ k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int 
 }
 
 // ================================================================================================
-// K4: r-z ring charge deposit, privatised in shared memory
+// K4: r-z ring charge deposit, privatised in shared memory, fixed-point (order-independent) sums
 // ================================================================================================
 // space_charge_kernel.cu:123-224.  The reference does 4 global atomicAdds per particle into a 16-32 KB
-// table; here each block accumulates a private fp64 copy in shared memory and flushes its non-zero
-// bins once.
+// table (float, or a double CAS loop) -- the result depends on the order the atomics land in.  Here each
+// block accumulates a private copy in shared memory and flushes its non-zero bins once, and the sums are
+// 64-bit FIXED-POINT (weights scaled by 2^38, |error| <= 2^-39 per weight, i.e. ~1e-12 of a bin):
+// integer addition is associative, so the mesh is bit-identical from run to run, for any grid and for
+// any split of the beam over GPUs.  sm_100 has no native 64-bit shared-memory atomic (both
+// atomicAdd(double) and atomicAdd(u64) on shared memory compile to ATOMS.CAST.SPIN loops), so a bin is
+// two u32 words updated with native ATOMS.ADD: low word first, the carry rides on the high-word add.
+#define HPS_BIN_SCALE 274877906944.0              /* 2^38 */
+#define HPS_BIN_INV_SCALE (1.0 / 274877906944.0)
+
+__device__ __forceinline__ void bin_add(u32* s_lo, u32* s_hi, int k, double w) {
+  const unsigned long long q = (unsigned long long)__double2ll_rn(w * HPS_BIN_SCALE);  // two's complement
+  const u32 lo = (u32)q;
+  u32 hi = (u32)(q >> 32);
+  if (lo) {
+    const u32 old = atomicAdd(&s_lo[k], lo);
+    hi += (u32)(old + lo < old);
+  }
+  if (hi) atomicAdd(&s_hi[k], hi);
+}
+
+struct DepCtx {
+  double phimc, xbar, ybar, epsq, ref, dr, dzg, hl, c2, drdr;
+  int nx, nz;
+};
+
+// one particle of space_charge_kernel.cu:123-224; returns 1 when it landed on the mesh
+__device__ __forceinline__ u32 deposit_one(const DepCtx& d, u32 l, u32 ll, double x, double y, double phi, u32* s_lo,
+                                           u32* s_hi, double& pmax) {
+  if (l != 0) return 0;
+  const double pr = rel_phi(phi, d.ref);
+  {  // Beam::UpdateMaxRPhi's phase half (beam_kernel.cu:836-842); only reported, never fed back
+    double tp = pr - d.phimc;
+    tp = tp > 0.0 ? tp : -tp;
+    pmax = pmax < tp ? tp : pmax;
+  }
+  if (ll != 0) return 0;
+  const int nx = d.nx, nz = d.nz;
+  const double dr = d.dr, dzg = d.dzg, drdr = d.drdr;
+  const double rsq_sh = (x - d.xbar) * (x - d.xbar) / d.epsq + (y - d.ybar) * (y - d.ybar) * d.epsq;
+  const int i = (int)(sqrt(rsq_sh) / dr + 1);
+  if (!(i <= nx)) return 0;
+  double ddz = pr - d.phimc;
+  while (ddz > K_PI || ddz < -K_PI) {
+    if (ddz > 0.0) ddz -= K_TWOPI; else ddz += K_TWOPI;
+  }
+  const double z = -d.c2 * ddz;
+  if (!(fabs(z) < d.hl)) return 0;
+  const double zz = z + d.hl;
+  const int jm1 = (int)(zz / dzg + 1);
+  int i1 = i + 1;
+  if (rsq_sh < 0.5 * drdr * (double)(i * i + (i - 1) * (i - 1))) i1 = i - 1;
+  if (i1 < 1) i1 = 1;
+  if (i1 > nx) i1 = nx;
+  int j1 = jm1 + 1;
+  if (zz < (jm1 - 1 + 0.5) * dzg) j1 = jm1 - 1;
+  if (j1 < 1) j1 = 1;
+  if (j1 > nz) j1 = nz;
+  double a;
+  if (i1 == i) a = 1.0;
+  else {
+    const double sqrtmp = sqrt(4.0 * rsq_sh / drdr - 1.0);
+    const double rminsq = 0.25 * drdr * (sqrtmp - 1.0) * (sqrtmp - 1.0);
+    const double rmaxsq = rminsq + sqrtmp * drdr;
+    if (i1 < i) a = (rmaxsq - (i - 1) * (i - 1) * drdr) / (rmaxsq - rminsq);
+    else a = ((i1 - 1) * (i1 - 1) * drdr - rminsq) / (rmaxsq - rminsq);
+  }
+  double cc = 1.0;
+  if (j1 != jm1) cc = (zz - (j1 - 1 + 0.5) * dzg) / ((jm1 - j1) * dzg);
+  const double bb = 1.0 - a, dd = 1.0 - cc;
+  // jm1 can reach nz+1 when zz/dzg rounds up to nz exactly; the reference then writes one row past
+  // its table.  Such a particle is dropped here instead (it carries weight cc = 1 into nowhere).
+  int k = (jm1 - 1) * nx + i;
+  if (jm1 >= 1 && jm1 <= nz) {
+    bin_add(s_lo, s_hi, k - 1, a * cc);
+    if (i1 != i) bin_add(s_lo, s_hi, k + (i1 - i) - 1, bb * cc);
+  }
+  if (j1 != jm1) {  // dd == 0 otherwise: the reference adds exact zeros
+    k = (j1 - 1) * nx + i;
+    bin_add(s_lo, s_hi, k - 1, a * dd);
+    if (i1 != i) bin_add(s_lo, s_hi, k + (i1 - i) - 1, bb * dd);
+  }
+  return 1;
+}
+
 __global__ void __launch_bounds__(512)
-k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, u32* ticket, const XrView xr) {
-  extern __shared__ double s_bins[];
+k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, u32* ticket, const __grid_constant__ XrView xr) {
+  extern __shared__ u32 s_words[];  // [nb] low words, [nb] high words
   if (!sc->remesh) return;
-  const int nx = (int)kp.nr, nz = (int)kp.nz;
+  unsigned long long* bins = reinterpret_cast<unsigned long long*>(bins_raw);
   const u32 nb = kp.nr * kp.nz;
-  for (u32 k = threadIdx.x; k < nb; k += blockDim.x) s_bins[k] = 0.0;
+  u32* s_lo = s_words;
+  u32* s_hi = s_words + nb;
+  for (u32 k = threadIdx.x; k < 2 * nb; k += blockDim.x) s_words[k] = 0u;
+  DepCtx d;
+  d.nx = (int)kp.nr; d.nz = (int)kp.nz;
+  d.phimc = st->v[HPS_STAT_PHI_AVG_R]; d.xbar = st->v[HPS_STAT_X_AVG_GOOD]; d.ybar = st->v[HPS_STAT_Y_AVG_GOOD];
+  d.epsq = st->v[HPS_STAT_X_SIG_GOOD] / st->v[HPS_STAT_Y_SIG_GOOD];
+  d.ref = st->v[HPS_STAT_PHI_AVG_GOOD];
+  {
+    const double beta = sc->beta;
+    const double gm = rsqrt(1.0 - beta * beta);
+    d.dr = sc->dr;
+    d.dzg = sc->dz * gm;
+    const double wave_len = K_CLIGHT / kp.freq;
+    d.hl = d.nz * 0.5 * d.dzg;
+    d.c2 = beta * gm * wave_len / K_TWOPI;
+    d.drdr = d.dr * d.dr;
+  }
   __syncthreads();
-  const double phimc = st->v[HPS_STAT_PHI_AVG_R], xbar = st->v[HPS_STAT_X_AVG_GOOD], ybar = st->v[HPS_STAT_Y_AVG_GOOD];
-  const double epsq = st->v[HPS_STAT_X_SIG_GOOD] / st->v[HPS_STAT_Y_SIG_GOOD];
-  const double ref = st->v[HPS_STAT_PHI_AVG_GOOD];
-  const double beta = sc->beta;
-  const double gm = rsqrt(1.0 - beta * beta);
-  const double dr = sc->dr;
-  const double dzg = sc->dz * gm;
-  const double wave_len = K_CLIGHT / kp.freq;
-  const double hl = nz * 0.5 * dzg;
-  const double c2 = beta * gm * wave_len / K_TWOPI;
-  const double drdr = dr * dr;
   u32 cnt = 0;
   double pmax = 0.0;
-  for (u32 np = blockIdx.x * blockDim.x + threadIdx.x; np < b.n; np += gridDim.x * blockDim.x) {
-    const u32 l = b.loss[np];
-    if (l != 0) continue;
-    const double pr = rel_phi(b.phi[np], ref);
-    {  // Beam::UpdateMaxRPhi's phase half (beam_kernel.cu:836-842); only reported, never fed back
-      double tp = pr - phimc;
-      tp = tp > 0.0 ? tp : -tp;
-      pmax = pmax < tp ? tp : pmax;
-    }
-    if (b.lloss[np] != 0) continue;
-    const double x = b.x[np], y = b.y[np];
-    const double rsq_sh = (x - xbar) * (x - xbar) / epsq + (y - ybar) * (y - ybar) * epsq;
-    const int i = (int)(sqrt(rsq_sh) / dr + 1);
-    if (!(i <= nx)) continue;
-    double ddz = pr - phimc;
-    while (ddz > K_PI || ddz < -K_PI) {
-      if (ddz > 0.0) ddz -= K_TWOPI; else ddz += K_TWOPI;
-    }
-    const double z = -c2 * ddz;
-    if (!(fabs(z) < hl)) continue;
-    const double zz = z + hl;
-    const int jm1 = (int)(zz / dzg + 1);
-    int i1 = i + 1;
-    if (rsq_sh < 0.5 * drdr * (double)(i * i + (i - 1) * (i - 1))) i1 = i - 1;
-    if (i1 < 1) i1 = 1;
-    if (i1 > nx) i1 = nx;
-    int j1 = jm1 + 1;
-    if (zz < (jm1 - 1 + 0.5) * dzg) j1 = jm1 - 1;
-    if (j1 < 1) j1 = 1;
-    if (j1 > nz) j1 = nz;
-    double a;
-    if (i1 == i) a = 1.0;
-    else {
-      const double sqrtmp = sqrt(4.0 * rsq_sh / drdr - 1.0);
-      const double rminsq = 0.25 * drdr * (sqrtmp - 1.0) * (sqrtmp - 1.0);
-      const double rmaxsq = rminsq + sqrtmp * drdr;
-      if (i1 < i) a = (rmaxsq - (i - 1) * (i - 1) * drdr) / (rmaxsq - rminsq);
-      else a = ((i1 - 1) * (i1 - 1) * drdr - rminsq) / (rmaxsq - rminsq);
-    }
-    double cc = 1.0;
-    if (j1 != jm1) cc = (zz - (j1 - 1 + 0.5) * dzg) / ((jm1 - j1) * dzg);
-    const double bb = 1.0 - a, d = 1.0 - cc;
-    // jm1 can reach nz+1 when zz/dzg rounds up to nz exactly; the reference then writes one row past
-    // its table.  Such a particle is dropped here instead (it carries weight cc = 1 into nowhere).
-    int k = (jm1 - 1) * nx + i;
-    if (jm1 >= 1 && jm1 <= nz) {
-      atomicAdd(&s_bins[k - 1], a * cc);
-      if (i1 != i) atomicAdd(&s_bins[k + (i1 - i) - 1], bb * cc);
-    }
-    if (j1 != jm1) {  // d == 0 otherwise: the reference adds exact zeros
-      k = (j1 - 1) * nx + i;
-      atomicAdd(&s_bins[k - 1], a * d);
-      if (i1 != i) atomicAdd(&s_bins[k + (i1 - i) - 1], bb * d);
-    }
-    cnt++;
+  // two adjacent particles per thread, every array read with one 128/64-bit access issued up front
+  const u32 npairs = (b.n + 1) >> 1;
+  for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
+    const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
+    const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
+    const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
+    const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
+    const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
+    cnt += deposit_one(d, L.x, LL.x, X.x, Y.x, PH.x, s_lo, s_hi, pmax);
+    if (2 * i2 + 1 < b.n) cnt += deposit_one(d, L.y, LL.y, X.y, Y.y, PH.y, s_lo, s_hi, pmax);
   }
   __syncthreads();
   for (u32 k = threadIdx.x; k < nb; k += blockDim.x) {
-    const double v = s_bins[k];
-    if (v != 0.0) atomicAdd(&bins[k], v);
+    const unsigned long long v = ((unsigned long long)s_hi[k] << 32) + s_lo[k];
+    if (v) atomicAdd(&bins[k], v);  // RED.ADD.64 at the L2: integer, order-independent
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -504,8 +582,9 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, u32*
   }
   if (xr.nranks <= 1) return;
   // Sharded beam: the rank's last block hands the rank-local mesh (+ on-mesh count, max |phi|) to every
-  // peer; k_field folds the R meshes in rank order.  XR_P2P: stores into the peers' boxes over NVLink,
-  // sequence number = this context's mesh hand-off counter xr.seq[1].  XR_NCCL: the two scalars are appended and the host all-gathers.
+  // peer; k_field folds the R meshes (integer sums: the order does not matter).  XR_P2P: stores into the
+  // peers' boxes over NVLink, sequence number = this context's mesh hand-off counter xr.seq[1].
+  // XR_NCCL: the two scalars are appended and the host all-gathers.
   __shared__ u32 s_last;
   __threadfence();
   __syncthreads();
@@ -513,8 +592,8 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, u32*
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const double cnt_d = (double)__ldcg(&sc->num_on_mesh);
-  const double pmax_d = __longlong_as_double((long long)__ldcg(&sc->abs_phi_max_bits));
+  const unsigned long long cnt_u = (unsigned long long)__ldcg(&sc->num_on_mesh);
+  const unsigned long long pmax_u = __ldcg(&sc->abs_phi_max_bits);
   if (xr.mode == XR_P2P) {
     __shared__ unsigned long long s_seq;
     if (threadIdx.x == 0) { s_seq = xr.seq[1] + 1ull; xr.seq[1] = s_seq; }  // k_field reads it back
@@ -522,15 +601,16 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, u32*
     const unsigned long long seq = s_seq;
     const int par = (int)(seq & 1ull);
     for (u32 k = threadIdx.x; k < nb + 2; k += blockDim.x) {
-      const double v = k < nb ? __ldcg(&bins[k]) : (k == nb ? cnt_d : pmax_d);
-      for (int p = 0; p < xr.nranks; ++p) *(volatile double*)&xr.peer[p]->bins[par][xr.rank][k] = v;
+      const unsigned long long v = k < nb ? __ldcg(&bins[k]) : (k == nb ? cnt_u : pmax_u);
+      for (int p = 0; p < xr.nranks; ++p)
+        *(volatile unsigned long long*)&xr.peer[p]->bins[par][xr.rank][k] = v;
     }
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < xr.nranks) st_release_sys(&xr.peer[threadIdx.x]->bflag[par][xr.rank], seq);
   } else if (threadIdx.x == 0) {
-    bins[nb] = cnt_d;
-    bins[nb + 1] = pmax_d;
+    bins[nb] = cnt_u;
+    bins[nb + 1] = pmax_u;
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
@@ -547,62 +627,64 @@ __device__ __forceinline__ void ellip_ke(double g, double& ee, double& ek) {
   ek = 1.38629436 - 0.5 * h + g * (0.1119697 - 0.1213486 * h + g * (0.07253230 - 0.02887472 * h));
 }
 
-// Work split: block (rp, ch) owns receiving radius rp and HPS_FIELD_RS consecutive source rings; it
-// builds the [HPS_FIELD_RS][nz] Green slice in shared memory, accumulates the partial field of its rings
-// at every node (zp = 0..nz, rp) and stores it; the last block of each rp (ticket) adds the chunk
-// partials in a fixed order, so the result is deterministic.  (nr+1) x ceil(nr/RS) blocks fill the GPU;
-// the previous one-block-per-rp version ran on 33 SMs only.
+// Work split: block (rp, ch) owns receiving radius rp and RS consecutive source rings (RS = blockDim.x / T,
+// T = power of two >= nz).  Thread (kk, t) computes ONE entry of the [RS][nz] Green slice (ring kk, axial
+// offset t) into shared memory, then the partial field of ring kk at node (zp = t, rp) with two independent
+// accumulation chains; the RS ring partials are folded in ring order, the chunk partial is stored, and the
+// last block of each rp (ticket) adds the chunk partials in a fixed order -- deterministic, and
+// (nr+1) x ceil(nr/RS) blocks of RS*T threads fill the GPU.
 __global__ void __launch_bounds__(1024)
 k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, double2* part, u32* tickets,
-        KickParams kp, const XrView xr) {
+        KickParams kp, int T, const __grid_constant__ XrView xr) {
   extern __shared__ double s_mem[];
   if (!sc->remesh) return;
   const u32 nr = kp.nr, nz = kp.nz;
+  const u32 RS = blockDim.x / T;
   const u32 irp = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
-  const u32 rs0 = ch * HPS_FIELD_RS;
-  const u32 nrs = min((u32)HPS_FIELD_RS, nr - rs0);
-  double* s_b = s_mem;                                                       // [RS][nz]
-  double2* s_g = reinterpret_cast<double2*>(s_mem + HPS_FIELD_RS * nz);      // [RS][nz]
-  double2* s_red = s_g + HPS_FIELD_RS * nz;                                  // [blockDim.x]
+  const u32 rs0 = ch * RS;
+  const u32 nrs = min(RS, nr - rs0);
+  const u32 kk = threadIdx.x / T, t = threadIdx.x % T;
+  const bool live = kk < nrs && t < nz;
+  double* s_b = s_mem;                                           // [RS][nz]
+  double2* s_g = reinterpret_cast<double2*>(s_mem + RS * nz);    // [RS][nz]
+  double2* s_p = s_g + RS * nz;                                  // [RS][nz] ring partials at nodes zp < nz
+  double2* s_red = s_p + RS * nz;                                // [blockDim.x]
   if (xr.nranks <= 1) {
     if (irp == 0 && ch == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
       st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
-    for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
-      const u32 k = e / nz, zs = e % nz;
-      s_b[k * nz + zs] = bins[zs * nr + rs0 + k];
-    }
+    const long long* ibins = reinterpret_cast<const long long*>(bins);  // fixed point, see k_deposit
+    if (live) s_b[kk * nz + t] = (double)ibins[t * nr + rs0 + kk] * HPS_BIN_INV_SCALE;
   } else {
-    // sharded beam: fold the R rank-local meshes in rank order (bit-identical on every rank)
+    // sharded beam: fold the R rank-local meshes (integer sums: exact, order-independent)
     const u32 nb = nr * nz;
-    const double* slot[HPS_XR_MAXR];
+    const unsigned long long* slot[HPS_XR_MAXR];
     if (xr.mode == XR_P2P) {
       const unsigned long long seq = xr.seq[1];  // advanced by this rank's k_deposit just before
       const int par = (int)(seq & 1ull);
       const XrBox* own = xr.peer[xr.rank];
       if ((int)threadIdx.x < xr.nranks) xr_wait(&own->bflag[par][threadIdx.x], seq, xr.err);
       __syncthreads();
-      for (int r = 0; r < xr.nranks; ++r) slot[r] = own->bins[par][r];
+      for (int r = 0; r < xr.nranks; ++r) slot[r] = reinterpret_cast<const unsigned long long*>(own->bins[par][r]);
     } else {
-      for (int r = 0; r < xr.nranks; ++r) slot[r] = xr.bins_gather + (size_t)r * (nb + 2);
+      for (int r = 0; r < xr.nranks; ++r) slot[r] = reinterpret_cast<const unsigned long long*>(xr.bins_gather) + (size_t)r * (nb + 2);
     }
-    for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
-      const u32 k = e / nz, zs = e % nz;
-      double a = *(const volatile double*)&slot[0][zs * nr + rs0 + k];
-      for (int r = 1; r < xr.nranks; ++r) a += *(const volatile double*)&slot[r][zs * nr + rs0 + k];
-      s_b[k * nz + zs] = a;
+    if (live) {
+      unsigned long long a = 0ull;
+      for (int r = 0; r < xr.nranks; ++r) a += *(const volatile unsigned long long*)&slot[r][t * nr + rs0 + kk];
+      s_b[kk * nz + t] = (double)(long long)a * HPS_BIN_INV_SCALE;
     }
     if (irp == 0 && ch == 0 && threadIdx.x == 0) {
       u32 cnt = 0;
       double pm = 0.0;
       for (int r = 0; r < xr.nranks; ++r) {
-        cnt += (u32)*(const volatile double*)&slot[r][nb];
-        pm = fmax(pm, *(const volatile double*)&slot[r][nb + 1]);
+        cnt += (u32)*(const volatile unsigned long long*)&slot[r][nb];
+        pm = fmax(pm, __longlong_as_double((long long)*(const volatile unsigned long long*)&slot[r][nb + 1]));
       }
       sc->num_on_mesh = cnt;
       if (sc->adj_bunch != 0) st->v[HPS_STAT_ABS_PHI_MAX] = pm;
     }
   }
-  {
+  if (live) {  // Green's function entry (ring rs0+kk -> radius rp, axial offset (t + 1/2) cells)
     const double beta = sc->beta;
     const double gm = rsqrt(1.0 - beta * beta);
     const double dr = sc->dr;
@@ -612,75 +694,63 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
     const double c1 = 5721.67 * (kp.current_frac / kp.mass) / (kp.freq * 1e6 * (double)kp.n_global);
     const double rp = irp * dr;
     const int adj = (int)sc->adj_bunch;
-    for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
-      const u32 jz = e % nz, k = rs0 + e / nz;
-      const double rs = sqrt(0.5 * (k * k + (k + 1) * (k + 1))) * dr;
-      const double zs = 0.5 * dzg, zp = (jz + 1) * dzg;
-      const double d = zp - zs;
-      double d2 = d * d;
-      const double c = (rp - rs) * (rp - rs), bq = (rp + rs) * (rp + rs);
-      const double rsrp = rs * rp;
-      double a = 4.0 * rsrp / (bq + d2);
-      double ee, ek;
-      ellip_ke(1.0 - a, ee, ek);
-      double er1 = 0.0;
-      a = sqrt(bq + d2);
-      const double rs2mrp2 = rs * rs - rp * rp;
-      if (rp != 0.0) er1 = (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
-      double ez1 = d * ee / (a * (c + d2));
-      for (int i = 1; i <= adj; ++i) {
-        double xi = i;
-        for (int j = 0; j < 2; ++j) {
-          const double d1 = d - xi * pl;
-          d2 = d1 * d1;
-          a = 4.0 * rsrp / (bq + d2);
-          ellip_ke(1.0 - a, ee, ek);
-          a = sqrt(bq + d2);
-          if (rp != 0.0) er1 += (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
-          ez1 += d1 * ee / (a * (c + d2));
-          xi = -xi;
-        }
+    const u32 jz = t, k = rs0 + kk;
+    const double rs = sqrt(0.5 * (k * k + (k + 1) * (k + 1))) * dr;
+    const double zs = 0.5 * dzg, zp = (jz + 1) * dzg;
+    const double d = zp - zs;
+    double d2 = d * d;
+    const double c = (rp - rs) * (rp - rs), bq = (rp + rs) * (rp + rs);
+    const double rsrp = rs * rp;
+    double a = 4.0 * rsrp / (bq + d2);
+    double ee, ek;
+    ellip_ke(1.0 - a, ee, ek);
+    double er1 = 0.0;
+    a = sqrt(bq + d2);
+    const double rs2mrp2 = rs * rs - rp * rp;
+    if (rp != 0.0) er1 = (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
+    double ez1 = d * ee / (a * (c + d2));
+    for (int i = 1; i <= adj; ++i) {
+      double xi = i;
+      for (int j = 0; j < 2; ++j) {
+        const double d1 = d - xi * pl;
+        d2 = d1 * d1;
+        a = 4.0 * rsrp / (bq + d2);
+        ellip_ke(1.0 - a, ee, ek);
+        a = sqrt(bq + d2);
+        if (rp != 0.0) er1 += (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
+        ez1 += d1 * ee / (a * (c + d2));
+        xi = -xi;
       }
-      s_g[e] = make_double2(c1 * er1, c1 * ez1);
     }
+    s_g[kk * nz + t] = make_double2(c1 * er1, c1 * ez1);
   }
   __syncthreads();
 
   const size_t nodes_per_rp = nz + 1;
   double2* my_part = part + ((size_t)irp * nch + ch) * nodes_per_rp;
-  // nodes (zp = 0..nz-1, rp): one thread per node, sources in (ring, zs) order
-  if (threadIdx.x < nz) {
-    const u32 zp = threadIdx.x;
-    double tx = 0.0, tz = 0.0;
-    for (u32 k = 0; k < nrs; ++k) {
-      const double* bk = s_b + k * nz;
-      const double2* gk = s_g + k * nz;
-      for (u32 zs = 0; zs < nz; ++zs) {
-        const double v = bk[zs];
-        if (v == 0.0) continue;
-        u32 dz;
-        double sign = 1.0;
-        if (zs >= zp) { dz = zs - zp; sign = -1.0; } else dz = zp - zs - 1;
-        const double2 g = gk[dz];
-        tx += v * g.x;
-        tz += sign * v * g.y;
-      }
+  double2 last = make_double2(0.0, 0.0);  // this thread's term of node (zp = nz, rp)
+  if (live) {
+    // node (zp = t, rp), sources of ring kk in zs order, even / odd zs in separate chains
+    const u32 zp = t;
+    const double* bk = s_b + kk * nz;
+    const double2* gk = s_g + kk * nz;
+    double tx[2] = {0.0, 0.0}, tz[2] = {0.0, 0.0};
+    for (u32 zs = 0; zs < nz; ++zs) {
+      const double v = bk[zs];
+      if (v == 0.0) continue;  // warp-uniform: the 32 lanes of a warp share ring kk
+      const bool up = zs >= zp;
+      const u32 dz = up ? zs - zp : zp - zs - 1;
+      const double2 g = gk[dz];
+      tx[zs & 1] += v * g.x;
+      tz[zs & 1] += up ? -(v * g.y) : v * g.y;
     }
-    my_part[zp] = make_double2(tx, tz);
+    s_p[kk * nz + zp] = make_double2(tx[0] + tx[1], tz[0] + tz[1]);
+    // node (zp = nz, rp): every source bin lies upstream (dz = nz - zs - 1); this thread owns zs = t
+    const double v = bk[t];
+    const double2 g = gk[nz - t - 1];
+    last = make_double2(v * g.x, v * g.y);
   }
-  // node (zp = nz, rp): every source bin lies upstream (dz = nz - zs - 1)
-  {
-    double tx = 0.0, tz = 0.0;
-    for (u32 e = threadIdx.x; e < nrs * nz; e += blockDim.x) {
-      const double v = s_b[e];
-      if (v == 0.0) continue;
-      const u32 k = e / nz, zs = e % nz;
-      const double2 g = s_g[k * nz + (nz - zs - 1)];
-      tx += v * g.x;
-      tz += v * g.y;
-    }
-    s_red[threadIdx.x] = make_double2(tx, tz);
-  }
+  s_red[threadIdx.x] = last;
   __syncthreads();
   for (u32 s = blockDim.x >> 1; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
@@ -689,6 +759,11 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
     }
     __syncthreads();
   }
+  if (threadIdx.x < nz) {  // fold the ring partials of this chunk in ring order
+    double2 a = s_p[threadIdx.x];
+    for (u32 k = 1; k < nrs; ++k) { a.x += s_p[k * nz + threadIdx.x].x; a.y += s_p[k * nz + threadIdx.x].y; }
+    my_part[threadIdx.x] = a;
+  }
   if (threadIdx.x == 0) my_part[nz] = s_red[0];
 
   // last block of this rp folds the chunk partials (fixed order)
@@ -696,8 +771,8 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const u32 t = atomicAdd(&tickets[irp], 1u);
-    s_last = (t == nch - 1) ? 1u : 0u;
+    const u32 tk = atomicAdd(&tickets[irp], 1u);
+    s_last = (tk == nch - 1) ? 1u : 0u;
   }
   __syncthreads();
   if (!s_last) return;
@@ -779,9 +854,9 @@ __device__ void finalize_stat(const double* t, const BeamView& b, DevStats* st, 
 
 // slots: 0 count(filter passes) 1 sum a 2 sum a^2 3 sum b 4 sum b^2 5 sum ab 6 MAX 7 MAX
 __global__ void __launch_bounds__(HPS_BLOCK)
-k_stat(BeamView b, DevStats* st, StatReq rq, double* partials, u32* ticket, const XrView xr) {
+k_stat(BeamView b, DevStats* st, StatReq rq, double* partials, u32* ticket, const __grid_constant__ XrView xr) {
   __shared__ double s_total[STAT_NS];
-  __shared__ double s_scratch[(HPS_BLOCK / 32) * STAT_NS];
+  __shared__ double s_scratch[HPS_BLOCK];
   const double phi_ref = st->phi_r_ref;
   const double xa = st->v[HPS_STAT_X_AVG], ya = st->v[HPS_STAT_Y_AVG], pa = st->v[HPS_STAT_PHI_AVG_R];
   const double thr = st->v[HPS_STAT_PHI_AVG_GOOD] + K_TWOPI + K_PI;
@@ -826,7 +901,7 @@ k_stat(BeamView b, DevStats* st, StatReq rq, double* partials, u32* ticket, cons
 // XR_P2P / single-GPU path runs inside the reducing kernel's last block
 // ================================================================================================
 __global__ void __launch_bounds__(HPS_BLOCK)
-k_xr_finalize(const XrView xr, FinReq f, BeamView b, DevStats* st, ScDev* sc, double* bins) {
+k_xr_finalize(const __grid_constant__ XrView xr, FinReq f, BeamView b, DevStats* st, ScDev* sc, double* bins) {
   __shared__ double s_t[HPS_XR_NS];
   if (f.kind == FK_LLOSS && st->need_lloss_pass == 0) return;  // k_lloss_pass did not run either
   if ((int)threadIdx.x < f.ns) {
@@ -915,20 +990,30 @@ void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDe
   k_lloss_pass<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, c.partials, c.ticket, c.xr);
 }
 void launch_moments(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins, const KickParams& kp,
-                    int do_policy) {
-  k_moments<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, bins, kp, do_policy, c.partials, c.ticket, c.xr);
+                    int do_policy, int with_lloss) {
+  k_moments<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, bins, kp, do_policy, with_lloss, c.partials, c.ticket, c.xr);
 }
-size_t deposit_smem(const KickParams& kp) { return (size_t)kp.nr * kp.nz * sizeof(double); }
-size_t field_smem(const KickParams& kp, int threads) {
-  return (size_t)HPS_FIELD_RS * kp.nz * (sizeof(double) + sizeof(double2)) + (size_t)threads * sizeof(double2);
+int moments_occupancy() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_moments, HPS_BLOCK, 0);
+  return nb;
 }
-int field_threads(const KickParams& kp) {
+size_t deposit_smem(const KickParams& kp) { return (size_t)kp.nr * kp.nz * 2 * sizeof(u32); }
+int field_threads(const KickParams& kp) {  // T: power of two >= nz (the tree reduction needs it)
   if (kp.nz == 0 || kp.nz > 1024) return 0;
   int t = 32;
-  while (t < (int)kp.nz) t <<= 1;  // power of two >= nz (the tree reduction needs it)
+  while (t < (int)kp.nz) t <<= 1;
   return t;
 }
-unsigned field_chunks(const KickParams& kp) { return (kp.nr + HPS_FIELD_RS - 1) / HPS_FIELD_RS; }
+static unsigned field_rs(const KickParams& kp) {  // source rings per block: RS * T threads <= 1024
+  const int t = field_threads(kp);
+  return t ? std::max(1, std::min(HPS_FIELD_RS, 1024 / t)) : 1;
+}
+size_t field_smem(const KickParams& kp, int /*threads*/) {
+  const size_t rs = field_rs(kp);
+  return rs * kp.nz * (sizeof(double) + 2 * sizeof(double2)) + rs * (size_t)field_threads(kp) * sizeof(double2);
+}
+unsigned field_chunks(const KickParams& kp) { return (kp.nr + field_rs(kp) - 1) / field_rs(kp); }
 cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
                            const KickParams& kp) {
   const size_t smem = deposit_smem(kp);
@@ -942,14 +1027,14 @@ cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, 
 }
 cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const double* bins, double2* field, double2* part,
                          u32* tickets, const KickParams& kp) {
-  const int threads = field_threads(kp);
-  const size_t smem = field_smem(kp, threads);
+  const int T = field_threads(kp);
+  const size_t smem = field_smem(kp, T);
   if (smem > 48 * 1024 && !g_field_smem_set) {
     cudaError_t e = cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     g_field_smem_set = 1;
   }
-  k_field<<<dim3(kp.nr + 1, field_chunks(kp)), threads, smem, c.stream>>>(st, sc, bins, field, part, tickets, kp, c.xr);
+  k_field<<<dim3(kp.nr + 1, field_chunks(kp)), T * field_rs(kp), smem, c.stream>>>(st, sc, bins, field, part, tickets, kp, T, c.xr);
   return cudaSuccess;
 }
 void launch_stat(const LaunchCfg& c, const BeamView& b, DevStats* st, const StatReq& rq) {

@@ -102,7 +102,7 @@ __device__ __forceinline__ void xr_exchange_p2p(double* total, int ns, unsigned 
 // false; the host then enqueues an all-gather and k_xr_finalize.
 template <int NS>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, double* partials, u32* ticket,
-                                            double* total /* shared, NS */, double* scratch /* shared, 32*NS */,
+                                            double* total /* shared, NS */, double* scratch /* shared, blockDim.x doubles */,
                                             const XrView& xr) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   warp_reduce<NS>(v, max_mask);
@@ -127,20 +127,40 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, 
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-  // last block: warp w reduces slots w, w+nw, ... ; lanes stride over the blocks in a fixed order
-  for (int s = wid; s < NS; s += nw) {
+  // last block: thread t folds slot (t % NSP) of the blocks g, g+G, g+2G, ... (g = t / NSP; the loads of
+  // one thread are independent, so they overlap); the G group sums are then folded in group order.
+  // Every order is fixed, so the result is bit-reproducible for a given grid.
+  {
+    constexpr int NSP = NS <= 4 ? 4 : (NS <= 8 ? 8 : 16);
+    const int G = blockDim.x / NSP;  // 256 threads -> 64 / 32 / 16 groups
+    const int s = threadIdx.x % NSP, g = threadIdx.x / NSP;
     const bool mx = (max_mask >> s) & 1u;
     double a = mx ? -DBL_MAX : 0.0;
-    for (u32 k = lane; k < gridDim.x; k += 32) {
-      double t = __ldcg(&partials[(size_t)k * NS + s]);
-      a = mx ? fmax(a, t) : a + t;
-    }
+    if (s < NS) {
+      // batches of 8 loads in flight before the (ordered) folds: the tail is L2-latency bound
+      for (u32 k0 = g; k0 < gridDim.x; k0 += 8 * G) {
+        double t[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double t = __shfl_xor_sync(0xffffffffu, a, o);
-      a = mx ? fmax(a, t) : a + t;
+        for (int j = 0; j < 8; ++j) {
+          const u32 k = k0 + j * G;
+          t[j] = k < gridDim.x ? __ldcg(&partials[(size_t)k * NS + s]) : (mx ? -DBL_MAX : 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = mx ? fmax(a, t[j]) : a + t[j];
+      }
     }
-    if (lane == 0) total[s] = a;
+    __syncthreads();  // scratch (blockDim.x doubles) is free again
+    scratch[threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.x < NS) {
+      const bool m2 = (max_mask >> threadIdx.x) & 1u;
+      double r = scratch[threadIdx.x];
+      for (int q = 1; q < G; ++q) {
+        const double t = scratch[q * NSP + threadIdx.x];
+        r = m2 ? fmax(r, t) : r + t;
+      }
+      total[threadIdx.x] = r;
+    }
   }
   if (threadIdx.x == 0) *ticket = 0u;
   __syncthreads();
@@ -578,7 +598,10 @@ __device__ __forceinline__ double rel_phi(double phi, double ref) {
   double tmp = phi - ref + K_PI;
   double sign = 1.0;
   if (tmp < 0) { sign = -1.0; tmp = -tmp; }
-  return sign * (fmod(tmp, K_TWOPI) - K_PI);
+  // fmod(t, 2pi) == t exactly for 0 <= t < 2pi (the case of every particle inside the bunch); the
+  // library call, a multi-iteration loop in fp64, is only taken by particles a full turn away
+  const double m = tmp < K_TWOPI ? tmp : fmod(tmp, K_TWOPI);
+  return sign * (m - K_PI);
 }
 
 struct KickCtx {  // block-uniform inputs of the space-charge kick, staged in shared memory

@@ -48,7 +48,9 @@ void launch_prepare_ops(const LaunchCfg&, const Op* ops, OpC* opcs, int nops, do
 void launch_segment(const LaunchCfg&, const BeamView&, const Op* host_ops, const Op* ops, const OpC* opcs, int nops,
                     int fin_mode, int dirty, int compat, DevStats*, const ScDev*, const double2* field, const KickParams&);
 void launch_lloss_pass(const LaunchCfg&, const BeamView&, DevStats*, ScDev*);
-void launch_moments(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&, int do_policy);
+void launch_moments(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&, int do_policy,
+                    int with_lloss);
+int moments_occupancy();
 cudaError_t launch_deposit(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&);
 cudaError_t launch_field(const LaunchCfg&, DevStats*, ScDev*, const double* bins, double2* field, double2* part,
                          u32* tickets, const KickParams&);

@@ -106,7 +106,7 @@ def compare(a, b, rtol):
     rep["n_lloss"] = (int((a["lloss"] != 0).sum()), int((b["lloss"] != 0).sum()))
     rep["loss_mismatch"] = int((a["loss"] != b["loss"]).sum())
     both = (a["loss"] == 0) & (b["loss"] == 0)
-    worst = 0.0
+    worst = worst_rel = 0.0
     for k in ("x", "xp", "y", "yp", "phi", "w"):
         va, vb = a[k][both], b[k][both]
         if len(va) == 0:
@@ -114,10 +114,17 @@ def compare(a, b, rtol):
         scale = max(np.std(va), 1e-300) if k != "w" else max(np.abs(va).max(), 1e-300)
         if k == "phi":
             scale = max(np.std(va), 1.0)
-        err = np.abs(va - vb).max() / scale
+        d = np.abs(va - vb)
+        err = d.max() / scale
         rep["err_" + k] = float(err)
         worst = max(worst, err)
+        # the north star's measure: relative to the coordinate's own magnitude (floored at its rms extent,
+        # since x, x', y, y' pass through zero)
+        rel = (d / np.maximum(np.abs(vb), max(np.std(vb), 1e-300))).max()
+        rep["rel_" + k] = float(rel)
+        worst_rel = max(worst_rel, rel)
     rep["worst"] = float(worst)
+    rep["worst_rel"] = float(worst_rel)
     rep["ok"] = rep["loss_equal"] and worst <= rtol
     return rep
 
@@ -169,9 +176,9 @@ def run_reference(workdir, n, first, last, sc=True, double=True, nr=32, nz=128, 
         for k, v in DC.items():
             cfg.append(f"{k} {v!r}")
     else:
-        cfg += [f"beam_in {beam_in}", f"freq {freq}"]
+        cfg += [f"beam_in {beam_in}", f"freq {float(freq)!r}"]
         if design_w is not None:
-            cfg.append(f"design_w {design_w!r}")
+            cfg.append(f"design_w {float(design_w)!r}")  # float(): repr(np.float64) is not a C number
     path = os.path.join(workdir, "ref.cfg")
     with open(path, "w") as f:
         f.write("\n".join(cfg) + "\n")
