@@ -216,6 +216,7 @@ class Beam:
         off, nl = C.c_uint64(), C.c_uint64()
         lib.hps_beam_local_range(self.h, C.byref(off), C.byref(nl))
         self.offset, self.n_local, self.n = off.value, nl.value, int(num)
+        self.stride = int(lib.hps_beam_local_stride(self.h))  # local particle j = global offset + j * stride
         if file:
             lib.hps_beam_set_frequency(self.h, cols["freq"])
             self._upload(cols["x"], cols["xp"], cols["y"], cols["yp"], cols["phi"], cols["w"], cols["loss"], cols["lloss"])

@@ -84,6 +84,7 @@ PROTOTYPES = {
     "hps_beam_create": (_vp, [_vp, C.c_uint64, C.c_double, C.c_double, C.c_double]),
     "hps_beam_destroy": (None, [_vp]),
     "hps_beam_local_range": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "hps_beam_local_stride": (C.c_uint64, [_vp]),
     "hps_beam_upload": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hps_beam_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hps_beam_download_phi_relative": (C.c_int, [_vp, C.c_int, _vp]),

@@ -69,7 +69,7 @@ struct hps_ctx {
 struct hps_beam {
   hps_ctx* ctx;
   BeamHost h;           // mass charge current freq design_w n_global
-  u32 n = 0, offset = 0, n_alloc = 0;
+  u32 n = 0, offset = 0, gstride = 1, n_alloc = 0;
   char* slab = nullptr;  // one allocation: 6 fp64 arrays + 2 u32 arrays
   double* c[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   u32 *loss = nullptr, *lloss = nullptr;
@@ -115,7 +115,7 @@ BeamView view(const hps_beam* b) {
   BeamView v;
   v.x = b->c[0]; v.xp = b->c[1]; v.y = b->c[2]; v.yp = b->c[3]; v.phi = b->c[4]; v.w = b->c[5];
   v.loss = b->loss; v.lloss = b->lloss;
-  v.n = b->n; v.offset = b->offset; v.n_global = b->h.n_global;
+  v.n = b->n; v.offset = b->offset; v.gstride = b->gstride; v.n_global = b->h.n_global;
   const u32 np2 = next_pow2(b->h.n_global);
   v.np2_quarter = np2 >= 4 ? np2 / 4 : 1;
   v.mass = b->h.mass; v.charge = b->h.charge;
@@ -484,12 +484,13 @@ hps_beam* hps_beam_create(hps_ctx* c, uint64_t n_global, double mass, double cha
   b->ctx = c;
   b->h.mass = mass; b->h.charge = charge; b->h.current = current; b->h.freq = 0.0; b->h.design_w = 0.0;
   b->h.n_global = (u32)n_global;
-  // contiguous index blocks; even block starts keep the 2-particle vector lanes aligned
+  // Interleaved ownership: rank r holds the global particles r, r + R, r + 2R, ...  The C1 beam recipe
+  // orders particles by phase, so contiguous blocks would give every rank a different slice of the bunch
+  // (different loss rates -> unequal sweep times -> every exchange waits for the slowest rank).
   const int nr = std::max(1, c->comm.nranks), rk = c->comm.rank;
-  const uint64_t per = ((n_global + nr - 1) / nr + 1) & ~1ull;
-  const uint64_t lo = std::min<uint64_t>(n_global, per * rk), hi = std::min<uint64_t>(n_global, per * (rk + 1));
-  b->offset = (u32)lo;
-  b->n = (u32)(hi - lo);
+  b->offset = (u32)rk;
+  b->gstride = (u32)nr;
+  b->n = (u32)(n_global > (uint64_t)rk ? (n_global - rk + nr - 1) / nr : 0);
   b->n_alloc = (u32)align_up(std::max<u32>(b->n, 4), 4);
   const size_t da = align_up((size_t)b->n_alloc * sizeof(double), 256), ua = align_up((size_t)b->n_alloc * sizeof(u32), 256);
   b->slab_bytes = 6 * da + 2 * ua;
@@ -518,6 +519,7 @@ int hps_beam_local_range(const hps_beam* b, uint64_t* off, uint64_t* nl) {
   if (nl) *nl = b->n;
   return HPS_OK;
 }
+uint64_t hps_beam_local_stride(const hps_beam* b) { return b->gstride; }
 
 int hps_beam_upload(hps_beam* b, const double* x, const double* xp, const double* y, const double* yp,
                     const double* phi, const double* w, const uint32_t* loss, const uint32_t* lloss) {
@@ -570,9 +572,14 @@ int hps_beam_download_phi_relative(hps_beam* b, int use_good, double* out) {
 // Host generators.  Every rank draws the complete glibc rand() sequence and keeps its own block, so a
 // sharded beam is bit-identical to the single-GPU one.
 static int upload_generated(hps_beam* b, std::vector<double> v[6]) {
-  const u32 o = b->offset;
-  return hps_beam_upload(b, v[0].data() + o, v[1].data() + o, v[2].data() + o, v[3].data() + o, v[4].data() + o,
-                         v[5].data() + o, nullptr, nullptr);
+  if (b->gstride == 1)
+    return hps_beam_upload(b, v[0].data(), v[1].data(), v[2].data(), v[3].data(), v[4].data(), v[5].data(), nullptr, nullptr);
+  std::vector<double> loc[6];
+  for (int k = 0; k < 6; ++k) {
+    loc[k].resize(b->n);
+    for (u32 i = 0; i < b->n; ++i) loc[k][i] = v[k][(size_t)b->offset + (size_t)i * b->gstride];
+  }
+  return hps_beam_upload(b, loc[0].data(), loc[1].data(), loc[2].data(), loc[3].data(), loc[4].data(), loc[5].data(), nullptr, nullptr);
 }
 static inline double urand() { return 2.0 * std::rand() / RAND_MAX - 1.0; }
 

@@ -100,6 +100,7 @@ struct BeamView {
   u32 *loss, *lloss;
   u32 n;        // local particles
   u32 offset;   // global index of local particle 0
+  u32 gstride;  // global index of local particle i = offset + i * gstride (sharded beams are interleaved)
   u32 n_global;
   u32 np2_quarter;  // NextPow2(n_global)/4: stride of the reference's kick launch (H2)
   double mass, charge;
@@ -108,17 +109,18 @@ struct BeamView {
 // ---- cross-rank exchange ("xr") for particle-sharded beams -------------------------
 // Every rank owns one XrBox in its own HBM; all ranks map every box (CUDA IPC over NVLink/NVSwitch).
 // A reduction's last block stores its rank-local partial vector into slot [rank] of EVERY peer's box,
-// publishes a sequence number, waits for the R slots of its own box and folds them in rank order --
-// so all ranks obtain bit-identical totals and every device-side decision stays rank-consistent.
-// Two parity buffers suffice: a rank can run at most one exchange ahead of its slowest peer.
+// waits for the R slots of its own box and folds them in rank order -- so all ranks obtain bit-identical
+// totals and every device-side decision stays rank-consistent.  The stores are "LL" words (the NCCL
+// low-latency idea): every 8-byte word carries 32 bits of payload and the 32-bit sequence number of the
+// exchange, and 8-byte stores are atomic on NVLink, so the receiver polls the data itself -- no separate
+// flag, no system-scope fence, one one-way trip of latency.  Two parity buffers suffice: a rank can run
+// at most one exchange ahead of its slowest peer.
 #define HPS_XR_MAXR 8
 #define HPS_XR_NS 16            // doubles per small-reduction slot (>= every kernel's NS)
-#define HPS_XR_BINS_CAP 25608   // nr*nz + 2 (count, max|phi|) doubles; 8*nr*nz <= 200 KB
+#define HPS_XR_BINS_CAP 25608   // nr*nz + 2 (count, max|phi|) 64-bit values; 8*nr*nz <= 200 KB
 struct XrBox {
-  unsigned long long flag[2][HPS_XR_MAXR];       // sequence number of the data in data[parity][rank]
-  double data[2][HPS_XR_MAXR][HPS_XR_NS];
-  unsigned long long bflag[2][HPS_XR_MAXR];      // same for the charge mesh
-  double bins[2][HPS_XR_MAXR][HPS_XR_BINS_CAP];
+  unsigned long long data[2][HPS_XR_MAXR][2 * HPS_XR_NS];       // LL words: payload | seq << 32
+  unsigned long long bins[2][HPS_XR_MAXR][2 * HPS_XR_BINS_CAP]; // LL words of the charge mesh
 };
 enum XrMode { XR_NONE = 0, XR_P2P = 1, XR_NCCL = 2 };
 struct XrView {

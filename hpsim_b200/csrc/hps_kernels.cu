@@ -43,66 +43,109 @@ __device__ void finalize_segment(int fin, const double* t, DevStats* st, u32 n_g
   }
 }
 
-// one op applied to one register-resident particle
-template <bool FULL>
-__device__ __forceinline__ void apply_op(Pt& pt, const u32 ll, const u32 gidx, const Op& op, const OpC& opc, const KickCtx& kc,
-                                         const double* cxy, const double2* __restrict__ field, const BeamView& b,
-                                         int compat, double& phi_fc, bool& live_fc) {
+// one op applied to the N register-resident particles of a thread.  The type dispatch and the shared-memory
+// reads of the op's parameters happen once per op, not once per particle, and the per-particle bodies sit
+// back to back so that their independent fp64 chains can overlap.
+template <bool FULL, int N>
+__device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const u32 (&gidx)[N], const bool (&valid)[N],
+                                         const Op& op, const OpC& opc, const KickCtx& kc, const double* cxy,
+                                         const double2* __restrict__ field, const BeamView& b, int compat,
+                                         double (&phi_fc)[N], bool (&live_fc)[N]) {
   const double* q = op.p;
   const double* c = opc.c;
   const double mass = b.mass, charge = b.charge;
+#define EACH for (int j = 0; j < N; ++j) if (valid[j])
+#define EACH_ALIVE for (int j = 0; j < N; ++j) if (valid[j] && pt[j].loss == 0)
   switch (op.type) {
-    case OP_DRIFT: if (pt.loss == 0) op_drift(pt, q, c, op.elem, mass); break;
-    case OP_QUAD_HALF: if (pt.loss == 0) op_quad_half(pt, q, c, op.elem, mass); break;
-    case OP_GAP_FIRST: if (pt.loss == 0) op_gap_first(pt, q, c, op.flag != 0, mass); break;
-    case OP_GAP_SECOND: if (pt.loss == 0) op_gap_second(pt, q, c, op.flag != 0, mass); break;
+    case OP_DRIFT:
+#pragma unroll
+      EACH_ALIVE op_drift(pt[j], q, c, op.elem, mass);
+      break;
+    case OP_QUAD_HALF:
+#pragma unroll
+      EACH_ALIVE op_quad_half(pt[j], q, c, op.elem, mass);
+      break;
+    case OP_GAP_FIRST:
+#pragma unroll
+      EACH_ALIVE op_gap_first(pt[j], q, c, op.flag != 0, mass);
+      break;
+    case OP_GAP_SECOND:
+#pragma unroll
+      EACH_ALIVE op_gap_second(pt[j], q, c, op.flag != 0, mass);
+      break;
     // the rare, code-heavy maps (7 dipoles and 2 bunchers in the whole linac) live in the FULL variant only,
     // which keeps the hot variant's SASS inside the instruction cache
-    case OP_DIPOLE_FIRST: if (FULL && pt.loss == 0) op_dipole(pt, q, false, mass); break;
-    case OP_DIPOLE_SECOND: if (FULL && pt.loss == 0) op_dipole(pt, q, true, mass); break;
-    case OP_BUNCHER: if (FULL && pt.loss == 0) op_buncher(pt, q, op.elem, mass, charge); break;
-    case OP_ROTATION:  // simulation_kernel.cu:511-529
-      if (pt.loss == 0) {
-        const double cosa = c[R_COS], sina = c[R_SIN];
-        const double x = pt.x, y = pt.y, xp = pt.xp, yp = pt.yp;
-        pt.x = x * cosa + y * sina; pt.y = y * cosa - x * sina;
-        pt.xp = xp * cosa + yp * sina; pt.yp = yp * cosa - xp * sina;
+    case OP_DIPOLE_FIRST:
+      if (FULL) {
+#pragma unroll
+        EACH_ALIVE op_dipole(pt[j], q, false, mass);
       }
       break;
+    case OP_DIPOLE_SECOND:
+      if (FULL) {
+#pragma unroll
+        EACH_ALIVE op_dipole(pt[j], q, true, mass);
+      }
+      break;
+    case OP_BUNCHER:
+      if (FULL) {
+#pragma unroll
+        EACH_ALIVE op_buncher(pt[j], q, op.elem, mass, charge);
+      }
+      break;
+    case OP_ROTATION: {  // simulation_kernel.cu:511-529
+      const double cosa = c[R_COS], sina = c[R_SIN];
+#pragma unroll
+      EACH_ALIVE {
+        const double x = pt[j].x, y = pt[j].y, xp = pt[j].xp, yp = pt[j].yp;
+        pt[j].x = x * cosa + y * sina; pt[j].y = y * cosa - x * sina;
+        pt[j].xp = xp * cosa + yp * sina; pt[j].yp = yp * cosa - xp * sina;
+      }
+      break;
+    }
     case OP_STEERER:  // simulation_kernel.cu:120-140
-      if (pt.loss == 0) {
-        const double gm1 = pt.w / mass;
+#pragma unroll
+      EACH_ALIVE {
+        const double gm1 = pt[j].w / mass;
         const double pm = sqrt(gm1 * (gm1 + 2.0)) * mass / K_CLIGHT;
-        if (q[0] > 1e-10) pt.xp += q[0] * charge / pm;
-        if (q[1] > 1e-10) pt.yp += q[1] * charge / pm;
+        if (q[0] > 1e-10) pt[j].xp += q[0] * charge / pm;
+        if (q[1] > 1e-10) pt[j].yp += q[1] * charge / pm;
       }
       break;
     case OP_CAPERTURE:  // simulation_kernel.cu:543-556 (reference particle exempt, H1)
-      if (gidx > 0 && pt.loss == 0) {
-        const double x = pt.x - cxy[0], y = pt.y - cxy[1];
-        if (x * x + y * y > q[0] * q[0]) pt.loss = op.elem;
+#pragma unroll
+      EACH_ALIVE if (gidx[j] > 0) {
+        const double x = pt[j].x - cxy[0], y = pt[j].y - cxy[1];
+        if (x * x + y * y > q[0] * q[0]) pt[j].loss = op.elem;
       }
       break;
-    case OP_RAPERTURE:  // simulation_kernel.cu:558-575
-      if (gidx > 0 && pt.loss == 0) {
-        const double xmin = cxy[0] - q[0], xmax = cxy[0] + q[1];
-        const double ymin = cxy[1] - q[3], ymax = cxy[1] + q[2];
-        if (pt.x < xmin || pt.x > xmax || pt.y < ymin || pt.y > ymax) pt.loss = op.elem;
+    case OP_RAPERTURE: {  // simulation_kernel.cu:558-575
+      const double xmin = cxy[0] - q[0], xmax = cxy[0] + q[1];
+      const double ymin = cxy[1] - q[3], ymax = cxy[1] + q[2];
+#pragma unroll
+      EACH_ALIVE if (gidx[j] > 0) {
+        if (pt[j].x < xmin || pt[j].x > xmax || pt[j].y < ymin || pt[j].y > ymax) pt[j].loss = op.elem;
       }
       break;
+    }
     case OP_SC_KICK:
       // H2: the reference launches the kick <<<grid, blck/4>>> with `while(indx > 0 && ...)`, so
       // global thread 0 exits at once and particles k*NextPow2(N)/4 never see a kick.
-      if (!(gidx == 0 || (compat && (gidx % b.np2_quarter) == 0)))
-        op_sc_kick(pt, ll, kc, field, mass);
+#pragma unroll
+      EACH if (!(gidx[j] == 0 || (compat && (gidx[j] % b.np2_quarter) == 0))) op_sc_kick(pt[j], ll[j], kc, field, mass);
       break;
     case OP_FREQ_CHANGE:  // beam_kernel.cu:1531-1538: every particle, lost or not
-      pt.phi *= q[0];
-      phi_fc = pt.phi;
-      live_fc = pt.loss == 0;
+#pragma unroll
+      EACH {
+        pt[j].phi *= q[0];
+        phi_fc[j] = pt[j].phi;
+        live_fc[j] = pt[j].loss == 0;
+      }
       break;
     default: break;
   }
+#undef EACH
+#undef EACH_ALIVE
 }
 
 __device__ __forceinline__ void seg_accumulate(double (&acc)[SEG_NS], const Pt& p, u32 ll, double phi_fc, bool live_fc) {
@@ -176,51 +219,49 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       const double2 W = reinterpret_cast<const double2*>(b.w)[i2];
       const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
       const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
-      Pt p0 = {X.x, XP.x, Y.x, YP.x, PH.x, W.x, L.x};
-      Pt p1 = {X.y, XP.y, Y.y, YP.y, PH.y, W.y, L.y};
-      const bool valid1 = 2 * i2 + 1 < b.n;
-      const u32 g0 = b.offset + 2 * i2, g1 = g0 + 1;
-      double fc0 = 0.0, fc1 = 0.0;
-      bool lf0 = false, lf1 = false;
-      for (int k = 0; k < nops; ++k) {
-        const Op& op = s_ops[k];
-        const OpC& oc = s_opc[k];
-        apply_op<FULL>(p0, LL.x, g0, op, oc, s_k, s_cxy, field, b, compat, fc0, lf0);
-        if (valid1) apply_op<FULL>(p1, LL.y, g1, op, oc, s_k, s_cxy, field, b, compat, fc1, lf1);
-      }
+      Pt p[2] = {{X.x, XP.x, Y.x, YP.x, PH.x, W.x, L.x}, {X.y, XP.y, Y.y, YP.y, PH.y, W.y, L.y}};
+      const u32 ll[2] = {LL.x, LL.y};
+      const bool valid[2] = {true, 2 * i2 + 1 < b.n};
+      const u32 g0 = b.offset + 2 * i2 * b.gstride;
+      const u32 g[2] = {g0, g0 + b.gstride};
+      double fc[2] = {0.0, 0.0};
+      bool lf[2] = {false, false};
+      for (int k = 0; k < nops; ++k) apply_op<FULL, 2>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
       if (nops > 0) {
-        if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p0.x, p1.x);
-        if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p0.xp, p1.xp);
-        if (dirty & 4) reinterpret_cast<double2*>(b.y)[i2] = make_double2(p0.y, p1.y);
-        if (dirty & 8) reinterpret_cast<double2*>(b.yp)[i2] = make_double2(p0.yp, p1.yp);
-        if (dirty & 16) reinterpret_cast<double2*>(b.phi)[i2] = make_double2(p0.phi, p1.phi);
-        if (dirty & 32) reinterpret_cast<double2*>(b.w)[i2] = make_double2(p0.w, p1.w);
-        if ((dirty & 64) && (p0.loss != L.x || p1.loss != L.y))
-          reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p0.loss, p1.loss);
+        if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p[0].x, p[1].x);
+        if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p[0].xp, p[1].xp);
+        if (dirty & 4) reinterpret_cast<double2*>(b.y)[i2] = make_double2(p[0].y, p[1].y);
+        if (dirty & 8) reinterpret_cast<double2*>(b.yp)[i2] = make_double2(p[0].yp, p[1].yp);
+        if (dirty & 16) reinterpret_cast<double2*>(b.phi)[i2] = make_double2(p[0].phi, p[1].phi);
+        if (dirty & 32) reinterpret_cast<double2*>(b.w)[i2] = make_double2(p[0].w, p[1].w);
+        if ((dirty & 64) && (p[0].loss != L.x || p[1].loss != L.y))
+          reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p[0].loss, p[1].loss);
       }
       if (fin_mode != FIN_NONE) {
-        seg_accumulate(acc, p0, LL.x, fc0, lf0);
-        if (valid1) seg_accumulate(acc, p1, LL.y, fc1, lf1);
+        seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
+        if (valid[1]) seg_accumulate(acc, p[1], ll[1], fc[1], lf[1]);
       }
     }
   } else {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x) {
-      const u32 l0 = b.loss[i], ll = b.lloss[i];
-      Pt p = {b.x[i], b.xp[i], b.y[i], b.yp[i], b.phi[i], b.w[i], l0};
-      const u32 g = b.offset + i;
-      double fc = 0.0;
-      bool lf = false;
-      for (int k = 0; k < nops; ++k) apply_op<FULL>(p, ll, g, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
+      const u32 l0 = b.loss[i];
+      Pt p[1] = {{b.x[i], b.xp[i], b.y[i], b.yp[i], b.phi[i], b.w[i], l0}};
+      const u32 ll[1] = {b.lloss[i]};
+      const bool valid[1] = {true};
+      const u32 g[1] = {b.offset + i * b.gstride};
+      double fc[1] = {0.0};
+      bool lf[1] = {false};
+      for (int k = 0; k < nops; ++k) apply_op<FULL, 1>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
       if (nops > 0) {
-        if (dirty & 1) b.x[i] = p.x;
-        if (dirty & 2) b.xp[i] = p.xp;
-        if (dirty & 4) b.y[i] = p.y;
-        if (dirty & 8) b.yp[i] = p.yp;
-        if (dirty & 16) b.phi[i] = p.phi;
-        if (dirty & 32) b.w[i] = p.w;
-        if ((dirty & 64) && p.loss != l0) b.loss[i] = p.loss;
+        if (dirty & 1) b.x[i] = p[0].x;
+        if (dirty & 2) b.xp[i] = p[0].xp;
+        if (dirty & 4) b.y[i] = p[0].y;
+        if (dirty & 8) b.yp[i] = p[0].yp;
+        if (dirty & 16) b.phi[i] = p[0].phi;
+        if (dirty & 32) b.w[i] = p[0].w;
+        if ((dirty & 64) && p[0].loss != l0) b.loss[i] = p[0].loss;
       }
-      if (fin_mode != FIN_NONE) seg_accumulate(acc, p, ll, fc, lf);
+      if (fin_mode != FIN_NONE) seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
     }
   }
   if (fin_mode == FIN_NONE) return;
@@ -598,16 +639,16 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
     __shared__ unsigned long long s_seq;
     if (threadIdx.x == 0) { s_seq = xr.seq[1] + 1ull; xr.seq[1] = s_seq; }  // k_field reads it back
     __syncthreads();
-    const unsigned long long seq = s_seq;
-    const int par = (int)(seq & 1ull);
+    const u32 seq32 = (u32)s_seq;
+    const int par = (int)(s_seq & 1ull);
     for (u32 k = threadIdx.x; k < nb + 2; k += blockDim.x) {
       const unsigned long long v = k < nb ? __ldcg(&bins[k]) : (k == nb ? cnt_u : pmax_u);
-      for (int p = 0; p < xr.nranks; ++p)
-        *(volatile unsigned long long*)&xr.peer[p]->bins[par][xr.rank][k] = v;
+      for (int p = 0; p < xr.nranks; ++p) {
+        unsigned long long* w = &xr.peer[p]->bins[par][xr.rank][2 * k];
+        ll_send(w, (u32)v, seq32);
+        ll_send(w + 1, (u32)(v >> 32), seq32);
+      }
     }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < xr.nranks) st_release_sys(&xr.peer[threadIdx.x]->bflag[par][xr.rank], seq);
   } else if (threadIdx.x == 0) {
     bins[nb] = cnt_u;
     bins[nb + 1] = pmax_u;
@@ -649,41 +690,8 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
   double2* s_g = reinterpret_cast<double2*>(s_mem + RS * nz);    // [RS][nz]
   double2* s_p = s_g + RS * nz;                                  // [RS][nz] ring partials at nodes zp < nz
   double2* s_red = s_p + RS * nz;                                // [blockDim.x]
-  if (xr.nranks <= 1) {
-    if (irp == 0 && ch == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
-      st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
-    const long long* ibins = reinterpret_cast<const long long*>(bins);  // fixed point, see k_deposit
-    if (live) s_b[kk * nz + t] = (double)ibins[t * nr + rs0 + kk] * HPS_BIN_INV_SCALE;
-  } else {
-    // sharded beam: fold the R rank-local meshes (integer sums: exact, order-independent)
-    const u32 nb = nr * nz;
-    const unsigned long long* slot[HPS_XR_MAXR];
-    if (xr.mode == XR_P2P) {
-      const unsigned long long seq = xr.seq[1];  // advanced by this rank's k_deposit just before
-      const int par = (int)(seq & 1ull);
-      const XrBox* own = xr.peer[xr.rank];
-      if ((int)threadIdx.x < xr.nranks) xr_wait(&own->bflag[par][threadIdx.x], seq, xr.err);
-      __syncthreads();
-      for (int r = 0; r < xr.nranks; ++r) slot[r] = reinterpret_cast<const unsigned long long*>(own->bins[par][r]);
-    } else {
-      for (int r = 0; r < xr.nranks; ++r) slot[r] = reinterpret_cast<const unsigned long long*>(xr.bins_gather) + (size_t)r * (nb + 2);
-    }
-    if (live) {
-      unsigned long long a = 0ull;
-      for (int r = 0; r < xr.nranks; ++r) a += *(const volatile unsigned long long*)&slot[r][t * nr + rs0 + kk];
-      s_b[kk * nz + t] = (double)(long long)a * HPS_BIN_INV_SCALE;
-    }
-    if (irp == 0 && ch == 0 && threadIdx.x == 0) {
-      u32 cnt = 0;
-      double pm = 0.0;
-      for (int r = 0; r < xr.nranks; ++r) {
-        cnt += (u32)*(const volatile unsigned long long*)&slot[r][nb];
-        pm = fmax(pm, __longlong_as_double((long long)*(const volatile unsigned long long*)&slot[r][nb + 1]));
-      }
-      sc->num_on_mesh = cnt;
-      if (sc->adj_bunch != 0) st->v[HPS_STAT_ABS_PHI_MAX] = pm;
-    }
-  }
+  // The Green's function slice does not depend on the charge mesh: it is computed first, so on a sharded
+  // beam the peers' meshes travel over NVLink meanwhile.
   if (live) {  // Green's function entry (ring rs0+kk -> radius rp, axial offset (t + 1/2) cells)
     const double beta = sc->beta;
     const double gm = rsqrt(1.0 - beta * beta);
@@ -723,6 +731,43 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
       }
     }
     s_g[kk * nz + t] = make_double2(c1 * er1, c1 * ez1);
+  }
+  if (xr.nranks <= 1) {
+    if (irp == 0 && ch == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
+      st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
+    const long long* ibins = reinterpret_cast<const long long*>(bins);  // fixed point, see k_deposit
+    if (live) s_b[kk * nz + t] = (double)ibins[t * nr + rs0 + kk] * HPS_BIN_INV_SCALE;
+  } else {
+    // sharded beam: fold the R rank-local meshes (integer sums: exact, order-independent)
+    const u32 nb = nr * nz;
+    const unsigned long long* slot[HPS_XR_MAXR];
+    const bool ll = xr.mode == XR_P2P;  // LL words in this rank's own box, polled in place
+    const unsigned long long seq = ll ? xr.seq[1] : 0ull;  // advanced by this rank's k_deposit just before
+    const u32 seq32 = (u32)seq;
+    if (ll) {
+      const XrBox* own = xr.peer[xr.rank];
+      for (int r = 0; r < xr.nranks; ++r) slot[r] = own->bins[(int)(seq & 1ull)][r];
+    } else {
+      for (int r = 0; r < xr.nranks; ++r) slot[r] = reinterpret_cast<const unsigned long long*>(xr.bins_gather) + (size_t)r * (nb + 2);
+    }
+    auto value = [&](int r, u32 k) -> unsigned long long {
+      return ll ? ll_recv64(slot[r] + 2 * (size_t)k, seq32, xr.err) : slot[r][k];
+    };
+    if (live) {
+      unsigned long long a = 0ull;
+      for (int r = 0; r < xr.nranks; ++r) a += value(r, t * nr + rs0 + kk);
+      s_b[kk * nz + t] = (double)(long long)a * HPS_BIN_INV_SCALE;
+    }
+    if (irp == 0 && ch == 0 && threadIdx.x == 0) {
+      u32 cnt = 0;
+      double pm = 0.0;
+      for (int r = 0; r < xr.nranks; ++r) {
+        cnt += (u32)value(r, nb);
+        pm = fmax(pm, __longlong_as_double((long long)value(r, nb + 1)));
+      }
+      sc->num_on_mesh = cnt;
+      if (sc->adj_bunch != 0) st->v[HPS_STAT_ABS_PHI_MAX] = pm;
+    }
   }
   __syncthreads();
 

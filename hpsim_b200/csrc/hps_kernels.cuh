@@ -39,12 +39,12 @@ __device__ __forceinline__ void warp_reduce(double (&v)[NS], unsigned max_mask) 
 }
 
 // ---- cross-rank exchange over peer memory (XrBox, hps_internal.h) ------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -54,42 +54,57 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 #define HPS_XR_TIMEOUT_NS 20000000000ull  // a peer that stays silent this long is reported, not waited for
 
-// Spins until flag == seq (written by a peer GPU through NVLink into this rank's box).
-__device__ __forceinline__ void xr_wait(const unsigned long long* flag, unsigned long long seq, u32* err) {
-  if (ld_acquire_sys(flag) == seq) return;
-  const unsigned long long t0 = global_ns();
-  while (ld_acquire_sys(flag) != seq) {
-    if (global_ns() - t0 > HPS_XR_TIMEOUT_NS) { *err = 1u; return; }
+// LL word = 32-bit payload | (32-bit sequence number << 32); 8-byte stores are single transactions.
+__device__ __forceinline__ void ll_send(unsigned long long* word, u32 payload, u32 seq32) {
+  st_sys_u64(word, (unsigned long long)payload | ((unsigned long long)seq32 << 32));
+}
+// Polls a word of this rank's own box until a peer has written it for exchange `seq32`.
+__device__ __forceinline__ u32 ll_recv(const unsigned long long* word, u32 seq32, u32* err) {
+  unsigned long long w = ld_sys_u64(word);
+  if ((u32)(w >> 32) != seq32) {
+    const unsigned long long t0 = global_ns();
+    do {
+      w = ld_sys_u64(word);
+      if (global_ns() - t0 > HPS_XR_TIMEOUT_NS) { *err = 1u; break; }
+    } while ((u32)(w >> 32) != seq32);
   }
+  return (u32)w;
+}
+__device__ __forceinline__ unsigned long long ll_recv64(const unsigned long long* pair, u32 seq32, u32* err) {
+  const u32 lo = ll_recv(pair, seq32, err), hi = ll_recv(pair + 1, seq32, err);
+  return (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
 
-// All threads of ONE block (the rank's last block) call this with the rank-local totals in shared
-// memory; on return total[] holds the fold over all ranks in rank order (bit-identical everywhere).
+// All threads of ONE block (the rank's last block, >= 2 * nranks * ns threads) call this with the
+// rank-local totals in shared memory; on return total[] holds the fold over all ranks in rank order
+// (bit-identical everywhere).
 __device__ __forceinline__ void xr_exchange_p2p(double* total, int ns, unsigned max_mask, const XrView& xr) {
   __shared__ unsigned long long s_seq;
+  __shared__ u32 s_recv[HPS_XR_MAXR * 2 * HPS_XR_NS];
   if (threadIdx.x == 0) { s_seq = *xr.seq + 1ull; *xr.seq = s_seq; }
   __syncthreads();
-  const unsigned long long seq = s_seq;
-  const int par = (int)(seq & 1ull);
-  for (int t = threadIdx.x; t < xr.nranks * ns; t += blockDim.x) {
-    const int p = t / ns, s = t - p * ns;
-    *(volatile double*)&xr.peer[p]->data[par][xr.rank][s] = total[s];
+  const u32 seq32 = (u32)s_seq;
+  const int par = (int)(s_seq & 1ull);
+  const int nw = 2 * ns;  // LL words per rank
+  for (int t = threadIdx.x; t < xr.nranks * nw; t += blockDim.x) {
+    const int p = t / nw, w = t - p * nw;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(total[w >> 1]);
+    ll_send(&xr.peer[p]->data[par][xr.rank][w], (w & 1) ? (u32)(bits >> 32) : (u32)bits, seq32);
   }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < xr.nranks) {
-    st_release_sys(&xr.peer[threadIdx.x]->flag[par][xr.rank], seq);
-    xr_wait(&xr.peer[xr.rank]->flag[par][threadIdx.x], seq, xr.err);
+  const XrBox* own = xr.peer[xr.rank];
+  for (int t = threadIdx.x; t < xr.nranks * nw; t += blockDim.x) {
+    const int r = t / nw, w = t - r * nw;
+    s_recv[r * (2 * HPS_XR_NS) + w] = ll_recv(&own->data[par][r][w], seq32, xr.err);
   }
   __syncthreads();
   if ((int)threadIdx.x < ns) {
     const int s = threadIdx.x;
     const bool mx = (max_mask >> s) & 1u;
-    const XrBox* own = xr.peer[xr.rank];
-    double a = *(const volatile double*)&own->data[par][0][s];
-    for (int r = 1; r < xr.nranks; ++r) {
-      const double t = *(const volatile double*)&own->data[par][r][s];
-      a = mx ? fmax(a, t) : a + t;
+    double a = 0.0;
+    for (int r = 0; r < xr.nranks; ++r) {
+      const u32* q = &s_recv[r * (2 * HPS_XR_NS) + 2 * s];
+      const double t = __longlong_as_double((long long)((unsigned long long)q[0] | ((unsigned long long)q[1] << 32)));
+      a = r == 0 ? t : (mx ? fmax(a, t) : a + t);
     }
     total[s] = a;
   }

@@ -131,11 +131,14 @@ int hps_ctx_flush_l2(hps_ctx*);
 /* ---- beam ---------------------------------------------------------------- */
 /* Replaces Beam::Beam(num, mass, charge, current) + AllocateBeam
  * (reference src/beam/src/beam.cpp:70-147).  With sharding, `n_global` is the
- * whole beam and this rank owns the contiguous block
- * [offset, offset+n_local) (hps_beam_local_range). */
+ * whole beam and this rank owns n_local particles, interleaved: local particle j
+ * is global particle offset + j * stride (offset = rank, stride = number of
+ * ranks; 0 and 1 for an unsharded beam).  Upload / download move the local
+ * particles in local order. */
 hps_beam* hps_beam_create(hps_ctx*, uint64_t n_global, double mass, double charge, double current);
 void hps_beam_destroy(hps_beam*);
 int hps_beam_local_range(const hps_beam*, uint64_t* offset, uint64_t* n_local);
+uint64_t hps_beam_local_stride(const hps_beam*);
 
 /* Replaces UpdateBeamOnDevice + Beam::InitBeamFromDistribution
  * (reference src/beam/src/beam.cu:197-218, beam.cpp:317-369): host arrays of

@@ -1192,6 +1192,7 @@ hps_beam* hps_beam_create(hps_ctx* c, uint64_t n, double mass, double charge, do
 }
 void hps_beam_destroy(hps_beam* b) { delete b; }
 int hps_beam_local_range(const hps_beam* b, uint64_t* off, uint64_t* nl) { *off = 0; *nl = b->n; return HPS_OK; }
+uint64_t hps_beam_local_stride(const hps_beam*) { return 1; }
 
 int hps_beam_upload(hps_beam* b, const double* x, const double* xp, const double* y, const double* yp,
                     const double* phi, const double* w, const uint32_t* loss, const uint32_t* lloss) {

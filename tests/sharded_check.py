@@ -34,20 +34,21 @@ def main():
 
     case = H.Case(lib, n=n, sc=True)
     run = case.run(first, last)
-    nloss = case.beam.get_loss_num("t")
-    nlloss = case.beam.get_loss_num("l")
-    mom = case.moments()
-    st = case.state()
+    st = case.state()            # same call sequence as the single-GPU run below: every Update* call can
+    mom = case.moments()         # mark more longitudinal losses (H3), so the order matters
+    nloss, nlloss = int(mom["loss"]), int(mom["lloss"])
     parts = [None] * world
-    dist.all_gather_object(parts, (case.beam.offset, st))
+    dist.all_gather_object(parts, (case.beam.offset, case.beam.stride, st))
     if rank != 0:
         return
-    full = {k: np.concatenate([p[1][k] for p in sorted(parts, key=lambda t: t[0])]) for k in st}
+    full = {k: np.empty(n, st[k].dtype) for k in st}
+    for off, stride, part in parts:  # local particle j of a rank is global particle off + j * stride
+        for k in st:
+            full[k][off::stride] = part[k]
     # single-GPU run of the same beam on a context without a communicator
     HPSim._ctx_cache.clear()  # the sharded objects keep their own context alive
     one = H.Case(lib, n=n, sc=True)
     run1 = one.run(first, last)
-    one.beam.get_loss_num("l")
     ref = one.state()
     rep = H.compare(full, ref, 1e-9)
     rep.update(mode=mode, world=world, n=n, range=[first, last], kicks=run["kicks"], remesh=(run["remesh"], run1["remesh"]),
