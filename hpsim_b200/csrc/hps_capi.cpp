@@ -94,6 +94,7 @@ struct hps_scheff {
   double2* field = nullptr;
   double2* field_part = nullptr;  // [nr+1][chunks][nz+1] partial fields of the split solve
   u32* field_tickets = nullptr;   // [nr+1]
+  double bin_scale = 0.0;         // fixed-point scale of the last simulate() (depends on the beam size)
 };
 
 namespace {
@@ -878,12 +879,13 @@ int hps_scheff_download_tables(hps_scheff* s, double* bins, double* field, doubl
   ScDev h;
   CK(c, cudaMemcpyAsync(&h, s->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  if (bins) {  // the device mesh is 64-bit fixed point (k_deposit): scale 2^-38
+  if (bins) {  // the device mesh is 64-bit fixed point (k_deposit)
     const size_t nb = (size_t)s->h.nr * s->h.nz;
+    const double scale = s->bin_scale > 0.0 ? s->bin_scale : 1.0;
     for (size_t k = 0; k < nb; ++k) {
       long long q;
       std::memcpy(&q, &bins[k], sizeof(q));
-      bins[k] = (double)q / 274877906944.0;
+      bins[k] = (double)q / scale;
     }
   }
   if (dr_dz) { dr_dz[0] = h.dr; dr_dz[1] = h.dz; }
@@ -937,6 +939,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
 
   const LaunchCfg l = cfg(c, b);
   const BeamView v = view(b);
+  if (sc) { int e = 0; while (e < 32 && (1ull << e) < (unsigned long long)b->h.n_global) ++e; sc->bin_scale = (double)(1ull << (62 - e)); }
   const uint64_t launches0 = c->launches;
   launch_prepare_ops(l, c->d_ops, c->d_opc, (int)nops, b->h.mass, b->h.charge);
   c->launches++;

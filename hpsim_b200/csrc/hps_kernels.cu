@@ -161,7 +161,10 @@ __device__ __forceinline__ void seg_accumulate(double (&acc)[SEG_NS], const Pt& 
 // PPT = particles per thread.  PPT == 2 moves two adjacent particles with one 128-bit access per
 // array; PPT == 1 halves the register footprint and doubles the resident warps (the maps are chains of
 // dependent fp64 operations, so the sweep is latency-bound before it is bandwidth-bound).
-template <int PPT, int MINB, bool FULL>
+// STAGED (PPT == 2 only): tiles of HPS_BLOCK pairs are brought into shared memory by TMA bulk copies, double
+// buffered, one tile ahead of the computation.
+#define HPS_SEG_STAGE_BYTES (HPS_BLOCK * (6 * 16 + 2 * 8))   /* one tile: 6 double2 + 2 uint2 per pair */
+template <int PPT, int MINB, bool FULL, bool STAGED>
 __global__ void __launch_bounds__(HPS_BLOCK, MINB)
 k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
           DevStats* st, const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials,
@@ -208,6 +211,77 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
   for (int s = 0; s < SEG_NS; ++s) acc[s] = 0.0;
   acc[2] = -DBL_MAX;
 
+  if (PPT == 2 && STAGED) {
+    extern __shared__ __align__(128) unsigned char s_stage[];  // [2][HPS_SEG_STAGE_BYTES]
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const u32 npairs = (b.n + 1) >> 1;
+    const u32 ntiles = (npairs + HPS_BLOCK - 1) / HPS_BLOCK;
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](u32 tile, int stage) {  // one thread: 8 bulk copies, one per array
+      const u32 p0 = tile * HPS_BLOCK;
+      const u32 np = min((u32)HPS_BLOCK, npairs - p0);
+      const u32 bd = np * 16u, bf = (np * 8u + 15u) & ~15u;
+      unsigned char* dst = s_stage + (size_t)stage * HPS_SEG_STAGE_BYTES;
+      mbar_expect_tx(&s_bar[stage], 6u * bd + 2u * bf);
+      const double* src[6] = {b.x, b.xp, b.y, b.yp, b.phi, b.w};
+#pragma unroll
+      for (int a = 0; a < 6; ++a) tma_load_1d(dst + a * (HPS_BLOCK * 16), src[a] + 2 * (size_t)p0, bd, &s_bar[stage]);
+      tma_load_1d(dst + 6 * (HPS_BLOCK * 16), b.loss + 2 * (size_t)p0, bf, &s_bar[stage]);
+      tma_load_1d(dst + 6 * (HPS_BLOCK * 16) + HPS_BLOCK * 8, b.lloss + 2 * (size_t)p0, bf, &s_bar[stage]);
+    };
+    if (threadIdx.x == 0 && blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    u32 it = 0;
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int stage = (int)(it & 1u);
+      // the other stage was consumed in the previous iteration (its __syncthreads below has passed)
+      if (threadIdx.x == 0 && tile + gridDim.x < ntiles) {
+        fence_proxy_async();
+        issue(tile + gridDim.x, stage ^ 1);
+      }
+      mbar_wait(&s_bar[stage], (it >> 1) & 1u);
+      const unsigned char* src = s_stage + (size_t)stage * HPS_SEG_STAGE_BYTES;
+      const u32 i2 = tile * HPS_BLOCK + threadIdx.x;
+      const bool act = i2 < npairs;
+      const double2* sd = reinterpret_cast<const double2*>(src);
+      const uint2* sf = reinterpret_cast<const uint2*>(src + 6 * (HPS_BLOCK * 16));
+      double2 X, XP, Y, YP, PH, W;
+      uint2 L, LL;
+      if (act) {
+        X = sd[threadIdx.x]; XP = sd[HPS_BLOCK + threadIdx.x]; Y = sd[2 * HPS_BLOCK + threadIdx.x];
+        YP = sd[3 * HPS_BLOCK + threadIdx.x]; PH = sd[4 * HPS_BLOCK + threadIdx.x]; W = sd[5 * HPS_BLOCK + threadIdx.x];
+        L = sf[threadIdx.x]; LL = sf[HPS_BLOCK + threadIdx.x];
+      }
+      __syncthreads();  // every thread holds its pair in registers: this stage may be refilled
+      if (!act) continue;
+      Pt p[2] = {{X.x, XP.x, Y.x, YP.x, PH.x, W.x, L.x}, {X.y, XP.y, Y.y, YP.y, PH.y, W.y, L.y}};
+      const u32 ll[2] = {LL.x, LL.y};
+      const bool valid[2] = {true, 2 * i2 + 1 < b.n};
+      const u32 g0 = b.offset + 2 * i2 * b.gstride;
+      const u32 g[2] = {g0, g0 + b.gstride};
+      double fc[2] = {0.0, 0.0};
+      bool lf[2] = {false, false};
+      for (int k = 0; k < nops; ++k) apply_op<FULL, 2>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
+      if (nops > 0) {
+        if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p[0].x, p[1].x);
+        if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p[0].xp, p[1].xp);
+        if (dirty & 4) reinterpret_cast<double2*>(b.y)[i2] = make_double2(p[0].y, p[1].y);
+        if (dirty & 8) reinterpret_cast<double2*>(b.yp)[i2] = make_double2(p[0].yp, p[1].yp);
+        if (dirty & 16) reinterpret_cast<double2*>(b.phi)[i2] = make_double2(p[0].phi, p[1].phi);
+        if (dirty & 32) reinterpret_cast<double2*>(b.w)[i2] = make_double2(p[0].w, p[1].w);
+        if ((dirty & 64) && (p[0].loss != L.x || p[1].loss != L.y))
+          reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p[0].loss, p[1].loss);
+      }
+      if (fin_mode != FIN_NONE) {
+        seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
+        if (valid[1]) seg_accumulate(acc, p[1], ll[1], fc[1], lf[1]);
+      }
+    }
+  } else
   if (PPT == 2) {
     const u32 npairs = (b.n + 1) >> 1;
     for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
@@ -270,10 +344,11 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
   }
 }
 #define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*, const __grid_constant__ XrView
-template __global__ void k_segment<2, 2, false>(SEG_ARGS);
-template __global__ void k_segment<1, 3, false>(SEG_ARGS);
-template __global__ void k_segment<1, 4, false>(SEG_ARGS);
-template __global__ void k_segment<1, 3, true>(SEG_ARGS);
+template __global__ void k_segment<2, 2, false, true>(SEG_ARGS);
+template __global__ void k_segment<2, 2, false, false>(SEG_ARGS);
+template __global__ void k_segment<1, 3, false, false>(SEG_ARGS);
+template __global__ void k_segment<1, 4, false, false>(SEG_ARGS);
+template __global__ void k_segment<1, 3, true, false>(SEG_ARGS);
 
 // one thread per op record of the uploaded program (once per simulate() call)
 __global__ void k_prepare_ops(const Op* __restrict__ ops, OpC* opcs, int nops, double mass, double charge) {
@@ -486,16 +561,21 @@ k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int 
 // space_charge_kernel.cu:123-224.  The reference does 4 global atomicAdds per particle into a 16-32 KB
 // table (float, or a double CAS loop) -- the result depends on the order the atomics land in.  Here each
 // block accumulates a private copy in shared memory and flushes its non-zero bins once, and the sums are
-// 64-bit FIXED-POINT (weights scaled by 2^38, |error| <= 2^-39 per weight, i.e. ~1e-12 of a bin):
+// 64-bit FIXED-POINT (weights scaled by a power of two, |error| <= 2^-43 per weight at 1 Mi particles):
 // integer addition is associative, so the mesh is bit-identical from run to run, for any grid and for
 // any split of the beam over GPUs.  sm_100 has no native 64-bit shared-memory atomic (both
 // atomicAdd(double) and atomicAdd(u64) on shared memory compile to ATOMS.CAST.SPIN loops), so a bin is
 // two u32 words updated with native ATOMS.ADD: low word first, the carry rides on the high-word add.
-#define HPS_BIN_SCALE 274877906944.0              /* 2^38 */
-#define HPS_BIN_INV_SCALE (1.0 / 274877906944.0)
+// The scale is 2^(62 - ceil(log2 N)): the largest power of two for which even N unit weights in one bin
+// cannot overflow 63 bits (2^46 at 64 Ki particles, 2^42 at 1 Mi, 2^38 at 16 Mi).
+__host__ __device__ inline double bin_scale(u32 n_global) {
+  int e = 0;
+  while (e < 32 && (1ull << e) < (unsigned long long)n_global) ++e;
+  return (double)(1ull << (62 - e));
+}
 
-__device__ __forceinline__ void bin_add(u32* s_lo, u32* s_hi, int k, double w) {
-  const unsigned long long q = (unsigned long long)__double2ll_rn(w * HPS_BIN_SCALE);  // two's complement
+__device__ __forceinline__ void bin_add(u32* s_lo, u32* s_hi, int k, double w, double scale) {
+  const unsigned long long q = (unsigned long long)__double2ll_rn(w * scale);  // two's complement
   const u32 lo = (u32)q;
   u32 hi = (u32)(q >> 32);
   if (lo) {
@@ -506,7 +586,7 @@ __device__ __forceinline__ void bin_add(u32* s_lo, u32* s_hi, int k, double w) {
 }
 
 struct DepCtx {
-  double phimc, xbar, ybar, epsq, ref, dr, dzg, hl, c2, drdr;
+  double phimc, xbar, ybar, epsq, ref, dr, dzg, hl, c2, drdr, scale;
   int nx, nz;
 };
 
@@ -558,18 +638,18 @@ __device__ __forceinline__ u32 deposit_one(const DepCtx& d, u32 l, u32 ll, doubl
   // its table.  Such a particle is dropped here instead (it carries weight cc = 1 into nowhere).
   int k = (jm1 - 1) * nx + i;
   if (jm1 >= 1 && jm1 <= nz) {
-    bin_add(s_lo, s_hi, k - 1, a * cc);
-    if (i1 != i) bin_add(s_lo, s_hi, k + (i1 - i) - 1, bb * cc);
+    bin_add(s_lo, s_hi, k - 1, a * cc, d.scale);
+    if (i1 != i) bin_add(s_lo, s_hi, k + (i1 - i) - 1, bb * cc, d.scale);
   }
   if (j1 != jm1) {  // dd == 0 otherwise: the reference adds exact zeros
     k = (j1 - 1) * nx + i;
-    bin_add(s_lo, s_hi, k - 1, a * dd);
-    if (i1 != i) bin_add(s_lo, s_hi, k + (i1 - i) - 1, bb * dd);
+    bin_add(s_lo, s_hi, k - 1, a * dd, d.scale);
+    if (i1 != i) bin_add(s_lo, s_hi, k + (i1 - i) - 1, bb * dd, d.scale);
   }
   return 1;
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, u32* ticket, const __grid_constant__ XrView xr) {
   extern __shared__ u32 s_words[];  // [nb] low words, [nb] high words
   if (!sc->remesh) return;
@@ -578,12 +658,14 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
   u32* s_lo = s_words;
   u32* s_hi = s_words + nb;
   for (u32 k = threadIdx.x; k < 2 * nb; k += blockDim.x) s_words[k] = 0u;
-  DepCtx d;
-  d.nx = (int)kp.nr; d.nz = (int)kp.nz;
-  d.phimc = st->v[HPS_STAT_PHI_AVG_R]; d.xbar = st->v[HPS_STAT_X_AVG_GOOD]; d.ybar = st->v[HPS_STAT_Y_AVG_GOOD];
-  d.epsq = st->v[HPS_STAT_X_SIG_GOOD] / st->v[HPS_STAT_Y_SIG_GOOD];
-  d.ref = st->v[HPS_STAT_PHI_AVG_GOOD];
-  {
+  __shared__ DepCtx s_d;  // block-uniform factors, derived once per block with the reference's expression order
+  if (threadIdx.x == 0) {
+    DepCtx d;
+    d.nx = (int)kp.nr; d.nz = (int)kp.nz;
+    d.scale = bin_scale(kp.n_global);
+    d.phimc = st->v[HPS_STAT_PHI_AVG_R]; d.xbar = st->v[HPS_STAT_X_AVG_GOOD]; d.ybar = st->v[HPS_STAT_Y_AVG_GOOD];
+    d.epsq = st->v[HPS_STAT_X_SIG_GOOD] / st->v[HPS_STAT_Y_SIG_GOOD];
+    d.ref = st->v[HPS_STAT_PHI_AVG_GOOD];
     const double beta = sc->beta;
     const double gm = rsqrt(1.0 - beta * beta);
     d.dr = sc->dr;
@@ -592,6 +674,7 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
     d.hl = d.nz * 0.5 * d.dzg;
     d.c2 = beta * gm * wave_len / K_TWOPI;
     d.drdr = d.dr * d.dr;
+    s_d = d;
   }
   __syncthreads();
   u32 cnt = 0;
@@ -604,8 +687,8 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
     const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
     const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
     const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
-    cnt += deposit_one(d, L.x, LL.x, X.x, Y.x, PH.x, s_lo, s_hi, pmax);
-    if (2 * i2 + 1 < b.n) cnt += deposit_one(d, L.y, LL.y, X.y, Y.y, PH.y, s_lo, s_hi, pmax);
+    cnt += deposit_one(s_d, L.x, LL.x, X.x, Y.x, PH.x, s_lo, s_hi, pmax);
+    if (2 * i2 + 1 < b.n) cnt += deposit_one(s_d, L.y, LL.y, X.y, Y.y, PH.y, s_lo, s_hi, pmax);
   }
   __syncthreads();
   for (u32 k = threadIdx.x; k < nb; k += blockDim.x) {
@@ -690,6 +773,7 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
   double2* s_g = reinterpret_cast<double2*>(s_mem + RS * nz);    // [RS][nz]
   double2* s_p = s_g + RS * nz;                                  // [RS][nz] ring partials at nodes zp < nz
   double2* s_red = s_p + RS * nz;                                // [blockDim.x]
+  const double inv_scale = 1.0 / bin_scale(kp.n_global);          // fixed-point mesh, see k_deposit
   // The Green's function slice does not depend on the charge mesh: it is computed first, so on a sharded
   // beam the peers' meshes travel over NVLink meanwhile.
   if (live) {  // Green's function entry (ring rs0+kk -> radius rp, axial offset (t + 1/2) cells)
@@ -736,7 +820,7 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
     if (irp == 0 && ch == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
       st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
     const long long* ibins = reinterpret_cast<const long long*>(bins);  // fixed point, see k_deposit
-    if (live) s_b[kk * nz + t] = (double)ibins[t * nr + rs0 + kk] * HPS_BIN_INV_SCALE;
+    if (live) s_b[kk * nz + t] = (double)ibins[t * nr + rs0 + kk] * inv_scale;
   } else {
     // sharded beam: fold the R rank-local meshes (integer sums: exact, order-independent)
     const u32 nb = nr * nz;
@@ -756,7 +840,7 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
     if (live) {
       unsigned long long a = 0ull;
       for (int r = 0; r < xr.nranks; ++r) a += value(r, t * nr + rs0 + kk);
-      s_b[kk * nz + t] = (double)(long long)a * HPS_BIN_INV_SCALE;
+      s_b[kk * nz + t] = (double)(long long)a * inv_scale;
     }
     if (irp == 0 && ch == 0 && threadIdx.x == 0) {
       u32 cnt = 0;
@@ -1016,20 +1100,25 @@ void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, c
   bool full = false;
   for (int k = 0; k < nops; ++k) full |= host_ops[k].type == OP_DIPOLE_FIRST || host_ops[k].type == OP_DIPOLE_SECOND || host_ops[k].type == OP_BUNCHER;
   const unsigned grid1 = c.grid_seg1, grid2 = c.grid_seg;
+#define SEG_CALL b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr
   if (full) {
-    k_segment<1, 3, true><<<grid1, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr);
+    k_segment<1, 3, true, false><<<grid1, HPS_BLOCK, 0, c.stream>>>(SEG_CALL);
     return;
   }
   switch (c.seg_variant) {
-    case 1:
-      k_segment<1, 3, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr);
-      break;
-    case 2:
-      k_segment<1, 4, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr);
-      break;
-    default:
-      k_segment<2, 2, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr);
+    case 1: k_segment<1, 3, false, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(SEG_CALL); break;
+    case 2: k_segment<1, 4, false, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(SEG_CALL); break;
+    default: k_segment<2, 2, false, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(SEG_CALL); break;
+    case 4: {  // TMA-staged loads: measured slower (35.0 vs 32.0 ms per C2 pass) -- the sweep is not load-bound
+      static int attr_set = 0;
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_segment<2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * HPS_SEG_STAGE_BYTES);
+        attr_set = 1;
+      }
+      k_segment<2, 2, false, true><<<grid2, HPS_BLOCK, 2 * HPS_SEG_STAGE_BYTES, c.stream>>>(SEG_CALL);
+    }
   }
+#undef SEG_CALL
 }
 void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
   k_lloss_pass<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, c.partials, c.ticket, c.xr);
@@ -1119,10 +1208,14 @@ void launch_rel_phi_out(const LaunchCfg& c, const BeamView& b, const DevStats* s
 }
 int segment_occupancy(int variant) {
   int nb = 0;
-  if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3, false>, HPS_BLOCK, 0);
-  else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 4, false>, HPS_BLOCK, 0);
-  else if (variant == -1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3, true>, HPS_BLOCK, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<2, 2, false>, HPS_BLOCK, 0);
+  if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3, false, false>, HPS_BLOCK, 0);
+  else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 4, false, false>, HPS_BLOCK, 0);
+  else if (variant == -1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3, true, false>, HPS_BLOCK, 0);
+  else if (variant != 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<2, 2, false, false>, HPS_BLOCK, 0);
+  else {
+    cudaFuncSetAttribute(k_segment<2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * HPS_SEG_STAGE_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<2, 2, false, true>, HPS_BLOCK, 2 * HPS_SEG_STAGE_BYTES);
+  }
   return nb;
 }
 

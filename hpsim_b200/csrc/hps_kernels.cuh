@@ -188,6 +188,39 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA bulk staging of particle tiles (cp.async.bulk global -> shared, completion on an mbarrier)
+// ------------------------------------------------------------------------------------------------
+// The sweeps are latency-bound: a thread loads its pair, computes for ~1 us, stores, loads the next pair.
+// Staging tile t+1 with one bulk copy per array while tile t is being computed takes the global-load
+// latency off the critical path without spending registers on a software prefetch.
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 16-byte aligned source / destination, size a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, u32 bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // element maps (one particle)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double beta_of(double w, double mass) {
