@@ -73,10 +73,18 @@ struct Saved {
 
 }  // namespace
 
+// Optional sharding of the oracle over several PROCESSES (tests only: tests/test_sharded_oracle.py drives
+// two ranks over torch.distributed/gloo).  It restates, on the CPU, which quantities a particle-sharded
+// beam has to exchange and where: every sum / count / max below goes through xr().
+typedef void (*hps_oracle_allreduce_fn)(double* buf, int count, int op /* 0 sum, 1 max */, void* user);
+
 struct hps_ctx {
   std::string err;
   int compat = 1;
   int nthreads = 0;
+  int rank = 0, nranks = 1;
+  hps_oracle_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
   // engine statics (simulation/src/simulation_engine.cu:19-33)
   uint prev_end = 0xffffffffu;
   double design_w = 0.0;
@@ -86,7 +94,10 @@ struct hps_ctx {
 
 struct hps_beam {
   hps_ctx* ctx;
-  uint n;
+  uint n;                     // local particles
+  uint ng;                    // particles of the whole beam (== n when unsharded)
+  uint off = 0, stride = 1;   // local particle i is global particle off + i * stride
+  uint gi(uint i) const { return off + i * stride; }
   double mass, charge, current, freq, design_w;
   std::vector<double> x, xp, y, yp, phi, phi_r, w;
   std::vector<uint> loss, lloss;
@@ -126,6 +137,16 @@ int fail(hps_ctx* c, int code, const std::string& m) {
   return code;
 }
 
+// cross-rank fold of `count` doubles (no-op for a single process)
+void xr(const hps_beam* b, double* v, int count, int op = 0) {
+  if (b->ctx->nranks > 1) b->ctx->allreduce(v, count, op, b->ctx->allreduce_user);
+}
+double xr1(const hps_beam* b, double v, int op = 0) { xr(b, &v, 1, op); return v; }
+// value held by the owner of global particle 0, seen by every rank
+double from_ref_particle(const hps_beam* b, const std::vector<double>& a) {
+  return xr1(b, (b->off == 0 && b->n > 0) ? a[0] : 0.0);
+}
+
 // ------------------------------------------------------------------ reductions
 // beam/inc/beam_kernel.cu:84-166 (XReduceKernel) + finalisers :1412-1427
 enum Filter { F_LOSS, F_GOOD };
@@ -138,6 +159,7 @@ long double sum1(const hps_beam* b, const std::vector<double>& a, Filter f) {
 #pragma omp parallel for reduction(+ : s) schedule(static)
   for (long i = 0; i < n; ++i)
     if (keep(b, (uint)i, f)) s += a[i];
+  if (b->ctx->nranks > 1) return (long double)xr1(b, (double)s);
   return s;
 }
 void sum2(const hps_beam* b, const std::vector<double>& a, Filter f, long double* s1, long double* s2) {
@@ -146,6 +168,7 @@ void sum2(const hps_beam* b, const std::vector<double>& a, Filter f, long double
 #pragma omp parallel for reduction(+ : p, q) schedule(static)
   for (long i = 0; i < n; ++i)
     if (keep(b, (uint)i, f)) { p += a[i]; q += (long double)(a[i] * a[i]); }
+  if (b->ctx->nranks > 1) { double t[2] = {(double)p, (double)q}; xr(b, t, 2); p = t[0]; q = t[1]; }
   *s1 = p; *s2 = q;
 }
 
@@ -153,24 +176,24 @@ void sum2(const hps_beam* b, const std::vector<double>& a, Filter f, long double
 void UpdateLoss(hps_beam* b) {
   uint c = 0;
   for (uint i = 0; i < b->n; ++i) c += b->loss[i] != 0;
-  b->s.num_loss = c;
+  b->s.num_loss = (uint)xr1(b, c);
 }
 void UpdateLlossCount(hps_beam* b) {
   uint c = 0;
   for (uint i = 0; i < b->n; ++i) c += b->lloss[i] != 0;
-  b->s.num_lloss = c;
+  b->s.num_lloss = (uint)xr1(b, c);
 }
 // beam.cu:1233-1255 + beam_kernel.cu:180-259
 void UpdateGoodParticleCount(hps_beam* b) {
   uint c = 0;
   for (uint i = 0; i < b->n; ++i) c += (b->loss[i] + b->lloss[i]) == 0;
-  b->s.num_good = c;
+  b->s.num_good = (uint)xr1(b, c);
 }
 // beam.cu:411-436; finalisers beam_kernel.cu:1412-1427
 void UpdateAvg(hps_beam* b, const std::vector<double>& a, int stat, bool good_only) {
   double s = (double)sum1(b, a, good_only ? F_GOOD : F_LOSS);
   if (!good_only) {
-    double surv = (double)(uint)(b->n - b->s.num_loss);
+    double surv = (double)(uint)(b->ng - b->s.num_loss);
     b->s.v[stat] = s / surv;
   } else {
     b->s.v[stat] = b->s.num_good > 0 ? s / b->s.num_good : -99999;
@@ -178,16 +201,16 @@ void UpdateAvg(hps_beam* b, const std::vector<double>& a, int stat, bool good_on
 }
 // beam.cu:651-678; finalisers beam_kernel.cu:1429-1446
 void UpdateSig(hps_beam* b, const std::vector<double>& a, int stat, bool good_only) {
-  if (!(b->n > 2)) return;  // beam.cpp:866-955 guards
+  if (!(b->ng > 2)) return;  // beam.cpp:866-955 guards
   long double s1, s2;
   sum2(b, a, good_only ? F_GOOD : F_LOSS, &s1, &s2);
-  double d = good_only ? (double)b->s.num_good : (double)(uint)(b->n - b->s.num_loss);
+  double d = good_only ? (double)b->s.num_good : (double)(uint)(b->ng - b->s.num_loss);
   double avg = (double)s1 / d, avg2 = (double)s2 / d;
   b->s.v[stat] = std::sqrt(avg2 - avg * avg);
 }
 // beam.cu:1122-1130 + beam_kernel.cu:1506-1522
 void UpdateRelativePhi(hps_beam* b, bool use_good) {
-  const double ref = use_good ? b->s.v[HPS_STAT_PHI_AVG_GOOD] : b->phi[0];
+  const double ref = use_good ? b->s.v[HPS_STAT_PHI_AVG_GOOD] : from_ref_particle(b, b->phi);
   const long n = b->n;
 #pragma omp parallel for schedule(static)
   for (long i = 0; i < n; ++i) {
@@ -208,7 +231,7 @@ void UpdateLongitudinalLoss(hps_beam* b) {
 // beam.cu:739-761 + beam_kernel.cu:612-723, 1385-1394
 void UpdateAvgXY(hps_beam* b) {
   double sx = (double)sum1(b, b->x, F_LOSS), sy = (double)sum1(b, b->y, F_LOSS);
-  double surv = (double)(uint)(b->n - b->s.num_loss);
+  double surv = (double)(uint)(b->ng - b->s.num_loss);
   b->s.v[HPS_STAT_X_AVG] = sx / surv;
   b->s.v[HPS_STAT_Y_AVG] = sy / surv;
 }
@@ -217,7 +240,7 @@ void UpdateAvgSigXY(hps_beam* b) {
   long double x1, x2, y1, y2;
   sum2(b, b->x, F_GOOD, &x1, &x2);
   sum2(b, b->y, F_GOOD, &y1, &y2);
-  double surv = (double)(uint)(b->n - b->s.num_loss);
+  double surv = (double)(uint)(b->ng - b->s.num_loss);
   double xa = (double)x1 / surv, x2a = (double)x2 / surv, ya = (double)y1 / surv, y2a = (double)y2 / surv;
   b->s.v[HPS_STAT_X_AVG_GOOD] = xa;
   b->s.v[HPS_STAT_X_SIG_GOOD] = std::sqrt(x2a - xa * xa);
@@ -237,6 +260,8 @@ void UpdateMaxRPhi(hps_beam* b) {
       r2m = r2m < r2 ? r2 : r2m;
       pm = pm < tp ? tp : pm;
     }
+  r2m = xr1(b, r2m, 1);
+  pm = xr1(b, pm, 1);
   b->s.v[HPS_STAT_R_MAX] = std::sqrt(r2m);
   b->s.v[HPS_STAT_ABS_PHI_MAX] = pm;
 }
@@ -249,16 +274,21 @@ void emit_sums(const hps_beam* b, const std::vector<double>& u, const std::vecto
       c += up[i]; c2 += (long double)(up[i] * up[i]);
       ac += (long double)(u[i] * up[i]);
     }
+  if (b->ctx->nranks > 1) {
+    double t[5] = {(double)a, (double)a2, (double)c, (double)c2, (double)ac};
+    xr(b, t, 5);
+    a = t[0]; a2 = t[1]; c = t[2]; c2 = t[3]; ac = t[4];
+  }
   o[0] = a; o[1] = a2; o[2] = c; o[3] = c2; o[4] = ac;
 }
 void UpdateTransverseEmittance(hps_beam* b, const std::vector<double>& u, const std::vector<double>& up,
                                int avg, int sig, int pavg, int psig, int emit) {
   long double o[5];
   emit_sums(b, u, up, o);
-  double surv = (double)(uint)(b->n - b->s.num_loss);
+  double surv = (double)(uint)(b->ng - b->s.num_loss);
   double x = (double)o[0] / surv, x2 = (double)o[1] / surv, xp = (double)o[2] / surv,
          xp2 = (double)o[3] / surv, xxp = (double)o[4] / surv;
-  double gamma1 = b->w[0] / b->mass;
+  double gamma1 = from_ref_particle(b, b->w) / b->mass;
   double betagamma = std::sqrt(gamma1 * (gamma1 + 2.0));
   b->s.v[avg] = x;
   b->s.v[sig] = std::sqrt(x2 - x * x);
@@ -267,13 +297,13 @@ void UpdateTransverseEmittance(hps_beam* b, const std::vector<double>& u, const 
   b->s.v[emit] = std::sqrt((x2 - x * x) * (xp2 - xp * xp) - (xxp - x * xp) * (xxp - x * xp)) * betagamma;
 }
 void UpdateEmittance(hps_beam* b) {  // beam.cpp:981-990
-  if (!(b->n > 2)) return;
+  if (!(b->ng > 2)) return;
   UpdateTransverseEmittance(b, b->x, b->xp, HPS_STAT_X_AVG, HPS_STAT_X_SIG, HPS_STAT_XP_AVG, HPS_STAT_XP_SIG, HPS_STAT_X_EMIT);
   UpdateTransverseEmittance(b, b->y, b->yp, HPS_STAT_Y_AVG, HPS_STAT_Y_SIG, HPS_STAT_YP_AVG, HPS_STAT_YP_SIG, HPS_STAT_Y_EMIT);
   UpdateRelativePhi(b, false);
   long double o[5];
   emit_sums(b, b->phi_r, b->w, o);
-  double surv = (double)(uint)(b->n - b->s.num_loss);
+  double surv = (double)(uint)(b->ng - b->s.num_loss);
   double phi = (double)o[0] / surv, phi2 = (double)o[1] / surv, w = (double)o[2] / surv,
          w2 = (double)o[3] / surv, phi_w = (double)o[4] / surv;
   double phi_var = phi2 - phi * phi, w_var = w2 - w * w, cov = phi_w - phi * w;
@@ -285,7 +315,7 @@ void UpdateEmittance(hps_beam* b) {  // beam.cpp:981-990
 }
 // beam.cpp:1003-1016
 void UpdateStatForSpaceCharge(hps_beam* b) {
-  if (!(b->n > 2)) return;
+  if (!(b->ng > 2)) return;
   UpdateLongitudinalLoss(b);
   UpdateGoodParticleCount(b);
   UpdateAvg(b, b->phi, HPS_STAT_PHI_AVG_GOOD, true);
@@ -463,6 +493,7 @@ double GapFirstHalf(hps_beam* b, double wavelen_in, double design_w_in, double p
   // the write happens only inside the loss==0 branch; with at least one live particle it lands
   bool any = false;
   for (uint i = 0; i < b->n && !any; ++i) any = b->loss[i] == 0;
+  if (b->ctx->nranks > 1) any = xr1(b, any ? 1.0 : 0.0, 1) != 0.0;
   return any ? wave_len : wavelen_in;
 }
 // simulation_kernel.cu:290-308
@@ -601,8 +632,8 @@ void RotationMap(hps_beam* b, double angle) {
 // simulation_kernel.cu:543-575 (particle 0 exempt, centred on the beam centroid)
 void CircularAperture(hps_beam* b, double aper, uint idx) {
   const double cx = b->s.v[HPS_STAT_X_AVG], cy = b->s.v[HPS_STAT_Y_AVG];
-  for (uint i = 1; i < b->n; ++i) {
-    if (b->loss[i] != 0) continue;
+  for (uint i = 0; i < b->n; ++i) {
+    if (b->gi(i) == 0 || b->loss[i] != 0) continue;
     double aper2 = aper * aper;
     double x = b->x[i] - cx, y = b->y[i] - cy;
     if (x * x + y * y > aper2) b->loss[i] = idx;
@@ -610,8 +641,8 @@ void CircularAperture(hps_beam* b, double aper, uint idx) {
 }
 void RectangularAperture(hps_beam* b, double xl, double xr, double yt, double yb, uint idx) {
   const double cx = b->s.v[HPS_STAT_X_AVG], cy = b->s.v[HPS_STAT_Y_AVG];
-  for (uint i = 1; i < b->n; ++i) {
-    if (b->loss[i] != 0) continue;
+  for (uint i = 0; i < b->n; ++i) {
+    if (b->gi(i) == 0 || b->loss[i] != 0) continue;
     double xmin = cx - xl, xmax = cx + xr, ymin = cy - yb, ymax = cy + yt;
     double x = b->x[i], y = b->y[i];
     if (x < xmin || x > xmax || y < ymin || y > ymax) b->loss[i] = idx;
@@ -837,6 +868,10 @@ void Deposit(hps_scheff* s, const hps_beam* b, double beta, double freq) {
     s->bins[k - 1] += bb * d;
     s->num_on_mesh += 1;
   }
+  if (b->ctx->nranks > 1) {  // the r-z charge mesh and the on-mesh count are the only SCHEFF data that cross ranks
+    xr(b, s->bins.data(), (int)s->bins.size());
+    s->num_on_mesh = (uint)xr1(b, s->num_on_mesh);
+  }
 }
 // space_charge_kernel.cu:472-568 (the -DDOUBLE_PRECISION field solve)
 void UpdateFieldTable(hps_scheff* s) {
@@ -864,18 +899,20 @@ void UpdateFieldTable(hps_scheff* s) {
 // space_charge_kernel.cu:573-706
 void ApplyKick(hps_scheff* s, hps_beam* b, double current, double freq, double beta, uint adj_bunch, double length,
                double ratio_r, double ratio_z, double ratio_q, double ratio_gm) {
-  const uint nx = s->nx, nz = s->nz, n = b->n;
+  const uint nx = s->nx, nz = s->nz, n = b->ng, nloc = b->n;
   // H2: launched <<<grid, blck/4>>> with `while(indx > 0 && ...)`: global thread 0 never runs
   const uint np2 = NextPow2(n);
   const uint stride = np2 >= 4 ? np2 / 4 : 1;
   const double phimc = b->s.v[HPS_STAT_PHI_AVG_R], xbar = b->s.v[HPS_STAT_X_AVG_GOOD], ybar = b->s.v[HPS_STAT_Y_AVG_GOOD];
   const double epsq = b->s.v[HPS_STAT_X_SIG_GOOD] / b->s.v[HPS_STAT_Y_SIG_GOOD];
   const double mass = b->mass;
-  const long ln = n;
+  const long ln = nloc;
 #pragma omp parallel for schedule(static)
-  for (long li = 1; li < ln; ++li) {
+  for (long li = 0; li < ln; ++li) {
     const uint indx = (uint)li;
-    if (b->ctx->compat && indx % stride == 0) continue;
+    const uint gindx = b->gi(indx);  // the quirks are tied to the index in the whole beam
+    if (gindx == 0) continue;
+    if (b->ctx->compat && gindx % stride == 0) continue;
     if (!(b->loss[indx] == 0 && b->lloss[indx] == 0)) continue;
     double x = b->x[indx], y = b->y[indx], xp = b->xp[indx], yp = b->yp[indx], phi = b->phi_r[indx], w = b->w[indx];
     double gmg = rsqrt_(1.0 - beta * beta);
@@ -954,8 +991,8 @@ void ScheffStart(hps_scheff* s, hps_beam* b, double length) {
   UpdateStatForSpaceCharge(b);
   uint good_cnt = b->s.num_good;
   double sigphi = b->s.v[HPS_STAT_PHI_SIG_GOOD];
-  double sigx = b->n < 2 ? 0.0 : b->s.v[HPS_STAT_X_SIG_GOOD];
-  double sigy = b->n < 2 ? 0.0 : b->s.v[HPS_STAT_Y_SIG_GOOD];
+  double sigx = b->ng < 2 ? 0.0 : b->s.v[HPS_STAT_X_SIG_GOOD];
+  double sigy = b->ng < 2 ? 0.0 : b->s.v[HPS_STAT_Y_SIG_GOOD];
   double ke = b->s.v[HPS_STAT_W_AVG_GOOD];
   double gamma = (double)ke / b->mass + 1.0;
   double beta = std::sqrt(1.0 - 1.0 / (gamma * gamma));
@@ -994,7 +1031,7 @@ void ScheffStart(hps_scheff* s, hps_beam* b, double length) {
       s->dr = 3.0 * b->s.v[getenv("HPS_SIGX") ? HPS_STAT_X_SIG_GOOD : HPS_STAT_Y_SIG_GOOD] / s->nx;
       s->dz = 3.0 * bl * b->s.v[HPS_STAT_PHI_SIG_GOOD] / (s->nz * PI);  // H8: clamp is dead code
     }
-    UpdateGreenTable(s, freq, beta, b->n, b->current * frac / b->mass, adj_bunch);
+    UpdateGreenTable(s, freq, beta, b->ng, b->current * frac / b->mass, adj_bunch);
     Deposit(s, b, beta, freq);
     UpdateFieldTable(s);
     ApplyKick(s, b, b->current * frac, freq, beta, adj_bunch, length, 1, 1, 1, 1.0);
@@ -1149,7 +1186,13 @@ const char* hps_last_error(const hps_ctx* c) { return c ? c->err.c_str() : g_err
 int hps_ctx_set_compat(hps_ctx* c, int v) { c->compat = v; return HPS_OK; }
 int hps_comm_unique_id(void*) { return HPS_ERR_COMM; }
 int hps_ctx_comm_init(hps_ctx* c, int, int nranks, const void*) {
-  return nranks == 1 ? HPS_OK : fail(c, HPS_ERR_COMM, "the CPU oracle is single-process");
+  return nranks == 1 ? HPS_OK : fail(c, HPS_ERR_COMM, "the CPU oracle shards through hps_oracle_set_comm (tests only)");
+}
+// oracle-only: shard beams created afterwards over `nranks` processes; `fn` folds a vector over all ranks
+int hps_oracle_set_comm(hps_ctx* c, int rank, int nranks, hps_oracle_allreduce_fn fn, void* user) {
+  if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !fn)) return fail(c, HPS_ERR_ARG, "bad communicator");
+  c->rank = rank; c->nranks = nranks; c->allreduce = fn; c->allreduce_user = user;
+  return HPS_OK;
 }
 int hps_ctx_comm_mode(hps_ctx*) { return 0; }
 int hps_ctx_synchronize(hps_ctx*) { return HPS_OK; }
@@ -1183,16 +1226,19 @@ int hps_oracle_get_threads(void) {
 hps_beam* hps_beam_create(hps_ctx* c, uint64_t n, double mass, double charge, double current) {
   if (!c || n == 0 || n > 0xffffffffull) { fail(c, HPS_ERR_ARG, "bad particle count"); return nullptr; }
   hps_beam* b = new hps_beam();
-  b->ctx = c; b->n = (uint)n; b->mass = mass; b->charge = charge; b->current = current;
+  b->ctx = c; b->ng = (uint)n; b->mass = mass; b->charge = charge; b->current = current;
+  // interleaved ownership like the product (hps_beam_create in hpsim_b200/csrc/hps_capi.cpp)
+  b->off = (uint)c->rank; b->stride = (uint)c->nranks;
+  b->n = n > (uint64_t)c->rank ? (uint)((n - c->rank + c->nranks - 1) / c->nranks) : 0;
   b->freq = 0.0; b->design_w = 0.0;
-  for (auto* v : {&b->x, &b->xp, &b->y, &b->yp, &b->phi, &b->phi_r, &b->w}) v->assign(n, 0.0);
-  b->loss.assign(n, 0); b->lloss.assign(n, 0);
+  for (auto* v : {&b->x, &b->xp, &b->y, &b->yp, &b->phi, &b->phi_r, &b->w}) v->assign(b->n, 0.0);
+  b->loss.assign(b->n, 0); b->lloss.assign(b->n, 0);
   std::memset(&b->s, 0, sizeof(b->s));
   return b;
 }
 void hps_beam_destroy(hps_beam* b) { delete b; }
-int hps_beam_local_range(const hps_beam* b, uint64_t* off, uint64_t* nl) { *off = 0; *nl = b->n; return HPS_OK; }
-uint64_t hps_beam_local_stride(const hps_beam*) { return 1; }
+int hps_beam_local_range(const hps_beam* b, uint64_t* off, uint64_t* nl) { *off = b->off; *nl = b->n; return HPS_OK; }
+uint64_t hps_beam_local_stride(const hps_beam* b) { return b->stride; }
 
 int hps_beam_upload(hps_beam* b, const double* x, const double* xp, const double* y, const double* yp,
                     const double* phi, const double* w, const uint32_t* loss, const uint32_t* lloss) {
@@ -1200,9 +1246,10 @@ int hps_beam_upload(hps_beam* b, const double* x, const double* xp, const double
   std::copy(x, x + n, b->x.begin()); std::copy(xp, xp + n, b->xp.begin());
   std::copy(y, y + n, b->y.begin()); std::copy(yp, yp + n, b->yp.begin());
   std::copy(phi, phi + n, b->phi.begin()); std::copy(w, w + n, b->w.begin());
-  b->x[0] = b->xp[0] = b->y[0] = b->yp[0] = 0.0;  // beam.cpp:344-345
-  if (loss) { std::copy(loss, loss + n, b->loss.begin()); b->loss[0] = 0; } else std::fill(b->loss.begin(), b->loss.end(), 0);
-  if (lloss) { std::copy(lloss, lloss + n, b->lloss.begin()); b->lloss[0] = 0; } else std::fill(b->lloss.begin(), b->lloss.end(), 0);
+  const bool own0 = b->off == 0 && n > 0;  // the reference particle lives on the owner of global index 0
+  if (own0) b->x[0] = b->xp[0] = b->y[0] = b->yp[0] = 0.0;  // beam.cpp:344-345
+  if (loss) { std::copy(loss, loss + n, b->loss.begin()); if (own0) b->loss[0] = 0; } else std::fill(b->loss.begin(), b->loss.end(), 0);
+  if (lloss) { std::copy(lloss, lloss + n, b->lloss.begin()); if (own0) b->lloss[0] = 0; } else std::fill(b->lloss.begin(), b->lloss.end(), 0);
   InitPhiAvgGood(b);
   return HPS_OK;
 }
@@ -1228,19 +1275,21 @@ int hps_beam_download_phi_relative(hps_beam* b, int use_good, double* out) {
 // beam.cpp:481-537 (glibc rand(); the reference is linked against the same libc)
 int hps_beam_set_dc(hps_beam* b, double ax, double bx, double ex, double ay, double by, double ey, double dphi,
                     double sync_phi, double sync_w, uint32_t seed) {
-  const uint n = b->n;
+  const uint n = b->ng;  // every rank draws the whole rand() sequence and keeps its own particles
   if (seed == 0) std::srand(std::time(NULL)); else std::srand(seed);
   double rs = 1.0;
   double gx = (1.0 + ax * ax) / bx, xmx = std::sqrt(ex / gx), xpmx = std::sqrt(ex * gx), dx = -ax / gx;
   double gy = (1.0 + ay * ay) / by, ymx = std::sqrt(ey / gy), ypmx = std::sqrt(ey * gy), dy = -ay / gy;
-  for (uint i = 0; i < n; ++i) {
+  for (uint g = 0; g < n; ++g) {
     double r1, r2, r3, r4, r5;
     do {
       do { r1 = 2.0 * std::rand() / RAND_MAX - 1.0; r2 = 2.0 * std::rand() / RAND_MAX - 1.0; } while (r1 * r1 + r2 * r2 > 1.0);
       do { r3 = 2.0 * std::rand() / RAND_MAX - 1.0; r4 = 2.0 * std::rand() / RAND_MAX - 1.0; } while (r3 * r3 + r4 * r4 > 1.0);
     } while (r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 > 1.0);
     r1 *= rs; r2 *= rs; r3 *= rs; r4 *= rs;
-    r5 = 2.0 * (double)(i + 1.0) / (double)n - 1.0;
+    r5 = 2.0 * (double)(g + 1.0) / (double)n - 1.0;
+    if (g < b->off || (g - b->off) % b->stride != 0) continue;
+    const uint i = (g - b->off) / b->stride;
     b->x[i] = 0.01 * (r1 * xmx + dx * r2 * xpmx);
     b->xp[i] = r2 * xpmx;
     b->y[i] = 0.01 * (r3 * ymx + dy * r4 * ypmx);
@@ -1248,7 +1297,7 @@ int hps_beam_set_dc(hps_beam* b, double ax, double bx, double ex, double ay, dou
     b->phi[i] = r5 * dphi + sync_phi;
     b->w[i] = sync_w;
   }
-  b->x[0] = b->xp[0] = b->y[0] = b->yp[0] = 0.0;
+  if (b->off == 0 && b->n > 0) b->x[0] = b->xp[0] = b->y[0] = b->yp[0] = 0.0;
   std::fill(b->loss.begin(), b->loss.end(), 0);
   std::fill(b->lloss.begin(), b->lloss.end(), 0);
   InitPhiAvgGood(b);
@@ -1257,7 +1306,7 @@ int hps_beam_set_dc(hps_beam* b, double ax, double bx, double ex, double ay, dou
 // beam.cpp:391-463
 int hps_beam_set_waterbag(hps_beam* b, double ax, double bx, double ex, double ay, double by, double ey, double az,
                           double bz, double ez, double sync_phi, double sync_w, double freq, uint32_t seed) {
-  const uint n = b->n;
+  const uint n = b->ng;  // every rank draws the whole rand() sequence and keeps its own particles
   if (seed == 0) std::srand(std::time(NULL)); else std::srand(seed);
   double rs = 1.0;
   double gx = (1.0 + ax * ax) / bx, xmx = std::sqrt(ex / gx), xpmx = std::sqrt(ex * gx), dx = -ax / gx;
@@ -1267,7 +1316,7 @@ int hps_beam_set_waterbag(hps_beam* b, double ax, double bx, double ex, double a
   b->freq = freq;
   double gm = sync_w / b->mass + 1.0;
   double beta = std::sqrt(1.0 - 1.0 / (gm * gm));
-  for (uint i = 0; i < n; ++i) {
+  for (uint g = 0; g < n; ++g) {
     double r1, r2, r3, r4, r5, r6;
     do {
       do { r1 = 2.0 * std::rand() / RAND_MAX - 1.0; r2 = 2.0 * std::rand() / RAND_MAX - 1.0; } while (r1 * r1 + r2 * r2 > 1.0);
@@ -1275,6 +1324,8 @@ int hps_beam_set_waterbag(hps_beam* b, double ax, double bx, double ex, double a
       do { r5 = 2.0 * std::rand() / RAND_MAX - 1.0; r6 = 2.0 * std::rand() / RAND_MAX - 1.0; } while (r5 * r5 + r6 * r6 > 1.0);
     } while (r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 + r5 * r5 + r6 * r6 > 1.0);
     r1 *= rs; r2 *= rs; r3 *= rs; r4 *= rs; r5 *= rs; r6 *= rs;
+    if (g < b->off || (g - b->off) % b->stride != 0) continue;
+    const uint i = (g - b->off) / b->stride;
     b->x[i] = 0.01 * (r1 * xmx + dx * r2 * xpmx);
     b->xp[i] = r2 * xpmx;
     b->y[i] = 0.01 * (r3 * ymx + dy * r4 * ypmx);
@@ -1282,7 +1333,7 @@ int hps_beam_set_waterbag(hps_beam* b, double ax, double bx, double ex, double a
     b->phi[i] = -(r5 * zmx + dz * zpmx * r6) * 2.0 * M_PI / (beta * wave_len) + sync_phi;
     b->w[i] = 2.0 * sync_w * zpmx * r6 + sync_w;
   }
-  b->x[0] = b->xp[0] = b->y[0] = b->yp[0] = 0.0;
+  if (b->off == 0 && b->n > 0) b->x[0] = b->xp[0] = b->y[0] = b->yp[0] = 0.0;
   std::fill(b->loss.begin(), b->loss.end(), 0);
   std::fill(b->lloss.begin(), b->lloss.end(), 0);
   InitPhiAvgGood(b);
@@ -1305,21 +1356,21 @@ int hps_beam_restore(hps_beam* b, int slot) {  // beam.cpp:603-647
   UpdateRelativePhi(b, true);
   return HPS_OK;
 }
-int hps_beam_set_ref_w(hps_beam* b, double w) { b->w[0] = w; b->design_w = w; return HPS_OK; }
-int hps_beam_set_ref_phi(hps_beam* b, double phi) { b->phi[0] = phi; return HPS_OK; }
+int hps_beam_set_ref_w(hps_beam* b, double w) { if (b->off == 0 && b->n > 0) b->w[0] = w; b->design_w = w; return HPS_OK; }
+int hps_beam_set_ref_phi(hps_beam* b, double phi) { if (b->off == 0 && b->n > 0) b->phi[0] = phi; return HPS_OK; }
 int hps_beam_set_frequency(hps_beam* b, double f) { b->freq = f; return HPS_OK; }
-double hps_beam_get_ref_w(hps_beam* b) { return b->w[0]; }
-double hps_beam_get_ref_phi(hps_beam* b) { return b->phi[0]; }
+double hps_beam_get_ref_w(hps_beam* b) { return from_ref_particle(b, b->w); }
+double hps_beam_get_ref_phi(hps_beam* b) { return from_ref_particle(b, b->phi); }
 double hps_beam_get_frequency(const hps_beam* b) { return b->freq; }
 double hps_beam_get_mass(const hps_beam* b) { return b->mass; }
 double hps_beam_get_charge(const hps_beam* b) { return b->charge; }
 double hps_beam_get_current(const hps_beam* b) { return b->current; }
-uint64_t hps_beam_get_size(const hps_beam* b) { return b->n; }
+uint64_t hps_beam_get_size(const hps_beam* b) { return b->ng; }
 
 int hps_beam_shift(hps_beam* b, int coord, double v) {  // beam.cpp:1595-1642 + beam_kernel.cu:1489-1496
   std::vector<double>* a[6] = {&b->x, &b->xp, &b->y, &b->yp, &b->phi, &b->w};
   if (coord < 0 || coord > 5) return fail(b->ctx, HPS_ERR_ARG, "bad coordinate");
-  for (uint i = 1; i < b->n; ++i) (*a[coord])[i] += v;
+  for (uint i = 0; i < b->n; ++i) if (b->gi(i) != 0) (*a[coord])[i] += v;
   if (coord == HPS_PHI) InitPhiAvgGood(b);
   return HPS_OK;
 }
@@ -1330,8 +1381,8 @@ int hps_beam_cut(hps_beam* b, int coord, double lo, double hi) {  // beam.cpp:15
     case HPS_W: a = &b->w; break; case HPS_PHI: a = &b->phi; break;
     default: return fail(b->ctx, HPS_ERR_ARG, "cut supports x, y, w, phi");
   }
-  for (uint i = 1; i < b->n; ++i)
-    if (b->loss[i] == 0 && (*a)[i] < hi && (*a)[i] > lo) b->loss[i] = 99999;
+  for (uint i = 0; i < b->n; ++i)
+    if (b->gi(i) != 0 && b->loss[i] == 0 && (*a)[i] < hi && (*a)[i] > lo) b->loss[i] = 99999;
   return HPS_OK;
 }
 
@@ -1469,7 +1520,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
   auto t1 = std::chrono::steady_clock::now();
   if (out) {
     std::memset(out, 0, sizeof(*out));
-    out->particles = b->n;
+    out->particles = b->ng;
     out->elements = last >= first ? last - first + 1 : 0;
     out->kicks = sc ? sc->kicks - k0 : 0;
     out->remesh = sc ? sc->remesh - r0 : 0;
