@@ -54,6 +54,8 @@ struct hps_ctx {
   XrBox* xr_box = nullptr;
   void* xr_mapped[HPS_XR_MAXR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
+  int pdl = 1;       // HPSIM_PDL=0 turns programmatic dependent launch off
+  u32 mesh_seq = 0;  // launch counter of k_field: sequence number of the mesh hand-off (same on all ranks)
   // optional per-launch timing (hps_ctx_set_profile): one event between consecutive launches
   int profile = 0;
   std::vector<cudaEvent_t> prof_ev;
@@ -137,6 +139,7 @@ LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
   l.partials = c->partials;
   l.ticket = c->ticket;
   l.xr = c->xr;
+  l.pdl = c->pdl && !c->profile;  // the per-launch events of profile mode sit between the kernels anyway
   return l;
 }
 
@@ -335,6 +338,7 @@ hps_ctx* hps_ctx_create(int device) {
   std::memset(&c->xr, 0, sizeof(c->xr));
   c->xr.nranks = 1;
   if (const char* v = getenv("HPSIM_SEG_VARIANT")) c->seg_variant = atoi(v);
+  if (const char* v = getenv("HPSIM_PDL")) c->pdl = atoi(v);
   int occ = ok ? segment_occupancy(c->seg_variant) : 0;
   if (occ < 1) occ = 1;
   c->seg_grid_cap = (unsigned)c->num_sms * (unsigned)occ;
@@ -980,7 +984,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
         return fail(c, HPS_ERR_COMM, "ncclAllGather of the charge mesh failed");
     }
     prof_mark(c, HPS_PROF_FIELD);
-    if (e == cudaSuccess) e = launch_field(l, b->st, sc->dev, sc->bins, sc->field, sc->field_part, sc->field_tickets, s.kp);
+    if (e == cudaSuccess) e = launch_field(l, b->st, sc->dev, sc->bins, sc->field, sc->field_part, sc->field_tickets, s.kp, ++c->mesh_seq);
     if (e != cudaSuccess) return fail(c, HPS_ERR_CUDA, std::string("kick launch: ") + cudaGetErrorString(e));
     c->launches += 3;
   }

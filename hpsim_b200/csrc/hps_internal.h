@@ -71,7 +71,8 @@ struct DevStats {
 
 struct ScDev {
   double dr, dz;
-  u32 num_on_mesh;
+  u32 num_on_mesh;      // particles this rank deposited on the mesh (k_deposit)
+  u32 num_on_mesh_all;  // ... of the whole beam (k_field); what the off-mesh point-charge kick uses
   u32 good_cnt_old;
   double sigr_old, sigz_old, gm_old;
   // decision of the current kick

@@ -176,6 +176,8 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
   __shared__ double s_total[SEG_NS];
   __shared__ double s_scratch[HPS_BLOCK];
 
+  pdl_launch_dependents();
+  pdl_wait();  // the op constants (k_prepare_ops) and everything below come from preceding kernels
   {  // stage the segment's op records (block-uniform) in shared memory
     const int nw = nops * (int)(sizeof(Op) / sizeof(double));
     const double* src = reinterpret_cast<const double*>(ops);
@@ -197,7 +199,7 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
     if (sc) {
       s_k.dr = sc->dr; s_k.dz = sc->dz; s_k.beta = sc->beta;
       s_k.ratio_r = sc->ratio_r; s_k.ratio_z = sc->ratio_z; s_k.ratio_q = sc->ratio_q; s_k.ratio_g = sc->ratio_g;
-      s_k.adj_bunch = sc->adj_bunch; s_k.num_on_mesh = sc->num_on_mesh;
+      s_k.adj_bunch = sc->adj_bunch; s_k.num_on_mesh = sc->num_on_mesh_all;
     }
     s_k.nr = kp.nr; s_k.nz = kp.nz;
     // a segment holds at most one kick (its first op); its block-uniform factors are derived here
@@ -508,6 +510,8 @@ k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int 
           u32* ticket, const __grid_constant__ XrView xr) {
   __shared__ double s_total[MOM_NS];
   __shared__ double s_scratch[HPS_BLOCK];
+  pdl_launch_dependents();
+  pdl_wait();
   // with_lloss: the longitudinal-loss pass (K2) runs in front of the moments inside this launch when K1
   // asked for it -- the common "nothing to mark" case then costs nothing instead of an empty kernel.  The
   // flag only changes in K1's finaliser, so every block sees the same value for the whole launch.
@@ -652,6 +656,8 @@ __device__ __forceinline__ u32 deposit_one(const DepCtx& d, u32 l, u32 ll, doubl
 __global__ void __launch_bounds__(512, 2)
 k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, u32* ticket, const __grid_constant__ XrView xr) {
   extern __shared__ u32 s_words[];  // [nb] low words, [nb] high words
+  pdl_launch_dependents();
+  pdl_wait();
   if (!sc->remesh) return;
   unsigned long long* bins = reinterpret_cast<unsigned long long*>(bins_raw);
   const u32 nb = kp.nr * kp.nz;
@@ -704,11 +710,9 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
     if (cnt) atomicAdd(&sc->num_on_mesh, cnt);
     atomicMax(&sc->abs_phi_max_bits, (unsigned long long)__double_as_longlong(pmax));
   }
-  if (xr.nranks <= 1) return;
-  // Sharded beam: the rank's last block hands the rank-local mesh (+ on-mesh count, max |phi|) to every
-  // peer; k_field folds the R meshes (integer sums: the order does not matter).  XR_P2P: stores into the
-  // peers' boxes over NVLink, sequence number = this context's mesh hand-off counter xr.seq[1].
-  // XR_NCCL: the two scalars are appended and the host all-gathers.
+  if (xr.mode != XR_NCCL) return;
+  // XR_NCCL only: the rank's last block appends the on-mesh count and max |phi| to the mesh, which the host
+  // then all-gathers.  (XR_P2P: k_field itself pushes the mesh to the peers, spread over all its blocks.)
   __shared__ u32 s_last;
   __threadfence();
   __syncthreads();
@@ -716,27 +720,11 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const unsigned long long cnt_u = (unsigned long long)__ldcg(&sc->num_on_mesh);
-  const unsigned long long pmax_u = __ldcg(&sc->abs_phi_max_bits);
-  if (xr.mode == XR_P2P) {
-    __shared__ unsigned long long s_seq;
-    if (threadIdx.x == 0) { s_seq = xr.seq[1] + 1ull; xr.seq[1] = s_seq; }  // k_field reads it back
-    __syncthreads();
-    const u32 seq32 = (u32)s_seq;
-    const int par = (int)(s_seq & 1ull);
-    for (u32 k = threadIdx.x; k < nb + 2; k += blockDim.x) {
-      const unsigned long long v = k < nb ? __ldcg(&bins[k]) : (k == nb ? cnt_u : pmax_u);
-      for (int p = 0; p < xr.nranks; ++p) {
-        unsigned long long* w = &xr.peer[p]->bins[par][xr.rank][2 * k];
-        ll_send(w, (u32)v, seq32);
-        ll_send(w + 1, (u32)(v >> 32), seq32);
-      }
-    }
-  } else if (threadIdx.x == 0) {
-    bins[nb] = cnt_u;
-    bins[nb + 1] = pmax_u;
+  if (threadIdx.x == 0) {
+    bins[nb] = (unsigned long long)__ldcg(&sc->num_on_mesh);
+    bins[nb + 1] = __ldcg(&sc->abs_phi_max_bits);
+    *ticket = 0u;
   }
-  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // ================================================================================================
@@ -759,8 +747,10 @@ __device__ __forceinline__ void ellip_ke(double g, double& ee, double& ek) {
 // (nr+1) x ceil(nr/RS) blocks of RS*T threads fill the GPU.
 __global__ void __launch_bounds__(1024)
 k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, double2* part, u32* tickets,
-        KickParams kp, int T, const __grid_constant__ XrView xr) {
+        KickParams kp, int T, u32 mesh_seq, const __grid_constant__ XrView xr) {
   extern __shared__ double s_mem[];
+  pdl_launch_dependents();
+  pdl_wait();
   if (!sc->remesh) return;
   const u32 nr = kp.nr, nz = kp.nz;
   const u32 RS = blockDim.x / T;
@@ -774,8 +764,25 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
   double2* s_p = s_g + RS * nz;                                  // [RS][nz] ring partials at nodes zp < nz
   double2* s_red = s_p + RS * nz;                                // [blockDim.x]
   const double inv_scale = 1.0 / bin_scale(kp.n_global);          // fixed-point mesh, see k_deposit
-  // The Green's function slice does not depend on the charge mesh: it is computed first, so on a sharded
-  // beam the peers' meshes travel over NVLink meanwhile.
+  // Sharded beam, XR_P2P: every block first stores its share of the rank-local mesh (+ on-mesh count and
+  // max |phi|) into all peers' boxes as LL words (sequence number = the host's launch counter of this
+  // kernel, identical on all ranks).  The Green's function slice does not depend on the charge mesh: it
+  // is computed next, so the peers' meshes travel over NVLink meanwhile; then the R meshes are polled
+  // and folded (integer sums: exact, order-independent).
+  if (xr.mode == XR_P2P) {
+    const u32 nb = nr * nz;
+    const unsigned long long* lb = reinterpret_cast<const unsigned long long*>(bins);
+    const u32 nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const int par = (int)(mesh_seq & 1u);
+    for (u32 k = blk * blockDim.x + threadIdx.x; k < nb + 2; k += nblk * blockDim.x) {
+      const unsigned long long v = k < nb ? lb[k] : (k == nb ? (unsigned long long)sc->num_on_mesh : sc->abs_phi_max_bits);
+      for (int p = 0; p < xr.nranks; ++p) {
+        unsigned long long* w = &xr.peer[p]->bins[par][xr.rank][2 * k];
+        ll_send(w, (u32)v, mesh_seq);
+        ll_send(w + 1, (u32)(v >> 32), mesh_seq);
+      }
+    }
+  }
   if (live) {  // Green's function entry (ring rs0+kk -> radius rp, axial offset (t + 1/2) cells)
     const double beta = sc->beta;
     const double gm = rsqrt(1.0 - beta * beta);
@@ -817,8 +824,10 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
     s_g[kk * nz + t] = make_double2(c1 * er1, c1 * ez1);
   }
   if (xr.nranks <= 1) {
-    if (irp == 0 && ch == 0 && threadIdx.x == 0 && sc->adj_bunch != 0)
-      st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
+    if (irp == 0 && ch == 0 && threadIdx.x == 0) {
+      sc->num_on_mesh_all = sc->num_on_mesh;
+      if (sc->adj_bunch != 0) st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
+    }
     const long long* ibins = reinterpret_cast<const long long*>(bins);  // fixed point, see k_deposit
     if (live) s_b[kk * nz + t] = (double)ibins[t * nr + rs0 + kk] * inv_scale;
   } else {
@@ -826,11 +835,10 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
     const u32 nb = nr * nz;
     const unsigned long long* slot[HPS_XR_MAXR];
     const bool ll = xr.mode == XR_P2P;  // LL words in this rank's own box, polled in place
-    const unsigned long long seq = ll ? xr.seq[1] : 0ull;  // advanced by this rank's k_deposit just before
-    const u32 seq32 = (u32)seq;
+    const u32 seq32 = mesh_seq;
     if (ll) {
       const XrBox* own = xr.peer[xr.rank];
-      for (int r = 0; r < xr.nranks; ++r) slot[r] = own->bins[(int)(seq & 1ull)][r];
+      for (int r = 0; r < xr.nranks; ++r) slot[r] = own->bins[(int)(mesh_seq & 1u)][r];
     } else {
       for (int r = 0; r < xr.nranks; ++r) slot[r] = reinterpret_cast<const unsigned long long*>(xr.bins_gather) + (size_t)r * (nb + 2);
     }
@@ -849,7 +857,7 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
         cnt += (u32)value(r, nb);
         pm = fmax(pm, __longlong_as_double((long long)value(r, nb + 1)));
       }
-      sc->num_on_mesh = cnt;
+      sc->num_on_mesh_all = cnt;
       if (sc->adj_bunch != 0) st->v[HPS_STAT_ABS_PHI_MAX] = pm;
     }
   }
@@ -1091,6 +1099,19 @@ __global__ void k_rel_phi_out(BeamView b, const DevStats* st, double* out) {
 // ================================================================================================
 static int g_field_smem_set = 0, g_deposit_smem_set = 0;
 
+// Launch with programmatic stream serialization (see pdl_wait in hps_kernels.cuh) when c.pdl is set.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(const LaunchCfg& c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = c.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 void launch_prepare_ops(const LaunchCfg& c, const Op* ops, OpC* opcs, int nops, double mass, double charge) {
   if (nops > 0) k_prepare_ops<<<(nops + 63) / 64, 64, 0, c.stream>>>(ops, opcs, nops, mass, charge);
 }
@@ -1108,7 +1129,7 @@ void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, c
   switch (c.seg_variant) {
     case 1: k_segment<1, 3, false, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(SEG_CALL); break;
     case 2: k_segment<1, 4, false, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(SEG_CALL); break;
-    default: k_segment<2, 2, false, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(SEG_CALL); break;
+    default: launch_chain(c, k_segment<2, 2, false, false>, dim3(grid2), dim3(HPS_BLOCK), 0, SEG_CALL); break;
     case 4: {  // TMA-staged loads: measured slower (35.0 vs 32.0 ms per C2 pass) -- the sweep is not load-bound
       static int attr_set = 0;
       if (!attr_set) {
@@ -1125,7 +1146,7 @@ void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDe
 }
 void launch_moments(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins, const KickParams& kp,
                     int do_policy, int with_lloss) {
-  k_moments<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, bins, kp, do_policy, with_lloss, c.partials, c.ticket, c.xr);
+  launch_chain(c, k_moments, dim3(c.grid_pairs), dim3(HPS_BLOCK), 0, b, st, sc, bins, kp, do_policy, with_lloss, c.partials, c.ticket, c.xr);
 }
 int moments_occupancy() {
   int nb = 0;
@@ -1156,11 +1177,11 @@ cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, 
     if (e != cudaSuccess) return e;
     g_deposit_smem_set = 1;
   }
-  k_deposit<<<c.grid_deposit, 512, smem, c.stream>>>(b, st, sc, bins, kp, c.ticket + 1, c.xr);
+  launch_chain(c, k_deposit, dim3(c.grid_deposit), dim3(512), smem, b, st, sc, bins, kp, c.ticket + 1, c.xr);
   return cudaSuccess;
 }
 cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const double* bins, double2* field, double2* part,
-                         u32* tickets, const KickParams& kp) {
+                         u32* tickets, const KickParams& kp, u32 mesh_seq) {
   const int T = field_threads(kp);
   const size_t smem = field_smem(kp, T);
   if (smem > 48 * 1024 && !g_field_smem_set) {
@@ -1168,7 +1189,7 @@ cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const doub
     if (e != cudaSuccess) return e;
     g_field_smem_set = 1;
   }
-  k_field<<<dim3(kp.nr + 1, field_chunks(kp)), T * field_rs(kp), smem, c.stream>>>(st, sc, bins, field, part, tickets, kp, T, c.xr);
+  launch_chain(c, k_field, dim3(kp.nr + 1, field_chunks(kp)), dim3(T * field_rs(kp)), smem, st, sc, bins, field, part, tickets, kp, T, mesh_seq, c.xr);
   return cudaSuccess;
 }
 void launch_stat(const LaunchCfg& c, const BeamView& b, DevStats* st, const StatReq& rq) {

@@ -38,6 +38,13 @@ __device__ __forceinline__ void warp_reduce(double (&v)[NS], unsigned max_mask) 
   }
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// The kick chain is a string of short kernels, each ending in a one-block reduction tail.  Launched with
+// the programmatic-stream-serialization attribute, the next kernel's blocks become resident while that
+// tail runs and wait here; pdl_wait() returns once the preceding grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- cross-rank exchange over peer memory (XrBox, hps_internal.h) ------------------------------
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

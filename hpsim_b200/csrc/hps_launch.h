@@ -17,6 +17,7 @@ struct LaunchCfg {
   unsigned grid_deposit;
   double* partials;       // [max grid][HPS_NSLOT]
   u32* ticket;            // [0] reductions, [1] deposit hand-off (sharded beams)
+  int pdl;                // launch the kick-chain kernels with programmatic stream serialization
   XrView xr;              // cross-rank exchange of a particle-sharded beam (mode XR_NONE otherwise)
 };
 
@@ -53,7 +54,7 @@ void launch_moments(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double
 int moments_occupancy();
 cudaError_t launch_deposit(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&);
 cudaError_t launch_field(const LaunchCfg&, DevStats*, ScDev*, const double* bins, double2* field, double2* part,
-                         u32* tickets, const KickParams&);
+                         u32* tickets, const KickParams&, u32 mesh_seq);
 unsigned field_chunks(const KickParams&);
 void launch_stat(const LaunchCfg&, const BeamView&, DevStats*, const StatReq&);
 void launch_set_phi_ref(const LaunchCfg&, const BeamView&, DevStats*, int use_good, double phi0);
