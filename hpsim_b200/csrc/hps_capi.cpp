@@ -130,7 +130,7 @@ LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
   l.stream = c->stream;
   const unsigned pairs = (b->n + 1) / 2;
   l.seg_variant = c->seg_variant;
-  const unsigned seg_items = c->seg_variant == 0 ? pairs : b->n;
+  const unsigned seg_items = segment_pairs(c->seg_variant) ? pairs : b->n;
   l.grid_seg = std::max(1u, std::min((seg_items + HPS_BLOCK - 1) / HPS_BLOCK, c->seg_grid_cap));
   l.grid_seg1 = std::max(1u, std::min((b->n + HPS_BLOCK - 1) / HPS_BLOCK, c->seg_grid_cap_full));
   l.grid_pairs = std::max(1u, std::min((pairs + HPS_BLOCK - 1) / HPS_BLOCK, c->max_grid));
@@ -342,7 +342,7 @@ hps_ctx* hps_ctx_create(int device) {
   int occ = ok ? segment_occupancy(c->seg_variant) : 0;
   if (occ < 1) occ = 1;
   c->seg_grid_cap = (unsigned)c->num_sms * (unsigned)occ;
-  c->seg_grid_cap_full = (unsigned)c->num_sms * (unsigned)std::max(1, ok ? segment_occupancy(-1) : 1);
+  c->seg_grid_cap_full = (unsigned)c->num_sms * (unsigned)std::max(1, ok ? segment_occupancy(segment_full_variant(c->seg_variant)) : 1);
   // the pair sweeps (K2/K3) hold a grid barrier: every block must be resident
   c->max_grid = (unsigned)c->num_sms * (unsigned)std::max(1, std::min(4, ok ? moments_occupancy() : 1));
   ok = ok && cudaMalloc(&c->partials, (size_t)c->num_sms * 8 * HPS_NSLOT * sizeof(double)) == cudaSuccess &&

@@ -49,7 +49,7 @@ struct Op {
 
 // Particle-independent sub-expressions of an op, evaluated ONCE on the device (k_prepare_ops) with
 // the same expression order the reference evaluates per particle, so the hoisting is bit-exact.
-#define HPS_OPC_N 32
+#define HPS_OPC_N 48
 struct OpC {
   double c[HPS_OPC_N];
 };

@@ -46,11 +46,12 @@ __device__ void finalize_segment(int fin, const double* t, DevStats* st, u32 n_g
 // one op applied to the N register-resident particles of a thread.  The type dispatch and the shared-memory
 // reads of the op's parameters happen once per op, not once per particle, and the per-particle bodies sit
 // back to back so that their independent fp64 chains can overlap.
-template <bool FULL, int N>
+// MATH: 0 = the reference's expression order, 1 = the fast maps (hps_kernels.cuh)
+template <bool FULL, int N, int MATH>
 __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const u32 (&gidx)[N], const bool (&valid)[N],
                                          const Op& op, const OpC& opc, const KickCtx& kc, const double* cxy,
                                          const double2* __restrict__ field, const BeamView& b, int compat,
-                                         double (&phi_fc)[N], bool (&live_fc)[N]) {
+                                         double (&phi_fc)[N], bool (&live_fc)[N], double inv_mass) {
   const double* q = op.p;
   const double* c = opc.c;
   const double mass = b.mass, charge = b.charge;
@@ -59,19 +60,19 @@ __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const 
   switch (op.type) {
     case OP_DRIFT:
 #pragma unroll
-      EACH_ALIVE op_drift(pt[j], q, c, op.elem, mass);
+      EACH_ALIVE { if (MATH) op_drift_f(pt[j], q, c, op.elem, inv_mass); else op_drift(pt[j], q, c, op.elem, mass); }
       break;
     case OP_QUAD_HALF:
 #pragma unroll
-      EACH_ALIVE op_quad_half(pt[j], q, c, op.elem, mass);
+      EACH_ALIVE { if (MATH) op_quad_half_f(pt[j], q, c, op.elem, inv_mass); else op_quad_half(pt[j], q, c, op.elem, mass); }
       break;
     case OP_GAP_FIRST:
 #pragma unroll
-      EACH_ALIVE op_gap_first(pt[j], q, c, op.flag != 0, mass);
+      EACH_ALIVE { if (MATH) op_gap_first_f(pt[j], q, c, op.flag != 0, inv_mass); else op_gap_first(pt[j], q, c, op.flag != 0, mass); }
       break;
     case OP_GAP_SECOND:
 #pragma unroll
-      EACH_ALIVE op_gap_second(pt[j], q, c, op.flag != 0, mass);
+      EACH_ALIVE { if (MATH) op_gap_second_f(pt[j], q, c, op.flag != 0, inv_mass); else op_gap_second(pt[j], q, c, op.flag != 0, mass); }
       break;
     // the rare, code-heavy maps (7 dipoles and 2 bunchers in the whole linac) live in the FULL variant only,
     // which keeps the hot variant's SASS inside the instruction cache
@@ -132,7 +133,10 @@ __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const 
       // H2: the reference launches the kick <<<grid, blck/4>>> with `while(indx > 0 && ...)`, so
       // global thread 0 exits at once and particles k*NextPow2(N)/4 never see a kick.
 #pragma unroll
-      EACH if (!(gidx[j] == 0 || (compat && (gidx[j] % b.np2_quarter) == 0))) op_sc_kick(pt[j], ll[j], kc, field, mass);
+      // (np2_quarter is a power of two)
+      EACH if (!(gidx[j] == 0 || (compat && (gidx[j] & (b.np2_quarter - 1u)) == 0u))) {
+        if (MATH) op_sc_kick_f(pt[j], ll[j], kc, field, inv_mass); else op_sc_kick(pt[j], ll[j], kc, field, mass);
+      }
       break;
     case OP_FREQ_CHANGE:  // beam_kernel.cu:1531-1538: every particle, lost or not
 #pragma unroll
@@ -161,10 +165,9 @@ __device__ __forceinline__ void seg_accumulate(double (&acc)[SEG_NS], const Pt& 
 // PPT = particles per thread.  PPT == 2 moves two adjacent particles with one 128-bit access per
 // array; PPT == 1 halves the register footprint and doubles the resident warps (the maps are chains of
 // dependent fp64 operations, so the sweep is latency-bound before it is bandwidth-bound).
-// STAGED (PPT == 2 only): tiles of HPS_BLOCK pairs are brought into shared memory by TMA bulk copies, double
-// buffered, one tile ahead of the computation.
-#define HPS_SEG_STAGE_BYTES (HPS_BLOCK * (6 * 16 + 2 * 8))   /* one tile: 6 double2 + 2 uint2 per pair */
-template <int PPT, int MINB, bool FULL, bool STAGED>
+// (A TMA-staged, double-buffered variant of the PPT == 2 loop was measured slower -- 35.0 vs 32.0 ms of sweep time
+// per C2 pass: the sweep is not load-bound and the per-tile block barrier re-aligns the warps -- and was removed.)
+template <int PPT, int MINB, bool FULL, int MATH>
 __global__ void __launch_bounds__(HPS_BLOCK, MINB)
 k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
           DevStats* st, const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials,
@@ -212,78 +215,8 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
 #pragma unroll
   for (int s = 0; s < SEG_NS; ++s) acc[s] = 0.0;
   acc[2] = -DBL_MAX;
+  const double inv_mass = 1.0 / b.mass;
 
-  if (PPT == 2 && STAGED) {
-    extern __shared__ __align__(128) unsigned char s_stage[];  // [2][HPS_SEG_STAGE_BYTES]
-    __shared__ __align__(8) unsigned long long s_bar[2];
-    const u32 npairs = (b.n + 1) >> 1;
-    const u32 ntiles = (npairs + HPS_BLOCK - 1) / HPS_BLOCK;
-    if (threadIdx.x == 0) {
-      mbar_init(&s_bar[0], 1);
-      mbar_init(&s_bar[1], 1);
-      mbar_fence_init();
-    }
-    __syncthreads();
-    auto issue = [&](u32 tile, int stage) {  // one thread: 8 bulk copies, one per array
-      const u32 p0 = tile * HPS_BLOCK;
-      const u32 np = min((u32)HPS_BLOCK, npairs - p0);
-      const u32 bd = np * 16u, bf = (np * 8u + 15u) & ~15u;
-      unsigned char* dst = s_stage + (size_t)stage * HPS_SEG_STAGE_BYTES;
-      mbar_expect_tx(&s_bar[stage], 6u * bd + 2u * bf);
-      const double* src[6] = {b.x, b.xp, b.y, b.yp, b.phi, b.w};
-#pragma unroll
-      for (int a = 0; a < 6; ++a) tma_load_1d(dst + a * (HPS_BLOCK * 16), src[a] + 2 * (size_t)p0, bd, &s_bar[stage]);
-      tma_load_1d(dst + 6 * (HPS_BLOCK * 16), b.loss + 2 * (size_t)p0, bf, &s_bar[stage]);
-      tma_load_1d(dst + 6 * (HPS_BLOCK * 16) + HPS_BLOCK * 8, b.lloss + 2 * (size_t)p0, bf, &s_bar[stage]);
-    };
-    if (threadIdx.x == 0 && blockIdx.x < ntiles) issue(blockIdx.x, 0);
-    u32 it = 0;
-    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int stage = (int)(it & 1u);
-      // the other stage was consumed in the previous iteration (its __syncthreads below has passed)
-      if (threadIdx.x == 0 && tile + gridDim.x < ntiles) {
-        fence_proxy_async();
-        issue(tile + gridDim.x, stage ^ 1);
-      }
-      mbar_wait(&s_bar[stage], (it >> 1) & 1u);
-      const unsigned char* src = s_stage + (size_t)stage * HPS_SEG_STAGE_BYTES;
-      const u32 i2 = tile * HPS_BLOCK + threadIdx.x;
-      const bool act = i2 < npairs;
-      const double2* sd = reinterpret_cast<const double2*>(src);
-      const uint2* sf = reinterpret_cast<const uint2*>(src + 6 * (HPS_BLOCK * 16));
-      double2 X, XP, Y, YP, PH, W;
-      uint2 L, LL;
-      if (act) {
-        X = sd[threadIdx.x]; XP = sd[HPS_BLOCK + threadIdx.x]; Y = sd[2 * HPS_BLOCK + threadIdx.x];
-        YP = sd[3 * HPS_BLOCK + threadIdx.x]; PH = sd[4 * HPS_BLOCK + threadIdx.x]; W = sd[5 * HPS_BLOCK + threadIdx.x];
-        L = sf[threadIdx.x]; LL = sf[HPS_BLOCK + threadIdx.x];
-      }
-      __syncthreads();  // every thread holds its pair in registers: this stage may be refilled
-      if (!act) continue;
-      Pt p[2] = {{X.x, XP.x, Y.x, YP.x, PH.x, W.x, L.x}, {X.y, XP.y, Y.y, YP.y, PH.y, W.y, L.y}};
-      const u32 ll[2] = {LL.x, LL.y};
-      const bool valid[2] = {true, 2 * i2 + 1 < b.n};
-      const u32 g0 = b.offset + 2 * i2 * b.gstride;
-      const u32 g[2] = {g0, g0 + b.gstride};
-      double fc[2] = {0.0, 0.0};
-      bool lf[2] = {false, false};
-      for (int k = 0; k < nops; ++k) apply_op<FULL, 2>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
-      if (nops > 0) {
-        if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p[0].x, p[1].x);
-        if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p[0].xp, p[1].xp);
-        if (dirty & 4) reinterpret_cast<double2*>(b.y)[i2] = make_double2(p[0].y, p[1].y);
-        if (dirty & 8) reinterpret_cast<double2*>(b.yp)[i2] = make_double2(p[0].yp, p[1].yp);
-        if (dirty & 16) reinterpret_cast<double2*>(b.phi)[i2] = make_double2(p[0].phi, p[1].phi);
-        if (dirty & 32) reinterpret_cast<double2*>(b.w)[i2] = make_double2(p[0].w, p[1].w);
-        if ((dirty & 64) && (p[0].loss != L.x || p[1].loss != L.y))
-          reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p[0].loss, p[1].loss);
-      }
-      if (fin_mode != FIN_NONE) {
-        seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
-        if (valid[1]) seg_accumulate(acc, p[1], ll[1], fc[1], lf[1]);
-      }
-    }
-  } else
   if (PPT == 2) {
     const u32 npairs = (b.n + 1) >> 1;
     for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
@@ -302,7 +235,7 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       const u32 g[2] = {g0, g0 + b.gstride};
       double fc[2] = {0.0, 0.0};
       bool lf[2] = {false, false};
-      for (int k = 0; k < nops; ++k) apply_op<FULL, 2>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
+      for (int k = 0; k < nops; ++k) apply_op<FULL, 2, MATH>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf, inv_mass);
       if (nops > 0) {
         if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p[0].x, p[1].x);
         if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p[0].xp, p[1].xp);
@@ -327,7 +260,7 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       const u32 g[1] = {b.offset + i * b.gstride};
       double fc[1] = {0.0};
       bool lf[1] = {false};
-      for (int k = 0; k < nops; ++k) apply_op<FULL, 1>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf);
+      for (int k = 0; k < nops; ++k) apply_op<FULL, 1, MATH>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf, inv_mass);
       if (nops > 0) {
         if (dirty & 1) b.x[i] = p[0].x;
         if (dirty & 2) b.xp[i] = p[0].xp;
@@ -346,11 +279,22 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
   }
 }
 #define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*, const __grid_constant__ XrView
-template __global__ void k_segment<2, 2, false, true>(SEG_ARGS);
-template __global__ void k_segment<2, 2, false, false>(SEG_ARGS);
-template __global__ void k_segment<1, 3, false, false>(SEG_ARGS);
-template __global__ void k_segment<1, 4, false, false>(SEG_ARGS);
-template __global__ void k_segment<1, 3, true, false>(SEG_ARGS);
+typedef void (*SegKernel)(SEG_ARGS);
+// variant -> kernel.  0: 2 particles/thread, fast maps (default); 1 / 2: 1 particle/thread at 3 / 4 blocks per SM;
+// 10, 11: variants 0, 1 with the reference's expression order (MATH = 0); -1 / -2: the full op set (dipole, buncher)
+static SegKernel seg_kernel(int variant) {
+  switch (variant) {
+    case 1: return k_segment<1, 3, false, 1>;
+    case 2: return k_segment<1, 4, false, 1>;
+    case 10: return k_segment<2, 2, false, 0>;
+    case 11: return k_segment<1, 3, false, 0>;
+    case -1: return k_segment<1, 3, true, 1>;
+    case -2: return k_segment<1, 3, true, 0>;
+    default: return k_segment<2, 2, false, 1>;
+  }
+}
+static int seg_full_variant(int variant) { return variant >= 10 ? -2 : -1; }
+static bool seg_pairs(int variant) { return !(variant == 1 || variant == 2 || variant == 11 || variant < 0); }
 
 // one thread per op record of the uploaded program (once per simulate() call)
 __global__ void k_prepare_ops(const Op* __restrict__ ops, OpC* opcs, int nops, double mass, double charge) {
@@ -1122,23 +1066,8 @@ void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, c
   for (int k = 0; k < nops; ++k) full |= host_ops[k].type == OP_DIPOLE_FIRST || host_ops[k].type == OP_DIPOLE_SECOND || host_ops[k].type == OP_BUNCHER;
   const unsigned grid1 = c.grid_seg1, grid2 = c.grid_seg;
 #define SEG_CALL b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr
-  if (full) {
-    k_segment<1, 3, true, false><<<grid1, HPS_BLOCK, 0, c.stream>>>(SEG_CALL);
-    return;
-  }
-  switch (c.seg_variant) {
-    case 1: k_segment<1, 3, false, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(SEG_CALL); break;
-    case 2: k_segment<1, 4, false, false><<<grid2, HPS_BLOCK, 0, c.stream>>>(SEG_CALL); break;
-    default: launch_chain(c, k_segment<2, 2, false, false>, dim3(grid2), dim3(HPS_BLOCK), 0, SEG_CALL); break;
-    case 4: {  // TMA-staged loads: measured slower (35.0 vs 32.0 ms per C2 pass) -- the sweep is not load-bound
-      static int attr_set = 0;
-      if (!attr_set) {
-        cudaFuncSetAttribute(k_segment<2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * HPS_SEG_STAGE_BYTES);
-        attr_set = 1;
-      }
-      k_segment<2, 2, false, true><<<grid2, HPS_BLOCK, 2 * HPS_SEG_STAGE_BYTES, c.stream>>>(SEG_CALL);
-    }
-  }
+  if (full) launch_chain(c, seg_kernel(seg_full_variant(c.seg_variant)), dim3(grid1), dim3(HPS_BLOCK), 0, SEG_CALL);
+  else launch_chain(c, seg_kernel(c.seg_variant), dim3(grid2), dim3(HPS_BLOCK), 0, SEG_CALL);
 #undef SEG_CALL
 }
 void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
@@ -1229,15 +1158,10 @@ void launch_rel_phi_out(const LaunchCfg& c, const BeamView& b, const DevStats* s
 }
 int segment_occupancy(int variant) {
   int nb = 0;
-  if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3, false, false>, HPS_BLOCK, 0);
-  else if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 4, false, false>, HPS_BLOCK, 0);
-  else if (variant == -1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<1, 3, true, false>, HPS_BLOCK, 0);
-  else if (variant != 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<2, 2, false, false>, HPS_BLOCK, 0);
-  else {
-    cudaFuncSetAttribute(k_segment<2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * HPS_SEG_STAGE_BYTES);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_segment<2, 2, false, true>, HPS_BLOCK, 2 * HPS_SEG_STAGE_BYTES);
-  }
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg_kernel(variant), HPS_BLOCK, 0);
   return nb;
 }
+int segment_full_variant(int variant) { return seg_full_variant(variant); }
+bool segment_pairs(int variant) { return seg_pairs(variant); }
 
 }  // namespace hps

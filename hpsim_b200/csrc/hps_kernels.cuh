@@ -18,6 +18,17 @@ namespace hps {
 #define K_PI 3.14159265358979323846
 #define K_TWOPI (3.14159265358979323846 * 2.0)
 
+// the element maps are plain fp64 arithmetic: they also compile for the host, where tests/host_maps.cu runs
+// the fast maps against the reference-order maps without a GPU
+#define HPS_HD __host__ __device__ __forceinline__
+HPS_HD double2 ld_field(const double2* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 struct Pt {
   double x, xp, y, yp, phi, w;
   u32 loss;
@@ -230,21 +241,27 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ------------------------------------------------------------------------------------------------
 // element maps (one particle)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double beta_of(double w, double mass) {
+HPS_HD double beta_of(double w, double mass) {
   double g1 = w / mass;
   return sqrt(g1 * (g1 + 2.0)) / (g1 + 1.0);
 }
 
 // ---- hoisted constants -------------------------------------------------------------------------
 // slots of OpC::c per op type
-enum { D_APER2 = 0, D_TWOPI_HL };
-enum { Q_APER2 = 0, Q_QG, Q_ABSQG, Q_LEN4, Q_TWOPI_LEN_HALF };
+enum { D_APER2 = 0, D_TWOPI_HL, D_PH_OVER_WL };
+enum { Q_APER2 = 0, Q_QG, Q_ABSQG, Q_LEN4, Q_TWOPI_LEN_HALF, Q_KC, Q_PH_OVER_WL };
 enum { R_COS = 0, R_SIN };
 enum { GC_CELL_LEN = 0, GC_DD, GC_WAVE_LEN, GC_BETA_IN, GC_DPS, GC_PI_CLBL_DPS, GC_D_CELL_LEN, GC_PI_DCL, GC_TWOPI_HALF_QLEN,
        GC_BETAG_CCL, GC_TWOPI_DD,
        // second half only
        GC_INV_MASS, GC_BETAG, GC_GMG, GC_INV_GMG2, GC_AQ, GC_BETA_OUT, GC_EFL, GC_CONCOMM, GC_CONCOMM1, GC_CON1, GC_CON2NEX,
-       GC_INV_GMGCL, GC_INV_FKIS, GC_FKR, GC_SINPS, GC_COSPS, GC_X5, GC_TTF_DEN, GC_PH_CONST, GC_TWOPI_DG, GC_AQ_EFL };
+       GC_INV_GMGCL, GC_INV_FKIS, GC_FKR, GC_SINPS, GC_COSPS, GC_X5, GC_TTF_DEN, GC_PH_CONST, GC_TWOPI_DG, GC_AQ_EFL,
+       // reciprocal / pre-divided forms used by the fast maps (slots 32..)
+       GF_DD_OVER_WL = 32,   // 2 pi dd / wavelength in force (the amp == 0 drift of either half)
+       GF_DCLQ_OVER_WL,      // (pi d_cell_len [0 when |d_cell_len| <= 1e-15] - 2 pi qlen/2) / wave_len
+       GF_IBETA_IN,          // 1 / beta_in
+       GF_IBETA_OUT,         // 1 / beta_out
+       GF_INV_TTF_DEN, GF_INV_GMG, GF_DG_OVER_WL, GF_INV_FKR, GF_BETAG_OVER_BIN };
 
 // indices into Op::p for the RF gap (rfgap_parameter.h:4-32)
 enum { G_LEN = 0, G_FREQ, G_CLBL, G_AMP, G_PHREF, G_PHSHIFT, G_EOUT, G_BETAC, G_DG, G_T, G_TP, G_SP,
@@ -253,13 +270,14 @@ enum { G_LEN = 0, G_FREQ, G_CLBL, G_AMP, G_PHREF, G_PHSHIFT, G_EOUT, G_BETAC, G_
 
 // Evaluates the particle-independent sub-expressions of one op.  Every value is produced by the very
 // expression (same operand order) the reference evaluates inside its per-particle loop.
-__device__ inline void prepare_op(const Op& op, OpC& o, double mass, double charge) {
+__host__ __device__ inline void prepare_op(const Op& op, OpC& o, double mass, double charge) {
   const double* q = op.p;
   double* c = o.c;
   switch (op.type) {
     case OP_DRIFT:
       c[D_APER2] = q[1] * q[1];
       c[D_TWOPI_HL] = K_TWOPI * q[0];
+      c[D_PH_OVER_WL] = c[D_TWOPI_HL] / q[2];
       break;
     case OP_QUAD_HALF: {
       double aper2 = q[1]; aper2 *= aper2;
@@ -269,6 +287,8 @@ __device__ inline void prepare_op(const Op& op, OpC& o, double mass, double char
       c[Q_ABSQG] = qg > 0.0 ? qg : -qg;
       c[Q_LEN4] = q[0] * 0.25;
       c[Q_TWOPI_LEN_HALF] = K_TWOPI * q[0] * 0.5;
+      c[Q_KC] = c[Q_ABSQG] * K_CLIGHT / mass;
+      c[Q_PH_OVER_WL] = c[Q_TWOPI_LEN_HALF] / q[3];
       break;
     }
     case OP_ROTATION:
@@ -290,6 +310,8 @@ __device__ inline void prepare_op(const Op& op, OpC& o, double mass, double char
       c[GC_D_CELL_LEN] = d_cell_len;
       c[GC_PI_DCL] = K_PI * d_cell_len;
       c[GC_TWOPI_HALF_QLEN] = K_TWOPI * 0.5 * (second ? qlen2 : qlen1);
+      c[GF_DD_OVER_WL] = c[GC_TWOPI_DD] / (second ? q[G_WAVELEN] : wave_len);
+      c[GF_DCLQ_OVER_WL] = (((d_cell_len > 1e-15 || d_cell_len < -1e-15) ? c[GC_PI_DCL] : 0.0) - c[GC_TWOPI_HALF_QLEN]) / wave_len;
       if (!second) {
         double gam = q[G_DESIGN_W] / mass;
         c[GC_BETA_IN] = sqrt((gam + 2.0) * gam) / (gam + 1.0);
@@ -297,6 +319,7 @@ __device__ inline void prepare_op(const Op& op, OpC& o, double mass, double char
         c[GC_DPS] = dps;
         c[GC_PI_CLBL_DPS] = K_PI * q[G_CLBL] + dps;
         c[GC_BETAG_CCL] = cell_len / (q[G_CLBL] * wave_len);  // "betag" of the CCL first half
+        c[GF_IBETA_IN] = 1.0 / c[GC_BETA_IN];
       } else {
         const double inv_mass = 1.0 / mass;
         c[GC_INV_MASS] = inv_mass;
@@ -349,6 +372,13 @@ __device__ inline void prepare_op(const Op& op, OpC& o, double mass, double char
         c[GC_DPS] = dps;
         c[GC_PI_CLBL_DPS] = K_PI * q[G_CLBL] + dps;
         c[GC_PH_CONST] = (u32)q[G_CELLNUM] * K_PI;
+        c[GF_IBETA_IN] = 1.0 / beta_in;
+        c[GF_IBETA_OUT] = 1.0 / c[GC_BETA_OUT];
+        c[GF_INV_TTF_DEN] = 1.0 / c[GC_TTF_DEN];
+        c[GF_INV_GMG] = 1.0 / gmg;
+        c[GF_DG_OVER_WL] = c[GC_TWOPI_DG] / wave_len;
+        c[GF_INV_FKR] = 1.0 / c[GC_FKR];
+        c[GF_BETAG_OVER_BIN] = betag_ccl / beta_in;
       }
       break;
     }
@@ -357,7 +387,7 @@ __device__ inline void prepare_op(const Op& op, OpC& o, double mass, double char
 }
 
 // simulation_kernel.cu:87-118 -- a lost particle keeps its pre-drift x,y (H11)
-__device__ __forceinline__ void op_drift(Pt& p, const double* q, const double* c, u32 elem, double mass) {
+HPS_HD void op_drift(Pt& p, const double* q, const double* c, u32 elem, double mass) {
   const double hl = q[0], aper2 = c[D_APER2], wavelen = q[2];
   double x = p.x, y = p.y;
   x += p.xp * hl;
@@ -370,7 +400,7 @@ __device__ __forceinline__ void op_drift(Pt& p, const double* q, const double* c
 }
 
 // simulation_kernel.cu:142-218 -- two quarter-length thick-lens maps, then the aperture test
-__device__ __forceinline__ void op_quad_half(Pt& p, const double* q, const double* c, u32 elem, double mass) {
+HPS_HD void op_quad_half(Pt& p, const double* q, const double* c, u32 elem, double mass) {
   const double length = q[0], wavelen = q[3];
   const double aper2 = c[Q_APER2], qg = c[Q_QG];
   double tx = p.x, ty = p.y;  // what the aperture test sees
@@ -406,7 +436,7 @@ __device__ __forceinline__ void op_quad_half(Pt& p, const double* q, const doubl
 }
 
 // simulation_kernel.cu:226-288
-__device__ __forceinline__ void op_gap_first(Pt& p, const double* q, const double* c, bool ccl, double mass) {
+HPS_HD void op_gap_first(Pt& p, const double* q, const double* c, bool ccl, double mass) {
   const double dd1 = c[GC_DD];
   const double phi = p.phi, w = p.w;
   p.x = p.x + dd1 * p.xp;
@@ -431,7 +461,7 @@ __device__ __forceinline__ void op_gap_first(Pt& p, const double* q, const doubl
 }
 
 // simulation_kernel.cu:16-73 (polynomial modified Bessel functions)
-__device__ __forceinline__ double bessi0c(double rx) {
+HPS_HD double bessi0c(double rx) {
   double ans, y, ax = fabs(rx);
   if (ax < 3.75) {
     y = rx / 3.75; y = y * y;
@@ -443,7 +473,7 @@ __device__ __forceinline__ double bessi0c(double rx) {
   }
   return ans;
 }
-__device__ __forceinline__ double bessi1c(double rx) {
+HPS_HD double bessi1c(double rx) {
   double y, ans, ax = fabs(rx);
   if (ax < 3.75) {
     y = rx / 3.75; y = y * y;
@@ -458,7 +488,7 @@ __device__ __forceinline__ double bessi1c(double rx) {
 }
 
 // simulation_kernel.cu:290-497
-__device__ __forceinline__ void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, double mass) {
+HPS_HD void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, double mass) {
   const double dd2 = c[GC_DD];
   double x = p.x, y = p.y, xp = p.xp, yp = p.yp;
   const double inv_mass = c[GC_INV_MASS];
@@ -555,7 +585,7 @@ __device__ __forceinline__ void op_gap_second(Pt& p, const double* q, const doub
 
 // simulation_kernel.cu:603-805.  q: 0 radius 1 angle 2 edge_in 3 edge_out 4 half_gap 5 k1 6 k2 7 field_index
 // 8 kinetic_energy 9 wavelen
-__device__ __forceinline__ void op_dipole(Pt& p, const double* q, bool second, double mass) {
+HPS_HD void op_dipole(Pt& p, const double* q, bool second, double mass) {
   double x = p.x, xp = p.xp, y = p.y, yp = p.yp;
   const double h = 1.0 / q[0];
   const double hf_g = q[4], k1 = q[5], k2 = q[6], findx = q[7], design_w = q[8];
@@ -614,7 +644,7 @@ __device__ __forceinline__ void op_dipole(Pt& p, const double* q, bool second, d
 }
 
 // simulation_kernel.cu:807-871.  q: 0 w_ref 1 freq 2 voltage 3 phase 4 aperture 5 freq_ratio 6 wavelen
-__device__ __forceinline__ void op_buncher(Pt& p, const double* q, u32 elem, double mass, double charge) {
+HPS_HD void op_buncher(Pt& p, const double* q, u32 elem, double mass, double charge) {
   const double wavelen = q[6];
   const double x = p.x, y = p.y, w = p.w;
   const double phi = p.phi * q[5];
@@ -648,8 +678,183 @@ __device__ __forceinline__ void op_buncher(Pt& p, const double* q, u32 elem, dou
   p.w = wf;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fast maps (MATH == 1): the same formulas with fewer fp64 divisions and square roots
+// ------------------------------------------------------------------------------------------------
+// The sweep is bound by the latency of dependent fp64 chains (profiles/r1_ncu_k_segment.txt: fp64 pipe 30 %,
+// top stall "wait"); an IEEE division is ~12 and a square root ~16 dependent instructions.  Here every
+// division by a block-uniform quantity is a multiplication by a reciprocal prepared once per op
+// (prepare_op / kick_prepare), sqrt-then-divide pairs are one rsqrt, and quotients that share a
+// denominator share one reciprocal.  Each rewrite moves a result by a few ulp (1e-16 relative); the parity
+// budget is 1e-9.  The aperture / loss tests themselves are evaluated exactly as in the reference.
+HPS_HD double inv_beta_of(double w, double inv_mass) {
+  const double g1 = w * inv_mass;
+  return (g1 + 1.0) * rsqrt(g1 * (g1 + 2.0));
+}
+
+HPS_HD void op_drift_f(Pt& p, const double* q, const double* c, u32 elem, double inv_mass) {
+  const double hl = q[0], aper2 = c[D_APER2];
+  double x = p.x, y = p.y;
+  x += p.xp * hl;
+  y += p.yp * hl;
+  if (aper2 != 0.0 && x * x + y * y > aper2) p.loss = elem;
+  else {
+    p.x = x; p.y = y;
+    p.phi += c[D_PH_OVER_WL] * inv_beta_of(p.w, inv_mass);
+  }
+}
+
+HPS_HD void op_quad_half_f(Pt& p, const double* q, const double* c, u32 elem, double inv_mass) {
+  const double length = q[0];
+  const double aper2 = c[Q_APER2], qg = c[Q_QG];
+  double tx = p.x, ty = p.y;
+  const double g1 = p.w * inv_mass;
+  const double t = g1 * (g1 + 2.0);
+  if (qg == 0) {
+    p.x = tx + p.xp * length * 0.5;
+    p.y = ty + p.yp * length * 0.5;
+  } else {
+    const double rbg = rsqrt(t * (1.0 + p.xp * p.xp + p.yp * p.yp));  // 1 / (beta gamma)_perp
+    const double k2 = c[Q_KC] * rbg;                                   // |qG| c / (m bg)
+    const double inv_k = rsqrt(k2), k = k2 * inv_k;
+    const double kds = c[Q_LEN4] * k;
+    double s, cs, sh = sinh(kds), ch = cosh(kds);
+    sincos(kds, &s, &cs);
+    const double sovk = s * inv_k, shovk = sh * inv_k, sk = s * k, shk = sh * k;
+    double x = p.x, xp = p.xp, y = p.y, yp = p.yp, u;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      if (qg > 0.0) {
+        u = cs * x + sovk * xp; xp = -sk * x + cs * xp; x = u;
+        u = ch * y + shovk * yp; yp = shk * y + ch * yp; y = u;
+      } else {
+        u = ch * x + shovk * xp; xp = shk * x + ch * xp; x = u;
+        u = cs * y + sovk * yp; yp = -sk * y + cs * yp; y = u;
+      }
+    }
+    p.x = x; p.xp = xp; p.y = y; p.yp = yp;
+    tx = x; ty = y;
+  }
+  if (aper2 != 0 && tx * tx + ty * ty > aper2) p.loss = elem;
+  else p.phi += c[Q_PH_OVER_WL] * ((g1 + 1.0) * rsqrt(t));
+}
+
+HPS_HD void op_gap_first_f(Pt& p, const double* q, const double* c, bool ccl, double inv_mass) {
+  const double dd1 = c[GC_DD];
+  const double phi = p.phi;
+  p.x = p.x + dd1 * p.xp;
+  p.y = p.y + dd1 * p.yp;
+  const double ib = inv_beta_of(p.w, inv_mass);
+  if (q[G_AMP] == 0.0) p.phi = phi + c[GF_DD_OVER_WL] * ib;
+  else if (!ccl) p.phi = phi + (c[GC_BETA_IN] * ib) * c[GC_PI_CLBL_DPS] + c[GF_DCLQ_OVER_WL] * ib;
+  else p.phi = phi + (1.0 - c[GC_BETAG_CCL] * (c[GF_IBETA_IN] - ib)) * c[GC_PI_CLBL_DPS];
+}
+
+// both modified Bessel functions from one argument reduction (simulation_kernel.cu:16-73)
+HPS_HD void bessi01c(double rx, double& b0, double& b1) {
+  const double ax = fabs(rx);
+  if (ax < 3.75) {
+    double y = rx * (1.0 / 3.75); y = y * y;
+    b0 = 1.0 + y * (3.5156229 + y * (3.0899424 + y * (1.2067492 + y * (0.2659732 + y * (0.360768e-1 + y * 0.45813e-2)))));
+    b1 = ax * (0.5 + y * (0.87890594 + y * (0.51498869 + y * (0.15084934 + y * (0.2658733e-1 + y * (0.301532e-2 + y * 0.32411e-3))))));
+  } else {
+    const double y = 3.75 / ax;
+    const double e = exp(ax) * rsqrt(ax);
+    b0 = e * (0.39894228 + y * (0.1328592e-1 + y * (0.225319e-2 + y * (-0.157565e-2 + y * (0.916281e-2 +
+         y * (-0.2057706e-1 + y * (0.2635537e-1 + y * (-0.1647633e-1 + y * 0.392377e-2))))))));
+    double a = 0.2282967e-1 + y * (-0.2895312e-1 + y * (0.1787654e-1 - y * 0.420059e-2));
+    a = 0.39894228 + y * (-0.3988024e-1 + y * (-0.362018e-2 + y * (0.163801e-2 + y * (-0.1031555e-1 + y * a))));
+    b1 = a * e;
+  }
+  if (rx < 0.0) b1 = -b1;
+}
+
+HPS_HD void op_gap_second_f(Pt& p, const double* q, const double* c, bool ccl, double inv_mass) {
+  const double dd2 = c[GC_DD];
+  double x = p.x, y = p.y, xp = p.xp, yp = p.yp;
+  const double phi = p.phi;
+  double w = p.w;
+  double gam = w * inv_mass;
+  const double t1 = gam * (gam + 2.0);
+  const double rbg1 = rsqrt(t1);
+  const double bg1 = t1 * rbg1;
+  const double ib1 = (gam + 1.0) * rbg1;  // 1 / beta
+  const double beta = bg1 / (gam + 1.0);
+  double t_fac, tp_fac, sp_fac;
+  {
+    double bb = beta;
+    if (beta > 1.1 * q[G_FBC]) bb = q[G_FBC];
+    else if (beta < q[G_FBMIN]) bb = q[G_FBMIN];
+    t_fac = q[G_T0] + bb * (q[G_T1] + bb * (q[G_T2] + bb * (q[G_T3] + bb * (q[G_T4] + bb * q[G_T5]))));
+    const double coef = bb * bb * c[GF_INV_TTF_DEN];
+    tp_fac = coef * (q[G_T1] + bb * (2 * q[G_T2] + bb * (3 * q[G_T3] + bb * (4 * q[G_T4] + 5 * bb * q[G_T5]))));
+    sp_fac = -coef * (q[G_S1] + bb * (2 * q[G_S2] + bb * (3 * q[G_S3] + bb * (4 * q[G_S4] + 5 * bb * q[G_S5]))));
+  }
+  if (q[G_AMP] == 0.0 || (ccl && beta < q[G_FBMIN])) {
+    p.x = x + dd2 * xp;
+    p.y = y + dd2 * yp;
+    p.phi = phi + c[GF_DD_OVER_WL] * ib1;
+    return;
+  }
+  const double gmg = c[GC_GMG], inv_gmg = c[GF_INV_GMG];
+  const double inv_gmg2 = c[GC_INV_GMG2];
+  const double concomm = c[GC_CONCOMM];
+  const double con1 = c[GC_CON1];
+  const double con2nex = c[GC_CON2NEX];
+  const double inv_gmgcl = c[GC_INV_GMGCL], inv_fkis = c[GC_INV_FKIS];
+  const double con5nex = concomm * (t_fac * inv_fkis - c[GC_X5] * tp_fac * inv_gmg2);
+  double tw = t_fac;
+  if (ccl) tw = t_fac - K_TWOPI * tp_fac * (c[GC_BETA_IN] * ib1 - 1.0) * c[GF_BETAG_OVER_BIN];
+  const double con5nex1 = c[GC_CONCOMM1] * t_fac;
+  const double con5nex2 = -con2nex * t_fac * inv_fkis;
+  const double fkr = c[GC_FKR];
+  const double sinps = c[GC_SINPS], cosps = c[GC_COSPS];
+  double phi1, sinp1, cosp1;
+  if (ccl) phi1 = phi + q[G_PHSHIFT] - c[GF_DG_OVER_WL] * ib1 + c[GC_PH_CONST];
+  else phi1 = phi + q[G_PHSHIFT];
+  sincos(phi1, &sinp1, &cosp1);
+  const double prome1 = -con1 * (tp_fac * (sinp1 - sinps) + sp_fac * (cosp1 - cosps));
+  sincos(phi1 + prome1, &sinp1, &cosp1);
+
+  const double rs_p = x * x + y * y;
+  const double rrp = x * xp + y * yp;
+  double iris = 0.0, ris = 0.0;
+  if (rs_p > 0.0) { iris = rsqrt(rs_p); ris = rs_p * iris; }
+  const double fkrris = fkr * ris;
+  double b0c, b1c;
+  bessi01c(fkrris, b0c, b1c);
+  const double b1p = (fkrris != 0.0) ? b0c - b1c * (iris * c[GF_INV_FKR]) : 0.5;
+  const double bes1covr = (ris != 0.0) ? b1c * iris : fkr * 0.5;
+  const double delte = c[GC_AQ_EFL] * (tw * b0c * cosp1 + ((tw - K_TWOPI * tp_fac) * inv_gmg * bes1covr + tw * inv_gmg * fkr * b1p -
+                                                           tw * gmg * bes1covr) * rrp * sinp1);
+  w += delte;
+  gam = w * inv_mass;
+  const double t2 = gam * (gam + 2.0);
+  const double rbg = rsqrt(t2);
+  const double ib = (gam + 1.0) * rbg;  // 1 / beta after the energy gain
+  const double bgr = bg1 * rbg;
+  const double onema = 1.0 - (con5nex * bes1covr + con5nex1 * b1p + con5nex2 * bes1covr) * cosp1;
+  const double dovbl = con2nex * bes1covr * tw * sinp1;
+  const double bgrovonema = bgr / onema;
+  xp = -dovbl * x + bgrovonema * xp;
+  x = x * onema + dd2 * xp;
+  yp = -dovbl * y + bgrovonema * yp;
+  y = y * onema + dd2 * yp;
+  const double rpris = rrp * iris;  // iris == 0 when rs_p == 0, as in the reference
+  const double prome = 2.0 * con1 * (-tp_fac * b0c + ris * tw * b1c * inv_gmgcl) * (sinp1 - sinps) -
+                       c[GC_EFL] * inv_mass * tw * b1c * rpris * (cosp1 - cosps);
+  double phi_new;
+  if (ccl) phi_new = phi + (1.0 - c[GC_BETAG_CCL] * (c[GF_IBETA_OUT] - ib)) * c[GC_PI_CLBL_DPS] + prome;
+  else phi_new = phi + (c[GC_BETA_OUT] * ib) * c[GC_PI_CLBL_DPS] + prome + c[GF_DCLQ_OVER_WL] * ib;
+  if (!(w > 0.0) || x != x || y != y || xp != xp || yp != yp || phi_new != phi_new) {
+    p.loss = 33333333u;
+  } else {
+    p.x = x; p.y = y; p.xp = xp; p.yp = yp; p.w = w; p.phi = phi_new;
+  }
+}
+
 // relative phase (beam_kernel.cu:1506-1522)
-__device__ __forceinline__ double rel_phi(double phi, double ref) {
+HPS_HD double rel_phi(double phi, double ref) {
   double tmp = phi - ref + K_PI;
   double sign = 1.0;
   if (tmp < 0) { sign = -1.0; tmp = -tmp; }
@@ -664,11 +869,12 @@ struct KickCtx {  // block-uniform inputs of the space-charge kick, staged in sh
   double dr, dz, beta, ratio_r, ratio_z, ratio_q, ratio_g;
   u32 adj_bunch, num_on_mesh, nr, nz;
   // derived once per block (kick_prepare) with the reference's expression order
-  double gmg, dr_eff, dzg, hl, c2, c3, xfac, yfac, pl, cbgcoef, nr_dr, er_c3, ez_c3, inv_mass_unused;
+  double gmg, dr_eff, dzg, hl, c2, c3, xfac, yfac, pl, cbgcoef, nr_dr, er_c3, ez_c3;
+  double inv_epsq, inv_dr, inv_dzg;  // reciprocals for the fast kick
 };
 
 // particle-independent part of space_charge_kernel.cu:597-616, 680-681
-__device__ inline void kick_prepare(KickCtx& k, const double* q, double mass, u32 n_global) {
+__host__ __device__ inline void kick_prepare(KickCtx& k, const double* q, double mass, u32 n_global) {
   const double length = q[0], current = q[1], freq = q[2];
   const double beta = k.beta;
   const double gmg = rsqrt(1.0 - beta * beta);
@@ -690,10 +896,13 @@ __device__ inline void kick_prepare(KickCtx& k, const double* q, double mass, u3
   const double ez_ratio = k.ratio_q / (k.ratio_z * k.ratio_z);
   k.er_c3 = er_ratio * c3;
   k.ez_c3 = ez_ratio * c3;
+  k.inv_epsq = 1.0 / k.epsq;
+  k.inv_dr = 1.0 / k.dr_eff;
+  k.inv_dzg = 1.0 / k.dzg;
 }
 
 // space_charge_kernel.cu:573-706
-__device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __restrict__ fld, double mass) {
+HPS_HD void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __restrict__ fld, double mass) {
   if (!(p.loss == 0 && lloss == 0)) return;
   const double beta = k.beta;
   const double phi = rel_phi(p.phi, k.phi_ref);
@@ -742,7 +951,7 @@ __device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, c
     u32 m = l + (k.nr + 1);
     const u32 tbl_sz = (k.nr + 1) * (k.nz + 1);
     if (m >= tbl_sz) m = tbl_sz - 1;
-    const double2 fl = __ldg(&fld[l]), fl1 = __ldg(&fld[l - 1]), fm = __ldg(&fld[m]), fm1 = __ldg(&fld[m - 1]);
+    const double2 fl = ld_field(&fld[l]), fl1 = ld_field(&fld[l - 1]), fm = ld_field(&fld[m]), fm1 = ld_field(&fld[m - 1]);
     cbgr = k.er_c3 * (d * (a * fl.x + b * fl1.x) + c * (a * fm.x + b * fm1.x));
     cbgzs = k.ez_c3 * (d * (a * fl.y + b * fl1.y) + c * (a * fm.y + b * fm1.y));
   }
@@ -756,6 +965,77 @@ __device__ __forceinline__ void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, c
     p.xp = bgx / bgzf;
     p.yp = bgy / bgzf;
     p.w *= 1.0 + (gm + 1.0) * (bgzf - bgz) / (gm * bgz);
+  }
+}
+
+// fast form of op_sc_kick: 1 sqrt-free rsqrt pair, 1 reciprocal and 1 division instead of 9 divisions + 2 sqrt
+HPS_HD void op_sc_kick_f(Pt& p, u32 lloss, const KickCtx& k, const double2* __restrict__ fld, double inv_mass) {
+  if (!(p.loss == 0 && lloss == 0)) return;
+  const double beta = k.beta;
+  const double phi = rel_phi(p.phi, k.phi_ref);
+  const double gmg = k.gmg;
+  const double hl = k.hl;
+  const double gm = p.w * inv_mass + 1.0;
+  const double tb = (gm - 1.0) * (gm + 1.0);
+  const double rbgz = rsqrt(tb);
+  const double bgz = tb * rbgz;
+  double bgx = bgz * p.xp, bgy = bgz * p.yp;
+  double bgzstar = gmg * (bgz - beta * gm);
+  const double xxbar = p.x - k.xbar, yybar = p.y - k.ybar;
+  const double r2 = xxbar * xxbar * k.inv_epsq + yybar * yybar * k.epsq;
+  double r = 1.0e-8, rinv = 1.0e8;
+  if (r2 > 0.0) { rinv = rsqrt(r2); r = r2 * rinv; }
+  const double xovr = xxbar * k.xfac * rinv, yovr = yybar * k.yfac * rinv;
+  double ddz = phi - k.phimc;
+  while (ddz > K_PI || ddz < -K_PI) {
+    if (ddz > 0.0) ddz -= K_TWOPI; else ddz += K_TWOPI;
+  }
+  double z = -k.c2 * ddz;
+  double cbgr, cbgzs;
+  if (r > k.nr_dr || fabs(z) > hl) {  // off the mesh: point-charge field of the on-mesh charge (H17)
+    z = -k.c2 * (phi - k.phimc);
+    const double rr = r * r;
+    double rd = rsqrt(z * z + rr);
+    double invd3 = rd * rd * rd;
+    double rod3 = r * invd3, zod3 = z * invd3;
+    for (int nb = 1; nb <= (int)k.adj_bunch; ++nb) {
+      int xi = nb;
+      for (int lr = 1; lr <= 2; ++lr) {
+        const double s = z + xi * k.pl;
+        rd = rsqrt(s * s + rr);
+        invd3 = rd * rd * rd;
+        rod3 += r * invd3;
+        zod3 += s * invd3;
+        xi = -xi;
+      }
+    }
+    cbgr = k.cbgcoef * rod3;
+    cbgzs = k.cbgcoef * zod3;
+  } else {
+    const double ri = r * k.inv_dr, zj = (z + hl) * k.inv_dzg;
+    const u32 i = 1 + (int)ri;
+    const double a = ri - (i - 1.0), b = 1.0 - a;
+    const u32 j = 1 + (int)zj;
+    const double c = zj - (j - 1.0), d = 1.0 - c;
+    const u32 l = (j - 1) * (k.nr + 1) + i;
+    u32 m = l + (k.nr + 1);
+    const u32 tbl_sz = (k.nr + 1) * (k.nz + 1);
+    if (m >= tbl_sz) m = tbl_sz - 1;
+    const double2 fl = ld_field(&fld[l]), fl1 = ld_field(&fld[l - 1]), fm = ld_field(&fld[m]), fm1 = ld_field(&fld[m - 1]);
+    cbgr = k.er_c3 * (d * (a * fl.x + b * fl1.x) + c * (a * fm.x + b * fm1.x));
+    cbgzs = k.ez_c3 * (d * (a * fl.y + b * fl1.y) + c * (a * fm.y + b * fm1.y));
+  }
+  bgx += cbgr * xovr;
+  bgy += cbgr * yovr;
+  bgzstar += cbgzs;
+  const double gstar = 1.0 + 0.5 * bgzstar * bgzstar;
+  const double bgzf = gmg * (bgzstar + beta * gstar);
+  if (bgzf <= 0.0) p.loss = 9999u;
+  else {
+    const double ibgzf = 1.0 / bgzf;
+    p.xp = bgx * ibgzf;
+    p.yp = bgy * ibgzf;
+    p.w *= 1.0 + (gm + 1.0) * (bgzf - bgz) * rbgz / gm;
   }
 }
 

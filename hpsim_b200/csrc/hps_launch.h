@@ -9,7 +9,7 @@ namespace hps {
 
 struct LaunchCfg {
   cudaStream_t stream;
-  int seg_variant;        // 0: 2 particles/thread, 1: 1 particle/thread (3 blocks/SM), 2: 1 particle/thread (4 blocks/SM)
+  int seg_variant;        // see seg_kernel() in hps_kernels.cu; 0 = default (2 particles/thread, fast maps)
   unsigned grid_seg;      // grid of the fused segment sweep (variant in use)
   unsigned grid_seg1;     // grid of the full-op-set variant (1 particle per thread)
   unsigned grid_pairs;    // grid of the 2-particles-per-thread statistic sweeps
@@ -63,6 +63,8 @@ void launch_shift(const LaunchCfg&, double* a, double v, u32 n, u32 offset);
 void launch_cut(const LaunchCfg&, const double* a, u32* loss, double lo, double hi, u32 n, u32 offset);
 void launch_rel_phi_out(const LaunchCfg&, const BeamView&, const DevStats*, double* out);
 int segment_occupancy(int variant);
+int segment_full_variant(int variant);  // the full-op-set kernel that goes with a variant
+bool segment_pairs(int variant);        // variant processes 2 particles per thread
 size_t deposit_smem(const KickParams&);
 size_t field_smem(const KickParams&, int threads);
 int field_threads(const KickParams&);

@@ -1,0 +1,150 @@
+// host_maps.cu -- TEST INFRASTRUCTURE (no GPU needed).
+//
+// The per-particle element maps of hpsim_b200/csrc/hps_kernels.cuh are plain fp64 arithmetic and compile for the
+// host.  This program runs every op record the planner produces for a lattice range through BOTH forms of each
+// map -- the reference's expression order (MATH = 0; restates simulation_kernel.cu:16-871 and
+// space_charge_kernel.cu:573-706) and the fast form the product launches by default (MATH = 1: reciprocals of
+// block-uniform quantities, rsqrt for sqrt-then-divide) -- on random particles around the design energy, and
+// reports the largest deviation.  tests/test_host_maps.py builds it with nvcc (host code only) and asserts
+// that the deviation stays at rounding level and that the loss flags agree.
+//
+//   host_maps <lattice.lat> <first index> <last index> <particles per op> <seed>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../hpsim_b200/csrc/hps_kernels.cuh"
+#include "../hpsim_b200/csrc/hps_plan.h"
+
+using namespace hps;
+
+static bool read_lattice(const char* path, std::vector<hps_elem>& out) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  char magic[4];
+  uint32_t ver = 0, n = 0;
+  bool ok = fread(magic, 1, 4, f) == 4 && fread(&ver, 4, 1, f) == 1 && fread(&n, 4, 1, f) == 1 && memcmp(magic, "HPSL", 4) == 0;
+  if (ok) {
+    out.resize(n);
+    ok = fread(out.data(), sizeof(hps_elem), n, f) == n;
+  }
+  fclose(f);
+  return ok;
+}
+
+struct Dev {
+  double x = 0, xp = 0, y = 0, yp = 0, phi = 0, w = 0;
+  long loss_mismatch = 0, n = 0;
+  void add(const Pt& a, const Pt& b) {
+    ++n;
+    if (a.loss != b.loss) { ++loss_mismatch; return; }
+    if (a.loss != 0) return;
+    auto rel = [](double u, double v, double floor_) { return fabs(u - v) / fmax(fabs(v), floor_); };
+    x = fmax(x, rel(a.x, b.x, 1e-3));
+    xp = fmax(xp, rel(a.xp, b.xp, 1e-3));
+    y = fmax(y, rel(a.y, b.y, 1e-3));
+    yp = fmax(yp, rel(a.yp, b.yp, 1e-3));
+    phi = fmax(phi, rel(a.phi, b.phi, 1.0));
+    w = fmax(w, rel(a.w, b.w, 1e-3));
+  }
+  double worst() const { return fmax(fmax(fmax(x, xp), fmax(y, yp)), fmax(phi, w)); }
+};
+
+int main(int argc, char** argv) {
+  if (argc < 6) { fprintf(stderr, "usage: host_maps lattice first last n seed\n"); return 2; }
+  std::vector<hps_elem> lat;
+  if (!read_lattice(argv[1], lat)) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+  const u32 first = (u32)atoi(argv[2]), last = (u32)atoi(argv[3]);
+  const int npart = atoi(argv[4]);
+  std::mt19937_64 rng((unsigned long long)atoll(argv[5]));
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+
+  const double mass = 939.294, charge = -1.0;
+  EngineState eng;
+  BeamHost beam = {mass, charge, 0.015, 201.25, 0.75, 1u << 20};
+  ScHost sc;  // off: the plan holds the element maps only
+  Plan plan = build_plan(lat, first, last, eng, beam, sc);
+  if (!plan.error.empty()) { fprintf(stderr, "plan: %s\n", plan.error.c_str()); return 2; }
+
+  Dev dev[16];
+  long nops[16] = {0};
+  double design_w = 0.75;
+  const double inv_mass = 1.0 / mass;
+  for (const Op& op : plan.ops) {
+    OpC oc;
+    memset(&oc, 0, sizeof(oc));
+    prepare_op(op, oc, mass, charge);
+    if (op.type == OP_GAP_FIRST || op.type == OP_GAP_SECOND) design_w = op.p[G_DESIGN_W];
+    nops[op.type]++;
+    for (int i = 0; i < npart; ++i) {
+      Pt a;
+      a.x = 4e-3 * U(rng); a.y = 4e-3 * U(rng); a.xp = 8e-3 * U(rng); a.yp = 8e-3 * U(rng);
+      a.phi = K_PI * U(rng) + K_TWOPI * floor(2000.0 * U(rng));
+      a.w = design_w * (1.0 + 0.01 * U(rng));
+      a.loss = 0;
+      if (i == 0) { a.x = a.y = a.xp = a.yp = 0.0; }  // the reference particle sits on the axis
+      Pt b = a;
+      switch (op.type) {
+        case OP_DRIFT: op_drift(a, op.p, oc.c, op.elem, mass); op_drift_f(b, op.p, oc.c, op.elem, inv_mass); break;
+        case OP_QUAD_HALF: op_quad_half(a, op.p, oc.c, op.elem, mass); op_quad_half_f(b, op.p, oc.c, op.elem, inv_mass); break;
+        case OP_GAP_FIRST: op_gap_first(a, op.p, oc.c, op.flag != 0, mass); op_gap_first_f(b, op.p, oc.c, op.flag != 0, inv_mass); break;
+        case OP_GAP_SECOND: op_gap_second(a, op.p, oc.c, op.flag != 0, mass); op_gap_second_f(b, op.p, oc.c, op.flag != 0, inv_mass); break;
+        default: continue;
+      }
+      dev[op.type].add(b, a);
+    }
+    if (op.type == OP_GAP_SECOND) design_w = op.p[G_EOUT];
+  }
+
+  // space-charge kick: synthetic but representative block-uniform context, smooth field table
+  {
+    const u32 nr = 32, nz = 128;
+    std::vector<double2> fld((nr + 1) * (nz + 1));
+    for (u32 j = 0; j <= nz; ++j)
+      for (u32 i = 0; i <= nr; ++i) fld[j * (nr + 1) + i] = make_double2(1e-3 * sin(0.2 * i) * cos(0.05 * j), 1e-3 * cos(0.1 * i) * sin(0.07 * j));
+    for (int rep = 0; rep < 64; ++rep) {
+      const double wavg = rep % 2 ? 0.75 : 40.0 + 700.0 * fabs(U(rng));
+      KickCtx k;
+      memset(&k, 0, sizeof(k));
+      const double gm = wavg / mass + 1.0;
+      k.beta = sqrt(1.0 - 1.0 / (gm * gm));
+      k.phimc = 0.01 * U(rng); k.xbar = 1e-4 * U(rng); k.ybar = 1e-4 * U(rng); k.epsq = 1.0 + 0.5 * U(rng);
+      k.phi_ref = K_TWOPI * floor(1000.0 * U(rng)) + 0.3 * U(rng);
+      k.dr = 3.0 * 2e-3 / nr; k.dz = k.beta * K_CLIGHT / 201.25 / nz * (rep % 2 ? 1.0 : 0.2);
+      k.ratio_r = 1.0 + 0.01 * U(rng); k.ratio_z = 1.0 + 0.01 * U(rng); k.ratio_q = 1.0; k.ratio_g = 1.0 + 0.001 * U(rng);
+      k.adj_bunch = rep % 2 ? 3 : 0; k.num_on_mesh = 900000; k.nr = nr; k.nz = nz;
+      const double q[3] = {0.025, 0.015, 201.25};
+      kick_prepare(k, q, mass, 1u << 20);
+      for (int i = 0; i < npart * 8; ++i) {
+        Pt a;
+        const double spread = (i % 5 == 0) ? 5.0 : 1.0;  // every 5th particle far out: the off-mesh branch
+        a.x = spread * 2e-3 * U(rng); a.y = spread * 2e-3 * U(rng); a.xp = 8e-3 * U(rng); a.yp = 8e-3 * U(rng);
+        a.phi = k.phi_ref + (rep % 2 ? K_PI : 0.3) * spread * U(rng);
+        a.w = wavg * (1.0 + 0.01 * U(rng));
+        a.loss = 0;
+        Pt b = a;
+        op_sc_kick(a, 0u, k, fld.data(), mass);
+        op_sc_kick_f(b, 0u, k, fld.data(), inv_mass);
+        dev[OP_SC_KICK].add(b, a);
+      }
+    }
+    nops[OP_SC_KICK] = 64;
+  }
+
+  const char* names[16] = {"none", "drift", "quad_half", "gap_first", "gap_second", "dipole_first", "dipole_second", "buncher",
+                           "rotation", "steerer", "caperture", "raperture", "sc_kick", "freq_change", "", ""};
+  double worst = 0.0;
+  long mism = 0;
+  for (int t = 0; t < 16; ++t) {
+    if (dev[t].n == 0) continue;
+    printf("%-12s ops %6ld particles %8ld loss_mismatch %ld  x %.2e xp %.2e y %.2e yp %.2e phi %.2e w %.2e\n", names[t], nops[t],
+           dev[t].n, dev[t].loss_mismatch, dev[t].x, dev[t].xp, dev[t].y, dev[t].yp, dev[t].phi, dev[t].w);
+    worst = fmax(worst, dev[t].worst());
+    mism += dev[t].loss_mismatch;
+  }
+  printf("WORST %.3e LOSS_MISMATCH %ld\n", worst, mism);
+  return 0;
+}
