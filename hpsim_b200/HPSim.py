@@ -75,6 +75,19 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
+def set_math(mode: str) -> None:
+    """Arithmetic of the fused segment kernel on the current device: "reference" (the reference's expression
+    order with IEEE-exact division / sqrt), "fast" or "reference_nvcc"; see hps_ctx_set_math in
+    include/hpsim_b200.h.  No reference counterpart."""
+    c = _ctx()
+    c.check(c.lib.hps_ctx_set_math(c.h, {"reference": 0, "fast": 1, "reference_nvcc": 2}[mode]))
+
+
+def get_math() -> str:
+    c = _ctx()
+    return {0: "reference", 1: "fast", 2: "reference_nvcc"}[c.lib.hps_ctx_get_math(c.h)]
+
+
 def init_sharding(rank: int, nranks: int, unique_id: bytes) -> str:
     """Particle-shard every Beam created afterwards over `nranks` processes (one GPU each, SPMD:
     all ranks must issue the same HPSim calls in the same order).  Returns the exchange mode."""

@@ -69,6 +69,8 @@ PROTOTYPES = {
     "hps_ctx_destroy": (None, [_vp]),
     "hps_last_error": (C.c_char_p, [_vp]),
     "hps_ctx_set_compat": (C.c_int, [_vp, C.c_int]),
+    "hps_ctx_set_math": (C.c_int, [_vp, C.c_int]),
+    "hps_ctx_get_math": (C.c_int, [_vp]),
     "hps_comm_unique_id": (C.c_int, [_vp]),
     "hps_ctx_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "hps_ctx_comm_mode": (C.c_int, [_vp]),
@@ -118,6 +120,7 @@ PROTOTYPES = {
     "hps_scheff_get": (C.c_int, [_vp, C.c_int, _dp]),
     "hps_scheff_set_mesh_size": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
     "hps_scheff_download_tables": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "hps_scheff_phase_cycles": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "hps_simulate": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(RunStats)]),
     "hps_engine_reset": (C.c_int, [_vp, _vp]),
 }

@@ -42,7 +42,8 @@ struct hps_ctx {
   unsigned max_grid = 0;    // cap for the light statistic sweeps
   unsigned seg_grid_cap = 0;  // resident blocks of the segment kernel variant in use
   unsigned seg_grid_cap_full = 0;
-  int seg_variant = 0;
+  int seg_variant = 20;  // HPS_MATH_REFERENCE, 2 particles per thread (seg_kernel() in hps_kernels.cu)
+  int fused = 1;   // moments + deposit + field solve in one launch (k_scheff) where the exchange mode allows it
   // program upload buffers
   Op* d_ops = nullptr;
   OpC* d_opc = nullptr;  // device-prepared constants, parallel to d_ops
@@ -55,6 +56,13 @@ struct hps_ctx {
   void* xr_mapped[HPS_XR_MAXR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   int pdl = 1;       // HPSIM_PDL=0 turns programmatic dependent launch off
+  // L2 residency (opt-in, HPSIM_L2_PERSIST=1): the particle slab of the beam being tracked becomes the stream's
+  // access-policy window (persisting lines).  Measured on C2: no gain (48.7 vs 48.0 ms per pass) -- the sweeps
+  // are bound by fp64 latency, not by where the 59 MB beam is read from -- so it is off by default.
+  int l2_persist = 0;
+  size_t l2_persist_max = 0, l2_window_max = 0;
+  const void* l2_window_base = nullptr;
+  size_t l2_window_bytes = 0;
   u32 mesh_seq = 0;  // launch counter of k_field: sequence number of the mesh hand-off (same on all ranks)
   // optional per-launch timing (hps_ctx_set_profile): one event between consecutive launches
   int profile = 0;
@@ -97,6 +105,7 @@ struct hps_scheff {
   double2* field_part = nullptr;  // [nr+1][chunks][nz+1] partial fields of the split solve
   u32* field_tickets = nullptr;   // [nr+1]
   double bin_scale = 0.0;         // fixed-point scale of the last simulate() (depends on the beam size)
+  unsigned fused_cap = 0;         // co-resident blocks of k_scheff for this mesh (0: fused chain not available)
 };
 
 namespace {
@@ -289,6 +298,14 @@ void prof_finish(hps_ctx* c) {
   c->prof_cls.clear();
 }
 
+int math_variant(int base, int mode) {  // base: 0 = 2 particles/thread, 1 / 2 = 1 particle/thread (3 / 4 blocks per SM)
+  switch (mode) {
+    case HPS_MATH_FAST: return base;
+    case HPS_MATH_REFERENCE: return base == 0 ? 20 : 21;
+    default: return base == 0 ? 10 : 11;  // HPS_MATH_REFERENCE_NVCC
+  }
+}
+
 int dirty_mask(const Op* ops, u32 n) {
   int d = 0;
   for (u32 i = 0; i < n; ++i) switch (ops[i].type) {
@@ -337,8 +354,17 @@ hps_ctx* hps_ctx_create(int device) {
             cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
   std::memset(&c->xr, 0, sizeof(c->xr));
   c->xr.nranks = 1;
-  if (const char* v = getenv("HPSIM_SEG_VARIANT")) c->seg_variant = atoi(v);
+  if (const char* v = getenv("HPSIM_SEG_VARIANT")) c->seg_variant = atoi(v);  // raw variant number (diagnostics)
+  if (const char* v = getenv("HPSIM_MATH"))  // "reference" / "fast" / "nvcc": same switch as hps_ctx_set_math
+    c->seg_variant = math_variant(c->seg_variant % 10, v[0] == 'r' ? HPS_MATH_REFERENCE : (v[0] == 'n' ? HPS_MATH_REFERENCE_NVCC : HPS_MATH_FAST));
   if (const char* v = getenv("HPSIM_PDL")) c->pdl = atoi(v);
+  if (const char* v = getenv("HPSIM_FUSED")) c->fused = atoi(v);
+  if (const char* v = getenv("HPSIM_L2_PERSIST")) c->l2_persist = atoi(v);
+  c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+  c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
+  if (c->l2_persist && c->l2_persist_max > 0 && c->l2_window_max > 0) {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max) != cudaSuccess) { cudaGetLastError(); c->l2_persist = 0; }
+  } else c->l2_persist = 0;
   int occ = ok ? segment_occupancy(c->seg_variant) : 0;
   if (occ < 1) occ = 1;
   c->seg_grid_cap = (unsigned)c->num_sms * (unsigned)occ;
@@ -374,6 +400,15 @@ void hps_ctx_destroy(hps_ctx* c) {
 }
 const char* hps_last_error(const hps_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
 int hps_ctx_set_compat(hps_ctx* c, int v) { c->compat = v; return HPS_OK; }
+int hps_ctx_get_math(hps_ctx* c) { return c->seg_variant >= 20 ? HPS_MATH_REFERENCE : (c->seg_variant >= 10 ? HPS_MATH_REFERENCE_NVCC : HPS_MATH_FAST); }
+int hps_ctx_set_math(hps_ctx* c, int mode) {
+  if (mode != HPS_MATH_REFERENCE && mode != HPS_MATH_FAST && mode != HPS_MATH_REFERENCE_NVCC) return fail(c, HPS_ERR_ARG, "unknown math mode");
+  c->seg_variant = math_variant(c->seg_variant % 10, mode);
+  const int occ = std::max(1, segment_occupancy(c->seg_variant));
+  c->seg_grid_cap = (unsigned)c->num_sms * (unsigned)occ;
+  c->seg_grid_cap_full = (unsigned)c->num_sms * (unsigned)std::max(1, segment_occupancy(segment_full_variant(c->seg_variant)));
+  return HPS_OK;
+}
 int hps_ctx_synchronize(hps_ctx* c) { CK(c, cudaStreamSynchronize(c->stream)); return HPS_OK; }
 uint64_t hps_ctx_launch_count(hps_ctx* c) { return c->launches; }
 int hps_ctx_set_profile(hps_ctx* c, int on) {
@@ -408,6 +443,10 @@ int hps_ctx_flush_l2(hps_ctx* c) {
     CK(c, cudaMalloc(&c->flush_buf, c->flush_bytes));
   }
   CK(c, cudaMemsetAsync(c->flush_buf, 0x5a, c->flush_bytes, c->stream));
+  if (c->l2_persist) {  // persisting lines survive ordinary traffic: drop them too
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaCtxResetPersistingL2Cache());
+  }
   return HPS_OK;
 }
 
@@ -515,6 +554,14 @@ void hps_beam_destroy(hps_beam* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
+  if (b->ctx->l2_window_base == b->slab && b->slab) {  // the stream's L2 window must not outlive the slab
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof(av));
+    cudaStreamSetAttribute(b->ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaCtxResetPersistingL2Cache();
+    b->ctx->l2_window_base = nullptr;
+    b->ctx->l2_window_bytes = 0;
+  }
   cudaFree(b->slab); cudaFree(b->st); cudaFree(b->tmp);
   for (auto& s : b->slot) cudaFree(s.slab);
   delete b;
@@ -799,7 +846,9 @@ static int scheff_alloc(hps_scheff* s) {
   kp.nr = s->h.nr; kp.nz = s->h.nz;
   CK(c, cudaMalloc(&s->bins, (nb + 2) * sizeof(double)));  // + on-mesh count, max |phi| (sharded hand-off)
   CK(c, cudaMalloc(&s->field, nf * sizeof(double2)));
-  CK(c, cudaMalloc(&s->field_part, nf * field_chunks(kp) * sizeof(double2)));
+  const size_t chunks = std::max<size_t>(field_chunks(kp), scheff_supported(kp) ? scheff_items(kp) / (s->h.nr + 1) : 0);
+  CK(c, cudaMalloc(&s->field_part, nf * chunks * sizeof(double2)));
+  s->fused_cap = scheff_supported(kp) ? (unsigned)std::max(0, scheff_occupancy(kp)) * (unsigned)c->num_sms : 0u;
   CK(c, cudaMalloc(&s->field_tickets, (s->h.nr + 1) * sizeof(u32)));
   CK(c, cudaMemsetAsync(s->field_tickets, 0, (s->h.nr + 1) * sizeof(u32), c->stream));
   CK(c, cudaMemsetAsync(s->bins, 0, (nb + 2) * sizeof(double), c->stream));
@@ -875,6 +924,14 @@ int hps_scheff_set_mesh_size(hps_scheff* s, uint32_t nr, uint32_t nz) {  // spac
   s->h.nr = nr; s->h.nz = nz;
   return scheff_alloc(s);
 }
+int hps_scheff_phase_cycles(hps_scheff* s, uint64_t out[8]) {
+  hps_ctx* c = s->ctx;
+  ScDev h;
+  CK(c, cudaMemcpyAsync(&h, s->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 8; ++i) out[i] = h.phase_clk[i];
+  return HPS_OK;
+}
 int hps_scheff_download_tables(hps_scheff* s, double* bins, double* field, double* dr_dz) {
   hps_ctx* c = s->ctx;
   cudaSetDevice(c->device);
@@ -941,6 +998,19 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
   std::memset(&before, 0, sizeof(before));
   if (sc) CK(c, cudaMemcpyAsync(&before, sc->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
 
+  if (c->l2_persist && b->slab && (c->l2_window_base != b->slab || c->l2_window_bytes != b->slab_bytes)) {
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof(av));
+    const size_t win = std::min(b->slab_bytes, c->l2_window_max);
+    av.accessPolicyWindow.base_ptr = b->slab;
+    av.accessPolicyWindow.num_bytes = win;
+    av.accessPolicyWindow.hitRatio = win ? (float)std::min(1.0, (double)c->l2_persist_max / (double)win) : 0.f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) { cudaGetLastError(); c->l2_persist = 0; }
+    c->l2_window_base = b->slab;
+    c->l2_window_bytes = b->slab_bytes;
+  }
   const LaunchCfg l = cfg(c, b);
   const BeamView v = view(b);
   if (sc) { int e = 0; while (e < 32 && (1ull << e) < (unsigned long long)b->h.n_global) ++e; sc->bin_scale = (double)(1ull << (62 - e)); }
@@ -962,6 +1032,16 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     }
     if (!s.kick_follows) { extra++; continue; }
     int rc = HPS_OK;
+    if (c->fused && c->xr.mode != XR_NCCL && sc->fused_cap > 0) {
+      // the whole chain in one resident grid: every block with particles, and enough blocks for the field items
+      const unsigned want = std::max((((unsigned)b->n + 1) / 2 + 511) / 512, scheff_items(s.kp));
+      const unsigned grid = std::max(1u, std::min(want, sc->fused_cap));
+      prof_mark(c, HPS_PROF_MOMENTS);
+      cudaError_t e = launch_scheff(l, grid, v, b->st, sc->dev, sc->bins, sc->field, sc->field_part, sc->field_tickets, s.kp, ++c->mesh_seq);
+      if (e != cudaSuccess) return fail(c, HPS_ERR_CUDA, std::string("kick launch: ") + cudaGetErrorString(e));
+      c->launches++;
+      continue;
+    }
     const int merged = c->xr.mode != XR_NCCL;  // K2 rides inside K3 (grid barrier) unless its finaliser is a separate kernel
     if (!merged) {
       prof_mark(c, HPS_PROF_LLOSS);

@@ -82,6 +82,9 @@ struct ScDev {
   double ratio_r, ratio_z, ratio_q, ratio_g;
   unsigned long long abs_phi_max_bits;
   unsigned long long n_kicks, n_remesh, n_lloss_pass;
+  // SM-clock cycles block 0 of k_scheff spent in each phase, summed over the kicks (hps_scheff_phase_cycles):
+  // 0 moments sweep, 1 reduction + finalisers + barrier, 2 deposit + flush, 3 Green slice, 4 barrier, 5 field solve
+  unsigned long long phase_clk[8];
 };
 
 // static (host-known) parameters of one space-charge kick

@@ -46,7 +46,8 @@ __device__ void finalize_segment(int fin, const double* t, DevStats* st, u32 n_g
 // one op applied to the N register-resident particles of a thread.  The type dispatch and the shared-memory
 // reads of the op's parameters happen once per op, not once per particle, and the per-particle bodies sit
 // back to back so that their independent fp64 chains can overlap.
-// MATH: 0 = the reference's expression order, 1 = the fast maps (hps_kernels.cuh)
+// MATH: 0 = the reference's expression order with nvcc's `/` and sqrt, 1 = the fast maps, 2 = the reference's
+// expression order with the branch-free exact arithmetic of hps_math.cuh (same bits as 0)
 template <bool FULL, int N, int MATH>
 __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const u32 (&gidx)[N], const bool (&valid)[N],
                                          const Op& op, const OpC& opc, const KickCtx& kc, const double* cxy,
@@ -60,19 +61,19 @@ __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const 
   switch (op.type) {
     case OP_DRIFT:
 #pragma unroll
-      EACH_ALIVE { if (MATH) op_drift_f(pt[j], q, c, op.elem, inv_mass); else op_drift(pt[j], q, c, op.elem, mass); }
+      EACH_ALIVE { if (MATH == 1) op_drift_f(pt[j], q, c, op.elem, inv_mass); else if (MATH == 2) op_drift<MathNR>(pt[j], q, c, op.elem, mass, inv_mass); else op_drift<MathLib>(pt[j], q, c, op.elem, mass, inv_mass); }
       break;
     case OP_QUAD_HALF:
 #pragma unroll
-      EACH_ALIVE { if (MATH) op_quad_half_f(pt[j], q, c, op.elem, inv_mass); else op_quad_half(pt[j], q, c, op.elem, mass); }
+      EACH_ALIVE { if (MATH == 1) op_quad_half_f(pt[j], q, c, op.elem, inv_mass); else if (MATH == 2) op_quad_half<MathNR>(pt[j], q, c, op.elem, mass, inv_mass); else op_quad_half<MathLib>(pt[j], q, c, op.elem, mass, inv_mass); }
       break;
     case OP_GAP_FIRST:
 #pragma unroll
-      EACH_ALIVE { if (MATH) op_gap_first_f(pt[j], q, c, op.flag != 0, inv_mass); else op_gap_first(pt[j], q, c, op.flag != 0, mass); }
+      EACH_ALIVE { if (MATH == 1) op_gap_first_f(pt[j], q, c, op.flag != 0, inv_mass); else if (MATH == 2) op_gap_first<MathNR>(pt[j], q, c, op.flag != 0, mass, inv_mass); else op_gap_first<MathLib>(pt[j], q, c, op.flag != 0, mass, inv_mass); }
       break;
     case OP_GAP_SECOND:
 #pragma unroll
-      EACH_ALIVE { if (MATH) op_gap_second_f(pt[j], q, c, op.flag != 0, inv_mass); else op_gap_second(pt[j], q, c, op.flag != 0, mass); }
+      EACH_ALIVE { if (MATH == 1) op_gap_second_f(pt[j], q, c, op.flag != 0, inv_mass); else if (MATH == 2) op_gap_second<MathNR>(pt[j], q, c, op.flag != 0, mass, inv_mass); else op_gap_second<MathLib>(pt[j], q, c, op.flag != 0, mass, inv_mass); }
       break;
     // the rare, code-heavy maps (7 dipoles and 2 bunchers in the whole linac) live in the FULL variant only,
     // which keeps the hot variant's SASS inside the instruction cache
@@ -135,7 +136,7 @@ __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const 
 #pragma unroll
       // (np2_quarter is a power of two)
       EACH if (!(gidx[j] == 0 || (compat && (gidx[j] & (b.np2_quarter - 1u)) == 0u))) {
-        if (MATH) op_sc_kick_f(pt[j], ll[j], kc, field, inv_mass); else op_sc_kick(pt[j], ll[j], kc, field, mass);
+        if (MATH == 1) op_sc_kick_f(pt[j], ll[j], kc, field, inv_mass); else if (MATH == 2) op_sc_kick<MathNR>(pt[j], ll[j], kc, field, mass, inv_mass); else op_sc_kick<MathLib>(pt[j], ll[j], kc, field, mass, inv_mass);
       }
       break;
     case OP_FREQ_CHANGE:  // beam_kernel.cu:1531-1538: every particle, lost or not
@@ -280,21 +281,27 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
 }
 #define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*, const __grid_constant__ XrView
 typedef void (*SegKernel)(SEG_ARGS);
-// variant -> kernel.  0: 2 particles/thread, fast maps (default); 1 / 2: 1 particle/thread at 3 / 4 blocks per SM;
-// 10, 11: variants 0, 1 with the reference's expression order (MATH = 0); -1 / -2: the full op set (dipole, buncher)
+// variant -> kernel.  20 (default): 2 particles/thread, reference-order maps with exact branch-free arithmetic;
+// 0: 2 particles/thread, fast maps; 1 / 2: fast maps, 1 particle/thread at 3 / 4 blocks per SM;
+// 10, 11: variants 0, 1 with the reference's expression order and nvcc's operators (MATH = 0); 20, 21: the same
+// with the branch-free exact arithmetic (MATH = 2); -1 / -2 / -3: the full op set (dipole, buncher)
 static SegKernel seg_kernel(int variant) {
   switch (variant) {
     case 1: return k_segment<1, 3, false, 1>;
     case 2: return k_segment<1, 4, false, 1>;
     case 10: return k_segment<2, 2, false, 0>;
     case 11: return k_segment<1, 3, false, 0>;
+    case 20: return k_segment<2, 2, false, 2>;
+    case 21: return k_segment<1, 3, false, 2>;
     case -1: return k_segment<1, 3, true, 1>;
     case -2: return k_segment<1, 3, true, 0>;
-    default: return k_segment<2, 2, false, 1>;
+    case -3: return k_segment<1, 3, true, 2>;
+    case 0: return k_segment<2, 2, false, 1>;
+    default: return k_segment<2, 2, false, 2>;
   }
 }
-static int seg_full_variant(int variant) { return variant >= 10 ? -2 : -1; }
-static bool seg_pairs(int variant) { return !(variant == 1 || variant == 2 || variant == 11 || variant < 0); }
+static int seg_full_variant(int variant) { return variant >= 20 ? -3 : (variant >= 10 ? -2 : -1); }
+static bool seg_pairs(int variant) { return !(variant == 1 || variant == 2 || variant == 11 || variant == 21 || variant < 0); }
 
 // one thread per op record of the uploaded program (once per simulate() call)
 __global__ void k_prepare_ops(const Op* __restrict__ ops, OpC* opcs, int nops, double mass, double charge) {
@@ -449,13 +456,15 @@ __device__ void finalize_moments(const double* t, double ref, u32 n_global, DevS
   if (do_policy) scheff_policy(st, sc, kp, t[8]);
 }
 
-__global__ void __launch_bounds__(HPS_BLOCK)
-k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, int with_lloss, double* partials,
-          u32* ticket, const __grid_constant__ XrView xr) {
-  __shared__ double s_total[MOM_NS];
-  __shared__ double s_scratch[HPS_BLOCK];
-  pdl_launch_dependents();
-  pdl_wait();
+// loads of values another block may have written earlier in the SAME launch (L1 is not coherent)
+__device__ __forceinline__ double ldv(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ u32 ldv(const u32* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldv(const int* p) { return __ldcg(p); }
+
+// body of K3; every thread of the grid calls it.  s_total: MOM_NS doubles, s_scratch: blockDim.x doubles (shared).
+__device__ __forceinline__ void moments_phase(const BeamView& b, DevStats* st, ScDev* sc, double* bins, const KickParams& kp,
+                                              int do_policy, int with_lloss, double* partials, u32* ticket, double* s_total,
+                                              double* s_scratch, const XrView& xr) {
   // with_lloss: the longitudinal-loss pass (K2) runs in front of the moments inside this launch when K1
   // asked for it -- the common "nothing to mark" case then costs nothing instead of an empty kernel.  The
   // flag only changes in K1's finaliser, so every block sees the same value for the whole launch.
@@ -501,6 +510,16 @@ k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int 
     const u32 nb = kp.nr * kp.nz;
     for (u32 k = threadIdx.x; k < nb; k += blockDim.x) bins[k] = 0.0;
   }
+}
+
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, int with_lloss, double* partials,
+          u32* ticket, const __grid_constant__ XrView xr) {
+  __shared__ double s_total[MOM_NS];
+  __shared__ double s_scratch[HPS_BLOCK];
+  pdl_launch_dependents();
+  pdl_wait();
+  moments_phase(b, st, sc, bins, kp, do_policy, with_lloss, partials, ticket, s_total, s_scratch, xr);
 }
 
 // ================================================================================================
@@ -597,12 +616,9 @@ __device__ __forceinline__ u32 deposit_one(const DepCtx& d, u32 l, u32 ll, doubl
   return 1;
 }
 
-__global__ void __launch_bounds__(512, 2)
-k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, u32* ticket, const __grid_constant__ XrView xr) {
-  extern __shared__ u32 s_words[];  // [nb] low words, [nb] high words
-  pdl_launch_dependents();
-  pdl_wait();
-  if (!sc->remesh) return;
+// body of K4 up to the flush of the block-private mesh; s_words: 2 * nr * nz u32 of shared memory
+__device__ __forceinline__ void deposit_phase(const BeamView& b, DevStats* st, ScDev* sc, double* bins_raw, const KickParams& kp,
+                                              u32* s_words) {
   unsigned long long* bins = reinterpret_cast<unsigned long long*>(bins_raw);
   const u32 nb = kp.nr * kp.nz;
   u32* s_lo = s_words;
@@ -613,13 +629,13 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
     DepCtx d;
     d.nx = (int)kp.nr; d.nz = (int)kp.nz;
     d.scale = bin_scale(kp.n_global);
-    d.phimc = st->v[HPS_STAT_PHI_AVG_R]; d.xbar = st->v[HPS_STAT_X_AVG_GOOD]; d.ybar = st->v[HPS_STAT_Y_AVG_GOOD];
-    d.epsq = st->v[HPS_STAT_X_SIG_GOOD] / st->v[HPS_STAT_Y_SIG_GOOD];
-    d.ref = st->v[HPS_STAT_PHI_AVG_GOOD];
-    const double beta = sc->beta;
+    d.phimc = ldv(&st->v[HPS_STAT_PHI_AVG_R]); d.xbar = ldv(&st->v[HPS_STAT_X_AVG_GOOD]); d.ybar = ldv(&st->v[HPS_STAT_Y_AVG_GOOD]);
+    d.epsq = ldv(&st->v[HPS_STAT_X_SIG_GOOD]) / ldv(&st->v[HPS_STAT_Y_SIG_GOOD]);
+    d.ref = ldv(&st->v[HPS_STAT_PHI_AVG_GOOD]);
+    const double beta = ldv(&sc->beta);
     const double gm = rsqrt(1.0 - beta * beta);
-    d.dr = sc->dr;
-    d.dzg = sc->dz * gm;
+    d.dr = ldv(&sc->dr);
+    d.dzg = ldv(&sc->dz) * gm;
     const double wave_len = K_CLIGHT / kp.freq;
     d.hl = d.nz * 0.5 * d.dzg;
     d.c2 = beta * gm * wave_len / K_TWOPI;
@@ -654,9 +670,20 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
     if (cnt) atomicAdd(&sc->num_on_mesh, cnt);
     atomicMax(&sc->abs_phi_max_bits, (unsigned long long)__double_as_longlong(pmax));
   }
+}
+
+__global__ void __launch_bounds__(512, 2)
+k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, u32* ticket, const __grid_constant__ XrView xr) {
+  extern __shared__ u32 s_words[];  // [nb] low words, [nb] high words
+  pdl_launch_dependents();
+  pdl_wait();
+  if (!sc->remesh) return;
+  deposit_phase(b, st, sc, bins_raw, kp, s_words);
   if (xr.mode != XR_NCCL) return;
   // XR_NCCL only: the rank's last block appends the on-mesh count and max |phi| to the mesh, which the host
   // then all-gathers.  (XR_P2P: k_field itself pushes the mesh to the peers, spread over all its blocks.)
+  unsigned long long* bins = reinterpret_cast<unsigned long long*>(bins_raw);
+  const u32 nb = kp.nr * kp.nz;
   __shared__ u32 s_last;
   __threadfence();
   __syncthreads();
@@ -683,97 +710,102 @@ __device__ __forceinline__ void ellip_ke(double g, double& ee, double& ek) {
   ek = 1.38629436 - 0.5 * h + g * (0.1119697 - 0.1213486 * h + g * (0.07253230 - 0.02887472 * h));
 }
 
-// Work split: block (rp, ch) owns receiving radius rp and RS consecutive source rings (RS = blockDim.x / T,
-// T = power of two >= nz).  Thread (kk, t) computes ONE entry of the [RS][nz] Green slice (ring kk, axial
-// offset t) into shared memory, then the partial field of ring kk at node (zp = t, rp) with two independent
-// accumulation chains; the RS ring partials are folded in ring order, the chunk partial is stored, and the
-// last block of each rp (ticket) adds the chunk partials in a fixed order -- deterministic, and
-// (nr+1) x ceil(nr/RS) blocks of RS*T threads fill the GPU.
-__global__ void __launch_bounds__(1024)
-k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, double2* part, u32* tickets,
-        KickParams kp, int T, u32 mesh_seq, const __grid_constant__ XrView xr) {
-  extern __shared__ double s_mem[];
-  pdl_launch_dependents();
-  pdl_wait();
-  if (!sc->remesh) return;
+struct FieldSmem {  // carve-up of the dynamic shared memory of the field solve (RS source rings per block)
+  double* s_b;     // [RS][nz] charge of the block's source rings
+  double2* s_g;    // [RS][nz] Green's function slice
+  double2* s_p;    // [RS][nz] ring partials at nodes zp < nz
+  double2* s_red;  // [blockDim.x]
+  __device__ FieldSmem(double* mem, u32 RS, u32 nz) {
+    s_b = mem;
+    s_g = reinterpret_cast<double2*>(mem + RS * nz);
+    s_p = s_g + RS * nz;
+    s_red = s_p + RS * nz;
+  }
+};
+
+// Sharded beam, XR_P2P: every block stores its share of the rank-local mesh (+ on-mesh count and max |phi|)
+// into all peers' boxes as LL words (sequence number = the host's launch counter of the field solve,
+// identical on all ranks).
+__device__ __forceinline__ void field_push_mesh(const ScDev* sc, const double* bins, const KickParams& kp, u32 mesh_seq, u32 blk,
+                                                u32 nblk, const XrView& xr) {
+  const u32 nb = kp.nr * kp.nz;
+  const unsigned long long* lb = reinterpret_cast<const unsigned long long*>(bins);
+  const int par = (int)(mesh_seq & 1u);
+  for (u32 k = blk * blockDim.x + threadIdx.x; k < nb + 2; k += nblk * blockDim.x) {
+    const unsigned long long v = k < nb ? __ldcg(&lb[k]) : (k == nb ? (unsigned long long)ldv(&sc->num_on_mesh) : __ldcg(&sc->abs_phi_max_bits));
+    for (int p = 0; p < xr.nranks; ++p) {
+      unsigned long long* w = &xr.peer[p]->bins[par][xr.rank][2 * k];
+      ll_send(w, (u32)v, mesh_seq);
+      ll_send(w + 1, (u32)(v >> 32), mesh_seq);
+    }
+  }
+}
+
+// Green's function entry (ring rs0+kk -> radius irp, axial offset (t + 1/2) cells) into s_g; does not depend on
+// the charge mesh (space_charge_kernel.cu:39-100)
+__device__ __forceinline__ void field_green(const ScDev* sc, const KickParams& kp, u32 irp, u32 rs0, u32 kk, u32 t, bool live,
+                                            const FieldSmem& m) {
+  if (!live) return;
+  const u32 nz = kp.nz;
+  const double beta = ldv(&sc->beta);
+  const double gm = rsqrt(1.0 - beta * beta);
+  const double dr = ldv(&sc->dr);
+  const double dzg = ldv(&sc->dz) * gm;
+  const double wave_len = K_CLIGHT / kp.freq;
+  const double pl = beta * gm * wave_len;
+  const double c1 = 5721.67 * (kp.current_frac / kp.mass) / (kp.freq * 1e6 * (double)kp.n_global);
+  const double rp = irp * dr;
+  const int adj = (int)ldv(&sc->adj_bunch);
+  const u32 jz = t, k = rs0 + kk;
+  const double rs = sqrt(0.5 * (k * k + (k + 1) * (k + 1))) * dr;
+  const double zs = 0.5 * dzg, zp = (jz + 1) * dzg;
+  const double d = zp - zs;
+  double d2 = d * d;
+  const double c = (rp - rs) * (rp - rs), bq = (rp + rs) * (rp + rs);
+  const double rsrp = rs * rp;
+  double a = 4.0 * rsrp / (bq + d2);
+  double ee, ek;
+  ellip_ke(1.0 - a, ee, ek);
+  double er1 = 0.0;
+  a = sqrt(bq + d2);
+  const double rs2mrp2 = rs * rs - rp * rp;
+  if (rp != 0.0) er1 = (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
+  double ez1 = d * ee / (a * (c + d2));
+  for (int i = 1; i <= adj; ++i) {
+    double xi = i;
+    for (int j = 0; j < 2; ++j) {
+      const double d1 = d - xi * pl;
+      d2 = d1 * d1;
+      a = 4.0 * rsrp / (bq + d2);
+      ellip_ke(1.0 - a, ee, ek);
+      a = sqrt(bq + d2);
+      if (rp != 0.0) er1 += (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
+      ez1 += d1 * ee / (a * (c + d2));
+      xi = -xi;
+    }
+  }
+  m.s_g[kk * nz + t] = make_double2(c1 * er1, c1 * ez1);
+}
+
+// Gathers the charge of the block's source rings (folding the R rank-local meshes of a sharded beam), then the
+// field of those rings at the nodes of radius irp; the last block of each radius folds the chunk partials.
+// Call with the Green slice of (irp, ch) already in m.s_g (a __syncthreads follows inside).
+__device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, double2* part,
+                                            u32* tickets, const KickParams& kp, u32 irp, u32 ch, u32 nch, u32 RS, u32 kk, u32 t,
+                                            bool live, u32 mesh_seq, const FieldSmem& m, const XrView& xr) {
   const u32 nr = kp.nr, nz = kp.nz;
-  const u32 RS = blockDim.x / T;
-  const u32 irp = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
   const u32 rs0 = ch * RS;
   const u32 nrs = min(RS, nr - rs0);
-  const u32 kk = threadIdx.x / T, t = threadIdx.x % T;
-  const bool live = kk < nrs && t < nz;
-  double* s_b = s_mem;                                           // [RS][nz]
-  double2* s_g = reinterpret_cast<double2*>(s_mem + RS * nz);    // [RS][nz]
-  double2* s_p = s_g + RS * nz;                                  // [RS][nz] ring partials at nodes zp < nz
-  double2* s_red = s_p + RS * nz;                                // [blockDim.x]
   const double inv_scale = 1.0 / bin_scale(kp.n_global);          // fixed-point mesh, see k_deposit
-  // Sharded beam, XR_P2P: every block first stores its share of the rank-local mesh (+ on-mesh count and
-  // max |phi|) into all peers' boxes as LL words (sequence number = the host's launch counter of this
-  // kernel, identical on all ranks).  The Green's function slice does not depend on the charge mesh: it
-  // is computed next, so the peers' meshes travel over NVLink meanwhile; then the R meshes are polled
-  // and folded (integer sums: exact, order-independent).
-  if (xr.mode == XR_P2P) {
-    const u32 nb = nr * nz;
-    const unsigned long long* lb = reinterpret_cast<const unsigned long long*>(bins);
-    const u32 nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
-    const int par = (int)(mesh_seq & 1u);
-    for (u32 k = blk * blockDim.x + threadIdx.x; k < nb + 2; k += nblk * blockDim.x) {
-      const unsigned long long v = k < nb ? lb[k] : (k == nb ? (unsigned long long)sc->num_on_mesh : sc->abs_phi_max_bits);
-      for (int p = 0; p < xr.nranks; ++p) {
-        unsigned long long* w = &xr.peer[p]->bins[par][xr.rank][2 * k];
-        ll_send(w, (u32)v, mesh_seq);
-        ll_send(w + 1, (u32)(v >> 32), mesh_seq);
-      }
-    }
-  }
-  if (live) {  // Green's function entry (ring rs0+kk -> radius rp, axial offset (t + 1/2) cells)
-    const double beta = sc->beta;
-    const double gm = rsqrt(1.0 - beta * beta);
-    const double dr = sc->dr;
-    const double dzg = sc->dz * gm;
-    const double wave_len = K_CLIGHT / kp.freq;
-    const double pl = beta * gm * wave_len;
-    const double c1 = 5721.67 * (kp.current_frac / kp.mass) / (kp.freq * 1e6 * (double)kp.n_global);
-    const double rp = irp * dr;
-    const int adj = (int)sc->adj_bunch;
-    const u32 jz = t, k = rs0 + kk;
-    const double rs = sqrt(0.5 * (k * k + (k + 1) * (k + 1))) * dr;
-    const double zs = 0.5 * dzg, zp = (jz + 1) * dzg;
-    const double d = zp - zs;
-    double d2 = d * d;
-    const double c = (rp - rs) * (rp - rs), bq = (rp + rs) * (rp + rs);
-    const double rsrp = rs * rp;
-    double a = 4.0 * rsrp / (bq + d2);
-    double ee, ek;
-    ellip_ke(1.0 - a, ee, ek);
-    double er1 = 0.0;
-    a = sqrt(bq + d2);
-    const double rs2mrp2 = rs * rs - rp * rp;
-    if (rp != 0.0) er1 = (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
-    double ez1 = d * ee / (a * (c + d2));
-    for (int i = 1; i <= adj; ++i) {
-      double xi = i;
-      for (int j = 0; j < 2; ++j) {
-        const double d1 = d - xi * pl;
-        d2 = d1 * d1;
-        a = 4.0 * rsrp / (bq + d2);
-        ellip_ke(1.0 - a, ee, ek);
-        a = sqrt(bq + d2);
-        if (rp != 0.0) er1 += (ek - (rs2mrp2 + d2) * ee / (c + d2)) / (2.0 * rp * a);
-        ez1 += d1 * ee / (a * (c + d2));
-        xi = -xi;
-      }
-    }
-    s_g[kk * nz + t] = make_double2(c1 * er1, c1 * ez1);
-  }
+  double* s_b = m.s_b;
+  double2 *s_g = m.s_g, *s_p = m.s_p, *s_red = m.s_red;
   if (xr.nranks <= 1) {
     if (irp == 0 && ch == 0 && threadIdx.x == 0) {
-      sc->num_on_mesh_all = sc->num_on_mesh;
-      if (sc->adj_bunch != 0) st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)sc->abs_phi_max_bits);
+      sc->num_on_mesh_all = ldv(&sc->num_on_mesh);
+      if (ldv(&sc->adj_bunch) != 0) st->v[HPS_STAT_ABS_PHI_MAX] = __longlong_as_double((long long)__ldcg(&sc->abs_phi_max_bits));
     }
     const long long* ibins = reinterpret_cast<const long long*>(bins);  // fixed point, see k_deposit
-    if (live) s_b[kk * nz + t] = (double)ibins[t * nr + rs0 + kk] * inv_scale;
+    if (live) s_b[kk * nz + t] = (double)__ldcg(&ibins[t * nr + rs0 + kk]) * inv_scale;
   } else {
     // sharded beam: fold the R rank-local meshes (integer sums: exact, order-independent)
     const u32 nb = nr * nz;
@@ -802,7 +834,7 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
         pm = fmax(pm, __longlong_as_double((long long)value(r, nb + 1)));
       }
       sc->num_on_mesh_all = cnt;
-      if (sc->adj_bunch != 0) st->v[HPS_STAT_ABS_PHI_MAX] = pm;
+      if (ldv(&sc->adj_bunch) != 0) st->v[HPS_STAT_ABS_PHI_MAX] = pm;
     }
   }
   __syncthreads();
@@ -867,6 +899,97 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
     field[node * (nr + 1) + irp] = make_double2(tx, tz);
   }
   if (threadIdx.x == 0) tickets[irp] = 0u;
+}
+
+// Work split: block (rp, ch) owns receiving radius rp and RS consecutive source rings (RS = blockDim.x / T,
+// T = power of two >= nz).  Thread (kk, t) computes ONE entry of the [RS][nz] Green slice (ring kk, axial
+// offset t) into shared memory, then the partial field of ring kk at node (zp = t, rp) with two independent
+// accumulation chains; the RS ring partials are folded in ring order, the chunk partial is stored, and the
+// last block of each rp (ticket) adds the chunk partials in a fixed order -- deterministic, and
+// (nr+1) x ceil(nr/RS) blocks of RS*T threads fill the GPU.
+__global__ void __launch_bounds__(1024)
+k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field, double2* part, u32* tickets,
+        KickParams kp, int T, u32 mesh_seq, const __grid_constant__ XrView xr) {
+  extern __shared__ double s_mem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  if (!sc->remesh) return;
+  const u32 RS = blockDim.x / T;
+  const u32 irp = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
+  const u32 rs0 = ch * RS;
+  const u32 nrs = min(RS, kp.nr - rs0);
+  const u32 kk = threadIdx.x / T, t = threadIdx.x % T;
+  const bool live = kk < nrs && t < kp.nz;
+  const FieldSmem m(s_mem, RS, kp.nz);
+  // XR_P2P: the mesh is pushed first; the Green's function slice does not depend on the charge mesh and is
+  // computed next, so the peers' meshes travel over NVLink meanwhile; then the R meshes are polled and folded.
+  if (xr.mode == XR_P2P) field_push_mesh(sc, bins, kp, mesh_seq, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, xr);
+  field_green(sc, kp, irp, rs0, kk, t, live, m);
+  field_solve(st, sc, bins, field, part, tickets, kp, irp, ch, nch, RS, kk, t, live, mesh_seq, m, xr);
+}
+
+// ================================================================================================
+// K3 + K4 + K5 in ONE launch: the whole space-charge chain between two segment sweeps
+// ================================================================================================
+// Three short, latency-bound kernels (21 + 27 + 24 us per kick on C2, profiles/r1_launches_summary.txt) become
+// one resident grid with two grid barriers:
+//   moments (+ lloss pass) -> last block: finalisers + Scheff::Start policy -> BARRIER ->
+//   [remesh kicks only] deposit into the block-private mesh, flush -> Green slice of the block's first
+//   field item (independent of the mesh: it hides the flush and the barrier) -> BARRIER -> field solve.
+// A sharded beam (XR_P2P) needs the complete rank-local mesh before it can be pushed to the peers, so there
+// the barrier sits before the push and the Green slice hides the NVLink transfer instead.
+// All blocks are co-resident (grid <= occupancy x SMs, hps_capi.cpp).  blockDim.x = 512 = RS * T.
+__global__ void __launch_bounds__(512, 2)
+k_scheff(BeamView b, DevStats* st, ScDev* sc, double* bins, double2* field, double2* part, u32* tickets, KickParams kp, int T,
+         u32 mesh_seq, double* partials, u32* ticket, const __grid_constant__ XrView xr) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];  // deposit: 2*nr*nz u32; field: FieldSmem (whichever is larger)
+  __shared__ double s_total[MOM_NS];
+  __shared__ double s_scratch[512];
+  pdl_launch_dependents();
+  pdl_wait();
+  const bool clk = blockIdx.x == 0 && threadIdx.x == 0;
+  long long t0 = clock64(), t1;
+#define PHASE(k) if (clk) { t1 = clock64(); sc->phase_clk[k] += (unsigned long long)(t1 - t0); t0 = t1; }
+  moments_phase(b, st, sc, bins, kp, 1, 1, partials, ticket, s_total, s_scratch, xr);
+  PHASE(0)
+  grid_barrier(ticket + 2);
+  PHASE(1)
+  if (ldv(&sc->remesh) == 0) return;
+
+  deposit_phase(b, st, sc, bins, kp, reinterpret_cast<u32*>(s_dyn));
+  __syncthreads();  // the block-private mesh has been flushed: the shared memory is free again
+  PHASE(2)
+
+  const u32 RS = min((u32)HPS_FIELD_RS, blockDim.x / (u32)T);
+  const u32 nch = (kp.nr + RS - 1) / RS;
+  const u32 nitems = (kp.nr + 1) * nch;
+  const u32 kk = threadIdx.x / T, t = threadIdx.x % T;
+  const FieldSmem m(reinterpret_cast<double*>(s_dyn), RS, kp.nz);
+  u32 item = blockIdx.x;
+  auto live_of = [&](u32 it) { const u32 rs0 = (it / (kp.nr + 1)) * RS; return kk < RS && kk < min(RS, kp.nr - rs0) && t < kp.nz; };
+  if (xr.mode == XR_P2P) {
+    grid_barrier(ticket + 2);
+    field_push_mesh(sc, bins, kp, mesh_seq, blockIdx.x, gridDim.x, xr);
+    PHASE(4)
+    if (item < nitems) field_green(sc, kp, item % (kp.nr + 1), (item / (kp.nr + 1)) * RS, kk, t, live_of(item), m);
+    PHASE(3)
+  } else {
+    if (item < nitems) field_green(sc, kp, item % (kp.nr + 1), (item / (kp.nr + 1)) * RS, kk, t, live_of(item), m);
+    PHASE(3)
+    grid_barrier(ticket + 2);
+    PHASE(4)
+  }
+  for (bool first = true; item < nitems; item += gridDim.x, first = false) {
+    const u32 irp = item % (kp.nr + 1), ch = item / (kp.nr + 1);
+    const bool live = live_of(item);
+    if (!first) {
+      __syncthreads();  // the previous item's shared memory has been consumed
+      field_green(sc, kp, irp, ch * RS, kk, t, live, m);
+    }
+    field_solve(st, sc, bins, field, part, tickets, kp, irp, ch, nch, RS, kk, t, live, mesh_seq, m, xr);
+  }
+  PHASE(5)
+#undef PHASE
 }
 
 // ================================================================================================
@@ -1041,7 +1164,7 @@ __global__ void k_rel_phi_out(BeamView b, const DevStats* st, double* out) {
 // ================================================================================================
 // launch wrappers
 // ================================================================================================
-static int g_field_smem_set = 0, g_deposit_smem_set = 0;
+static int g_field_smem_set = 0, g_deposit_smem_set = 0, g_scheff_smem_set = 0;
 
 // Launch with programmatic stream serialization (see pdl_wait in hps_kernels.cuh) when c.pdl is set.
 template <typename... KArgs, typename... Args>
@@ -1120,6 +1243,33 @@ cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const doub
   }
   launch_chain(c, k_field, dim3(kp.nr + 1, field_chunks(kp)), dim3(T * field_rs(kp)), smem, st, sc, bins, field, part, tickets, kp, T, mesh_seq, c.xr);
   return cudaSuccess;
+}
+// ---- fused chain (k_scheff): 512 threads = RS * T per block
+static unsigned scheff_rs(const KickParams& kp) {
+  const int t = field_threads(kp);
+  return (t && t <= 512) ? std::max(1, std::min(HPS_FIELD_RS, 512 / t)) : 0;
+}
+size_t scheff_smem(const KickParams& kp) {
+  const size_t rs = scheff_rs(kp);
+  const size_t fld = rs * kp.nz * (sizeof(double) + 2 * sizeof(double2)) + 512 * sizeof(double2);
+  return std::max(fld, deposit_smem(kp));
+}
+bool scheff_supported(const KickParams& kp) { return scheff_rs(kp) != 0 && scheff_smem(kp) <= 200 * 1024; }
+unsigned scheff_items(const KickParams& kp) { const unsigned rs = scheff_rs(kp); return rs ? (kp.nr + 1) * ((kp.nr + rs - 1) / rs) : 0; }
+int scheff_occupancy(const KickParams& kp) {
+  const size_t smem = scheff_smem(kp);
+  if (smem > 48 * 1024 && !g_scheff_smem_set) {
+    if (cudaFuncSetAttribute(k_scheff, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 0;
+    g_scheff_smem_set = 1;
+  }
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scheff, 512, smem);
+  return nb;
+}
+cudaError_t launch_scheff(const LaunchCfg& c, unsigned grid, const BeamView& b, DevStats* st, ScDev* sc, double* bins, double2* field,
+                          double2* part, u32* tickets, const KickParams& kp, u32 mesh_seq) {
+  return launch_chain(c, k_scheff, dim3(grid), dim3(512), scheff_smem(kp), b, st, sc, bins, field, part, tickets, kp, field_threads(kp),
+                      mesh_seq, c.partials, c.ticket, c.xr);
 }
 void launch_stat(const LaunchCfg& c, const BeamView& b, DevStats* st, const StatReq& rq) {
   k_stat<<<c.grid_single, HPS_BLOCK, 0, c.stream>>>(b, st, rq, c.partials, c.ticket, c.xr);

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <float.h>
 #include "hps_internal.h"
+#include "hps_math.cuh"
 
 namespace hps {
 
@@ -241,9 +242,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ------------------------------------------------------------------------------------------------
 // element maps (one particle)
 // ------------------------------------------------------------------------------------------------
-HPS_HD double beta_of(double w, double mass) {
-  double g1 = w / mass;
-  return sqrt(g1 * (g1 + 2.0)) / (g1 + 1.0);
+// The reference-order maps are templates over the arithmetic back end M (hps_math.cuh): MathLib = nvcc's own
+// `/` and sqrt (with their slow-path branches), MathNR = the same IEEE results from branch-free sequences, with
+// divisions by per-op constants done as one multiplication + exact-remainder correction.  Same bits either way.
+template <class M>
+HPS_HD double beta_of(double w, double mass, double inv_mass) {
+  double g1 = M::udiv_(w, mass, inv_mass);
+  return M::div(M::sqrt_(g1 * (g1 + 2.0)), g1 + 1.0);
 }
 
 // ---- hoisted constants -------------------------------------------------------------------------
@@ -387,7 +392,8 @@ __host__ __device__ inline void prepare_op(const Op& op, OpC& o, double mass, do
 }
 
 // simulation_kernel.cu:87-118 -- a lost particle keeps its pre-drift x,y (H11)
-HPS_HD void op_drift(Pt& p, const double* q, const double* c, u32 elem, double mass) {
+template <class M>
+HPS_HD void op_drift(Pt& p, const double* q, const double* c, u32 elem, double mass, double inv_mass) {
   const double hl = q[0], aper2 = c[D_APER2], wavelen = q[2];
   double x = p.x, y = p.y;
   x += p.xp * hl;
@@ -395,12 +401,13 @@ HPS_HD void op_drift(Pt& p, const double* q, const double* c, u32 elem, double m
   if (aper2 != 0.0 && x * x + y * y > aper2) p.loss = elem;
   else {
     p.x = x; p.y = y;
-    p.phi += c[D_TWOPI_HL] / (wavelen * beta_of(p.w, mass));
+    p.phi += M::div(c[D_TWOPI_HL], wavelen * beta_of<M>(p.w, mass, inv_mass));
   }
 }
 
 // simulation_kernel.cu:142-218 -- two quarter-length thick-lens maps, then the aperture test
-HPS_HD void op_quad_half(Pt& p, const double* q, const double* c, u32 elem, double mass) {
+template <class M>
+HPS_HD void op_quad_half(Pt& p, const double* q, const double* c, u32 elem, double mass, double inv_mass) {
   const double length = q[0], wavelen = q[3];
   const double aper2 = c[Q_APER2], qg = c[Q_QG];
   double tx = p.x, ty = p.y;  // what the aperture test sees
@@ -409,16 +416,18 @@ HPS_HD void op_quad_half(Pt& p, const double* q, const double* c, u32 elem, doub
     p.x = tx + p.xp * length * 0.5;
     p.y = ty + p.yp * length * 0.5;
   } else {
-    double gamma1 = p.w / mass;
-    double bg = sqrt(gamma1 * (gamma1 + 2.0) * (1.0 + p.xp * p.xp + p.yp * p.yp));
-    double k = sqrt(c[Q_ABSQG] / (bg * mass) * K_CLIGHT);
-    double inv_k = 1.0 / k;
+    double gamma1 = M::udiv_(p.w, mass, inv_mass);
+    double bg = M::sqrt_(gamma1 * (gamma1 + 2.0) * (1.0 + p.xp * p.xp + p.yp * p.yp));
+    double k = M::sqrt_(M::div(c[Q_ABSQG], bg * mass) * K_CLIGHT);
+    double inv_k = M::rcp(k);
     double kds = c[Q_LEN4] * k;
     double s, cs, sh = sinh(kds), ch = cosh(kds);
     sincos(kds, &s, &cs);
     double sovk = s * inv_k, shovk = sh * inv_k, sk = s * k, shk = sh * k;
     double x = p.x, xp = p.xp, y = p.y, yp = p.yp, t;
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int rep = 0; rep < 2; ++rep) {
       if (qg > 0.0) {
         t = cs * x + sovk * xp; xp = -sk * x + cs * xp; x = t;
@@ -432,54 +441,58 @@ HPS_HD void op_quad_half(Pt& p, const double* q, const double* c, u32 elem, doub
     tx = x; ty = y;
   }
   if (aper2 != 0 && tx * tx + ty * ty > aper2) p.loss = elem;
-  else p.phi += c[Q_TWOPI_LEN_HALF] / (wavelen * beta_of(p.w, mass));
+  else p.phi += M::div(c[Q_TWOPI_LEN_HALF], wavelen * beta_of<M>(p.w, mass, inv_mass));
 }
 
 // simulation_kernel.cu:226-288
-HPS_HD void op_gap_first(Pt& p, const double* q, const double* c, bool ccl, double mass) {
+template <class M>
+HPS_HD void op_gap_first(Pt& p, const double* q, const double* c, bool ccl, double mass, double inv_mass) {
   const double dd1 = c[GC_DD];
   const double phi = p.phi, w = p.w;
   p.x = p.x + dd1 * p.xp;
   p.y = p.y + dd1 * p.yp;
   const double wave_len = c[GC_WAVE_LEN];
   if (q[G_AMP] == 0.0) {
-    p.phi += c[GC_TWOPI_DD] / (wave_len * beta_of(w, mass));
+    p.phi += M::div(c[GC_TWOPI_DD], wave_len * beta_of<M>(w, mass, inv_mass));
   } else {
     const double beta_in = c[GC_BETA_IN];
-    const double gam = w / mass;
-    const double beta = sqrt((gam + 2.0) * gam) / (gam + 1.0);
+    const double gam = M::udiv_(w, mass, inv_mass);
+    const double beta = M::div(M::sqrt_((gam + 2.0) * gam), gam + 1.0);
     if (!ccl) {
       const double d_cell_len = c[GC_D_CELL_LEN];
-      const double dphi_qlen1 = c[GC_TWOPI_HALF_QLEN] / (beta * wave_len);
+      const double den = beta * wave_len, rden = M::rcp(den);  // two quotients share this denominator
+      const double dphi_qlen1 = M::udiv_(c[GC_TWOPI_HALF_QLEN], den, rden);
       double dphi_clen = 0.0;
-      if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = c[GC_PI_DCL] / (beta * wave_len);
-      p.phi = phi + (1.0 - (beta - beta_in) / beta) * c[GC_PI_CLBL_DPS] + dphi_clen - dphi_qlen1;
+      if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = M::udiv_(c[GC_PI_DCL], den, rden);
+      p.phi = phi + (1.0 - M::div(beta - beta_in, beta)) * c[GC_PI_CLBL_DPS] + dphi_clen - dphi_qlen1;
     } else {
-      p.phi = phi + (1.0 - (beta - beta_in) * c[GC_BETAG_CCL] / (beta * beta_in)) * c[GC_PI_CLBL_DPS];
+      p.phi = phi + (1.0 - M::div((beta - beta_in) * c[GC_BETAG_CCL], beta * beta_in)) * c[GC_PI_CLBL_DPS];
     }
   }
 }
 
 // simulation_kernel.cu:16-73 (polynomial modified Bessel functions)
+template <class M>
 HPS_HD double bessi0c(double rx) {
   double ans, y, ax = fabs(rx);
   if (ax < 3.75) {
-    y = rx / 3.75; y = y * y;
+    y = M::udiv_(rx, 3.75, 1.0 / 3.75); y = y * y;
     ans = 1.0 + y * (3.5156229 + y * (3.0899424 + y * (1.2067492 + y * (0.2659732 + y * (0.360768e-1 + y * 0.45813e-2)))));
   } else {
-    y = 3.75 / ax;
+    y = M::div(3.75, ax);
     ans = (exp(ax) * rsqrt(ax)) * (0.39894228 + y * (0.1328592e-1 + y * (0.225319e-2 + y * (-0.157565e-2 + y * (0.916281e-2 +
           y * (-0.2057706e-1 + y * (0.2635537e-1 + y * (-0.1647633e-1 + y * 0.392377e-2))))))));
   }
   return ans;
 }
+template <class M>
 HPS_HD double bessi1c(double rx) {
   double y, ans, ax = fabs(rx);
   if (ax < 3.75) {
-    y = rx / 3.75; y = y * y;
+    y = M::udiv_(rx, 3.75, 1.0 / 3.75); y = y * y;
     ans = ax * (0.5 + y * (0.87890594 + y * (0.51498869 + y * (0.15084934 + y * (0.2658733e-1 + y * (0.301532e-2 + y * 0.32411e-3))))));
   } else {
-    y = 3.75 / ax;
+    y = M::div(3.75, ax);
     ans = 0.2282967e-1 + y * (-0.2895312e-1 + y * (0.1787654e-1 - y * 0.420059e-2));
     ans = 0.39894228 + y * (-0.3988024e-1 + y * (-0.362018e-2 + y * (0.163801e-2 + y * (-0.1031555e-1 + y * ans))));
     ans = ans * (exp(ax) * rsqrt(ax));
@@ -488,7 +501,8 @@ HPS_HD double bessi1c(double rx) {
 }
 
 // simulation_kernel.cu:290-497
-HPS_HD void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, double mass) {
+template <class M>
+HPS_HD void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, double mass, double inv_mass_rn) {
   const double dd2 = c[GC_DD];
   double x = p.x, y = p.y, xp = p.xp, yp = p.yp;
   const double inv_mass = c[GC_INV_MASS];
@@ -496,8 +510,8 @@ HPS_HD void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, dou
   double w = p.w;
   const double beta_in = c[GC_BETA_IN];
   double gam = w * inv_mass;
-  const double bg1 = sqrt(gam * (gam + 2.0));
-  double beta = bg1 / (gam + 1.0);
+  const double bg1 = M::sqrt_(gam * (gam + 2.0));
+  double beta = M::div(bg1, gam + 1.0);
   // transit-time factors from the 5th-order fits (GetTransitTimeFactors)
   double t_fac, tp_fac, sp_fac;
   {
@@ -505,19 +519,19 @@ HPS_HD void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, dou
     if (beta > 1.1 * q[G_FBC]) bb = q[G_FBC];
     else if (beta < q[G_FBMIN]) bb = q[G_FBMIN];
     t_fac = q[G_T0] + bb * (q[G_T1] + bb * (q[G_T2] + bb * (q[G_T3] + bb * (q[G_T4] + bb * q[G_T5]))));
-    double coef = bb * bb / c[GC_TTF_DEN];
+    double coef = M::udiv_(bb * bb, c[GC_TTF_DEN], c[GF_INV_TTF_DEN]);
     tp_fac = coef * (q[G_T1] + bb * (2 * q[G_T2] + bb * (3 * q[G_T3] + bb * (4 * q[G_T4] + 5 * bb * q[G_T5]))));
     sp_fac = -coef * (q[G_S1] + bb * (2 * q[G_S2] + bb * (3 * q[G_S3] + bb * (4 * q[G_S4] + 5 * bb * q[G_S5]))));
   }
   if (q[G_AMP] == 0.0 || (ccl && beta < q[G_FBMIN])) {
     p.x = x + dd2 * xp;
     p.y = y + dd2 * yp;
-    p.phi += c[GC_TWOPI_DD] / (q[G_WAVELEN] * beta_of(w, mass));
+    p.phi += M::div(c[GC_TWOPI_DD], q[G_WAVELEN] * beta_of<M>(w, mass, inv_mass_rn));
     return;
   }
   const double wave_len = c[GC_WAVE_LEN];
   const double betag_ccl = c[GC_BETAG_CCL];
-  const double gmg = c[GC_GMG];
+  const double gmg = c[GC_GMG], rgmg = c[GF_INV_GMG];
   const double inv_gmg2 = c[GC_INV_GMG2];
   const double efl = c[GC_EFL];
   const double concomm = c[GC_CONCOMM];
@@ -526,14 +540,14 @@ HPS_HD void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, dou
   const double inv_gmgcl = c[GC_INV_GMGCL], inv_fkis = c[GC_INV_FKIS];
   const double con5nex = concomm * (t_fac * inv_fkis - c[GC_X5] * tp_fac * inv_gmg2);
   double tw;
-  if (ccl) tw = t_fac - K_TWOPI * tp_fac * (beta_in / beta - 1.0) * betag_ccl / beta_in;
+  if (ccl) tw = t_fac - M::udiv_(K_TWOPI * tp_fac * (M::div(beta_in, beta) - 1.0) * betag_ccl, beta_in, c[GF_IBETA_IN]);
   else tw = t_fac;
   const double con5nex1 = c[GC_CONCOMM1] * t_fac;
   const double con5nex2 = -con2nex * t_fac * inv_fkis;
   const double fkr = c[GC_FKR];
   const double sinps = c[GC_SINPS], cosps = c[GC_COSPS];
   double phi1, sinp1, cosp1;
-  if (ccl) phi1 = phi + q[G_PHSHIFT] - c[GC_TWOPI_DG] / (beta * wave_len) + c[GC_PH_CONST];
+  if (ccl) phi1 = phi + q[G_PHSHIFT] - M::div(c[GC_TWOPI_DG], beta * wave_len) + c[GC_PH_CONST];
   else phi1 = phi + q[G_PHSHIFT];
   sincos(phi1, &sinp1, &cosp1);
   const double prome1 = -con1 * (tp_fac * (sinp1 - sinps) + sp_fac * (cosp1 - cosps));
@@ -541,40 +555,42 @@ HPS_HD void op_gap_second(Pt& p, const double* q, const double* c, bool ccl, dou
 
   const double rs_p = x * x + y * y;
   const double rrp = x * xp + y * yp;
-  const double ris = sqrt(rs_p);
+  const double ris = M::sqrt_(rs_p);
+  const double rris = M::rcp(ris);  // b1c / ris and rrp / ris share it; unused (and NaN) when ris == 0
   const double fkrris = fkr * ris;
-  const double b0c = bessi0c(fkrris);
-  const double b1c = bessi1c(fkrris);
-  const double b1p = (fkrris != 0.0) ? b0c - b1c / fkrris : 0.5;
+  const double b0c = bessi0c<M>(fkrris);
+  const double b1c = bessi1c<M>(fkrris);
+  const double b1p = (fkrris != 0.0) ? b0c - M::div(b1c, fkrris) : 0.5;
   double bes1covr, rpris = 0.0;
-  if (ris != 0.0) bes1covr = b1c / ris; else bes1covr = fkr * 0.5;
-  const double delte = c[GC_AQ_EFL] * (tw * b0c * cosp1 + ((tw - K_TWOPI * tp_fac) / gmg * bes1covr + tw / gmg * fkr * b1p -
+  if (ris != 0.0) bes1covr = M::udiv_(b1c, ris, rris); else bes1covr = fkr * 0.5;
+  const double delte = c[GC_AQ_EFL] * (tw * b0c * cosp1 + (M::udiv_(tw - K_TWOPI * tp_fac, gmg, rgmg) * bes1covr + M::udiv_(tw, gmg, rgmg) * fkr * b1p -
                                                            tw * gmg * bes1covr) * rrp * sinp1);
   w += delte;
   gam = w * inv_mass;
-  const double bg = sqrt(gam * (gam + 2.0));
-  beta = bg / (gam + 1.0);
-  const double bgr = bg1 / bg;
+  const double bg = M::sqrt_(gam * (gam + 2.0));
+  beta = M::div(bg, gam + 1.0);
+  const double bgr = M::div(bg1, bg);
   const double onema = 1.0 - (con5nex * bes1covr + con5nex1 * b1p + con5nex2 * bes1covr) * cosp1;
   const double dovbl = con2nex * bes1covr * tw * sinp1;
-  const double bgrovonema = bgr / onema;
+  const double bgrovonema = M::div(bgr, onema);
   xp = -dovbl * x + bgrovonema * xp;
   x = x * onema + dd2 * xp;
   yp = -dovbl * y + bgrovonema * yp;
   y = y * onema + dd2 * yp;
-  if (rs_p > 0.0) rpris = rrp / ris;
+  if (rs_p > 0.0) rpris = M::udiv_(rrp, ris, rris);
   const double prome = 2.0 * con1 * (-tp_fac * b0c + ris * tw * b1c * inv_gmgcl) * (sinp1 - sinps) -
                        efl * inv_mass * tw * b1c * rpris * (cosp1 - cosps);
   const double beta_out = c[GC_BETA_OUT];
   double phi_new;
   if (ccl) {
-    phi_new = phi + (1.0 - (beta - beta_out) * betag_ccl / (beta * beta_out)) * c[GC_PI_CLBL_DPS] + prome;
+    phi_new = phi + (1.0 - M::div((beta - beta_out) * betag_ccl, beta * beta_out)) * c[GC_PI_CLBL_DPS] + prome;
   } else {
     const double d_cell_len = c[GC_D_CELL_LEN];
-    const double dphi_qlen2 = c[GC_TWOPI_HALF_QLEN] / (beta * wave_len);
+    const double den = beta * wave_len, rden = M::rcp(den);
+    const double dphi_qlen2 = M::udiv_(c[GC_TWOPI_HALF_QLEN], den, rden);
     double dphi_clen = 0.0;
-    if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = c[GC_PI_DCL] / (beta * wave_len);
-    phi_new = phi + (1.0 - (beta - beta_out) / beta) * c[GC_PI_CLBL_DPS] + prome + dphi_clen - dphi_qlen2;
+    if (d_cell_len > 1e-15 || d_cell_len < -1e-15) dphi_clen = M::udiv_(c[GC_PI_DCL], den, rden);
+    phi_new = phi + (1.0 - M::div(beta - beta_out, beta)) * c[GC_PI_CLBL_DPS] + prome + dphi_clen - dphi_qlen2;
   }
   if (w <= 0.0 || x != x || y != y || xp != xp || yp != yp || w != w || phi_new != phi_new) {
     p.loss = 33333333u;  // the reference also printf()s here; coordinates keep their pre-gap values
@@ -722,7 +738,9 @@ HPS_HD void op_quad_half_f(Pt& p, const double* q, const double* c, u32 elem, do
     sincos(kds, &s, &cs);
     const double sovk = s * inv_k, shovk = sh * inv_k, sk = s * k, shk = sh * k;
     double x = p.x, xp = p.xp, y = p.y, yp = p.yp, u;
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int rep = 0; rep < 2; ++rep) {
       if (qg > 0.0) {
         u = cs * x + sovk * xp; xp = -sk * x + cs * xp; x = u;
@@ -871,6 +889,7 @@ struct KickCtx {  // block-uniform inputs of the space-charge kick, staged in sh
   // derived once per block (kick_prepare) with the reference's expression order
   double gmg, dr_eff, dzg, hl, c2, c3, xfac, yfac, pl, cbgcoef, nr_dr, er_c3, ez_c3;
   double inv_epsq, inv_dr, inv_dzg;  // reciprocals for the fast kick
+  double wavg_dbg;                   // (tests/gpu_maps_check.cu only)
 };
 
 // particle-independent part of space_charge_kernel.cu:597-616, 680-681
@@ -902,7 +921,8 @@ __host__ __device__ inline void kick_prepare(KickCtx& k, const double* q, double
 }
 
 // space_charge_kernel.cu:573-706
-HPS_HD void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __restrict__ fld, double mass) {
+template <class M>
+HPS_HD void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __restrict__ fld, double mass, double inv_mass) {
   if (!(p.loss == 0 && lloss == 0)) return;
   const double beta = k.beta;
   const double phi = rel_phi(p.phi, k.phi_ref);
@@ -910,14 +930,15 @@ HPS_HD void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __rest
   const double dr = k.dr_eff;
   const double dzg = k.dzg;
   const double hl = k.hl;
-  const double gm = p.w / mass + 1.0;
-  const double bgz = sqrt((gm - 1.0) * (gm + 1.0));
+  const double gm = M::udiv_(p.w, mass, inv_mass) + 1.0;
+  const double bgz = M::sqrt_((gm - 1.0) * (gm + 1.0));
   double bgx = bgz * p.xp, bgy = bgz * p.yp;
   double bgzstar = gmg * (bgz - beta * gm);
   const double xxbar = p.x - k.xbar, yybar = p.y - k.ybar;
-  double r = sqrt(xxbar * xxbar / k.epsq + yybar * yybar * k.epsq);
+  double r = M::sqrt_(M::udiv_(xxbar * xxbar, k.epsq, k.inv_epsq) + yybar * yybar * k.epsq);
   if (r == 0.0) r = 1.0e-8;
-  const double xovr = xxbar * k.xfac / r, yovr = yybar * k.yfac / r;
+  const double rr = M::rcp(r);  // x/r and y/r share the denominator
+  const double xovr = M::udiv_(xxbar * k.xfac, r, rr), yovr = M::udiv_(yybar * k.yfac, r, rr);
   double ddz = phi - k.phimc;
   while (ddz > K_PI || ddz < -K_PI) {
     if (ddz > 0.0) ddz -= K_TWOPI; else ddz += K_TWOPI;
@@ -926,15 +947,15 @@ HPS_HD void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __rest
   double cbgr, cbgzs;
   if (r > k.nr_dr || fabs(z) > hl) {  // off the mesh: point-charge field of the on-mesh charge (H17)
     z = -k.c2 * (phi - k.phimc);
-    double d = sqrt(z * z + r * r);
-    double invd3 = 1.0 / (d * d * d);
+    double d = M::sqrt_(z * z + r * r);
+    double invd3 = M::rcp(d * d * d);
     double rod3 = r * invd3, zod3 = z * invd3;
     for (int nb = 1; nb <= (int)k.adj_bunch; ++nb) {
       int xi = nb;
       for (int lr = 1; lr <= 2; ++lr) {
         double s = z + xi * k.pl;
-        d = sqrt(s * s + r * r);
-        invd3 = 1.0 / (d * d * d);
+        d = M::sqrt_(s * s + r * r);
+        invd3 = M::rcp(d * d * d);
         rod3 += r * invd3;
         zod3 += s * invd3;
         xi = -xi;
@@ -943,10 +964,11 @@ HPS_HD void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __rest
     cbgr = k.cbgcoef * rod3;
     cbgzs = k.cbgcoef * zod3;
   } else {
-    const u32 i = 1 + (int)(r / dr);
-    const double a = r / dr - (i - 1.0), b = 1.0 - a;
-    const u32 j = 1 + (int)((z + hl) / dzg);
-    const double c = (z + hl) / dzg - (j - 1.0), d = 1.0 - c;
+    const double ri = M::udiv_(r, dr, k.inv_dr), zj = M::udiv_(z + hl, dzg, k.inv_dzg);
+    const u32 i = 1 + (int)ri;
+    const double a = ri - (i - 1.0), b = 1.0 - a;
+    const u32 j = 1 + (int)zj;
+    const double c = zj - (j - 1.0), d = 1.0 - c;
     const u32 l = (j - 1) * (k.nr + 1) + i;
     u32 m = l + (k.nr + 1);
     const u32 tbl_sz = (k.nr + 1) * (k.nz + 1);
@@ -962,9 +984,10 @@ HPS_HD void op_sc_kick(Pt& p, u32 lloss, const KickCtx& k, const double2* __rest
   const double bgzf = gmg * (bgzstar + beta * gstar);
   if (bgzf <= 0.0) p.loss = 9999u;
   else {
-    p.xp = bgx / bgzf;
-    p.yp = bgy / bgzf;
-    p.w *= 1.0 + (gm + 1.0) * (bgzf - bgz) / (gm * bgz);
+    const double rbgzf = M::rcp(bgzf);  // shared by the two transverse quotients
+    p.xp = M::udiv_(bgx, bgzf, rbgzf);
+    p.yp = M::udiv_(bgy, bgzf, rbgzf);
+    p.w *= 1.0 + M::div((gm + 1.0) * (bgzf - bgz), gm * bgz);
   }
 }
 

@@ -56,6 +56,13 @@ cudaError_t launch_deposit(const LaunchCfg&, const BeamView&, DevStats*, ScDev*,
 cudaError_t launch_field(const LaunchCfg&, DevStats*, ScDev*, const double* bins, double2* field, double2* part,
                          u32* tickets, const KickParams&, u32 mesh_seq);
 unsigned field_chunks(const KickParams&);
+// fused moments + deposit + field solve (k_scheff); grid must not exceed scheff_occupancy() x SM count
+bool scheff_supported(const KickParams&);
+int scheff_occupancy(const KickParams&);
+unsigned scheff_items(const KickParams&);
+size_t scheff_smem(const KickParams&);
+cudaError_t launch_scheff(const LaunchCfg&, unsigned grid, const BeamView&, DevStats*, ScDev*, double* bins, double2* field,
+                          double2* part, u32* tickets, const KickParams&, u32 mesh_seq);
 void launch_stat(const LaunchCfg&, const BeamView&, DevStats*, const StatReq&);
 void launch_set_phi_ref(const LaunchCfg&, const BeamView&, DevStats*, int use_good, double phi0);
 void launch_copy_stat(const LaunchCfg&, DevStats*, int dst, int src);

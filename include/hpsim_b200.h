@@ -98,6 +98,21 @@ int hps_abi_version(void);
  * There is deliberately no "fixed physics" mode in this round; the switch exists
  * so that tests can assert the quirks are the only difference. */
 int hps_ctx_set_compat(hps_ctx*, int compat_reference);
+/* Arithmetic of the element maps and of the space-charge kick in the fused segment kernel.
+ * HPS_MATH_REFERENCE: the reference's own expression order, operation by operation
+ *   (simulation_kernel.cu:16-871, space_charge_kernel.cu:573-706), every division and square root
+ *   IEEE-correctly rounded -- computed with branch-free Newton sequences and, for divisions by per-op
+ *   constants, one multiplication by a prepared reciprocal plus an exact-remainder correction
+ *   (hpsim_b200/csrc/hps_math.cuh); bit-identical to HPS_MATH_REFERENCE_NVCC.
+ * HPS_MATH_REFERENCE_NVCC: the same expressions with nvcc's own `/` and sqrt (kept as the cross-check).
+ * HPS_MATH_FAST: divisions by per-op constants are plain multiplications by reciprocals and
+ *   sqrt-then-divide pairs are one rsqrt; every map result is within a few ulp of the reference-order
+ *   value (tests/host_maps.cu), loss decisions are identical on every fixture, but the dynamics amplify
+ *   the ulp-level differences: particles that dropped out of the RF bucket can deviate by 1e-6.
+ * No reference counterpart. */
+enum { HPS_MATH_REFERENCE = 0, HPS_MATH_FAST = 1, HPS_MATH_REFERENCE_NVCC = 2 };
+int hps_ctx_set_math(hps_ctx*, int mode);
+int hps_ctx_get_math(hps_ctx*);
 
 /* Multi-GPU particle sharding.  The reference is single-GPU; this
  * has no reference counterpart.  `nccl_unique_id` is the 128-byte ncclUniqueId
@@ -258,6 +273,10 @@ int hps_scheff_set_mesh_size(hps_scheff*, uint32_t nr, uint32_t nz);
 /* Debug/parity taps (the reference's -D_DEBUG table dumps, space_charge.cu:246-304).
  * bins: nr*nz doubles; field: (nr+1)*(nz+1)*2 doubles (Er,Ez interleaved). */
 int hps_scheff_download_tables(hps_scheff*, double* bins, double* field, double* dr_dz);
+/* SM-clock cycles block 0 of the fused space-charge chain (k_scheff) spent per phase, summed over all
+ * kicks so far: 0 moment sweep, 1 reduction tail + policy + grid barrier, 2 deposit + flush, 3 Green
+ * slice, 4 grid barrier (+ mesh push of a sharded beam), 5 field solve; 6-7 unused. */
+int hps_scheff_phase_cycles(hps_scheff*, uint64_t out[8]);
 
 /* ---- simulate ------------------------------------------------------------ */
 typedef struct hps_run_stats {

@@ -1184,6 +1184,8 @@ hps_ctx* hps_ctx_create(int device) { (void)device; return new hps_ctx(); }
 void hps_ctx_destroy(hps_ctx* c) { delete c; }
 const char* hps_last_error(const hps_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
 int hps_ctx_set_compat(hps_ctx* c, int v) { c->compat = v; return HPS_OK; }
+int hps_ctx_set_math(hps_ctx*, int) { return HPS_OK; }
+int hps_ctx_get_math(hps_ctx*) { return HPS_MATH_REFERENCE; }  // the oracle only knows the reference's expression order
 int hps_comm_unique_id(void*) { return HPS_ERR_COMM; }
 int hps_ctx_comm_init(hps_ctx* c, int, int nranks, const void*) {
   return nranks == 1 ? HPS_OK : fail(c, HPS_ERR_COMM, "the CPU oracle shards through hps_oracle_set_comm (tests only)");
@@ -1494,6 +1496,7 @@ int hps_scheff_set_mesh_size(hps_scheff* s, uint32_t nr, uint32_t nz) {
   SetMeshSize(s, nr, nz);
   return HPS_OK;
 }
+int hps_scheff_phase_cycles(hps_scheff*, uint64_t out[8]) { for (int i = 0; i < 8; ++i) out[i] = 0; return HPS_OK; }
 int hps_scheff_download_tables(hps_scheff* s, double* bins, double* field, double* dr_dz) {
   if (bins) std::copy(s->bins.begin(), s->bins.end(), bins);
   if (field) std::copy(s->field.begin(), s->field.end(), field);

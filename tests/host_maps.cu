@@ -9,6 +9,7 @@
 // that the deviation stays at rounding level and that the loss flags agree.
 //
 //   host_maps <lattice.lat> <first index> <last index> <particles per op> <seed>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,7 +54,107 @@ struct Dev {
   double worst() const { return fmax(fmax(fmax(x, xp), fmax(y, yp)), fmax(phi, w)); }
 };
 
+// whole-range tracking (space charge off) of a beam file with either form of the maps
+static bool read_beam(const char* path, std::vector<Pt>& out) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  char magic[4]; uint32_t ver; unsigned long long n;
+  if (fread(magic, 1, 4, f) != 4 || fread(&ver, 4, 1, f) != 1 || fread(&n, 8, 1, f) != 1) return false;
+  out.resize(n);
+  std::vector<double> a(n);
+  double Pt::*fld[6] = {&Pt::x, &Pt::xp, &Pt::y, &Pt::yp, &Pt::phi, &Pt::w};
+  for (int k = 0; k < 6; ++k) {
+    if (fread(a.data(), 8, n, f) != n) return false;
+    for (size_t i = 0; i < n; ++i) out[i].*fld[k] = a[i];
+  }
+  std::vector<uint32_t> l(n);
+  if (fread(l.data(), 4, n, f) != n) return false;
+  for (size_t i = 0; i < n; ++i) out[i].loss = l[i];
+  fclose(f);
+  return true;
+}
+
+static int track_main(int argc, char** argv) {
+  std::vector<hps_elem> lat;
+  std::vector<Pt> beam0;
+  if (argc < 6 || !read_lattice(argv[2], lat) || !read_beam(argv[5], beam0)) { fprintf(stderr, "track: bad arguments\n"); return 2; }
+  const u32 first = (u32)atoi(argv[3]), last = (u32)atoi(argv[4]);
+  const double mass = 939.294, charge = -1.0, inv_mass = 1.0 / mass;
+  EngineState eng;
+  BeamHost bh = {mass, charge, 0.015, 201.25, 0.75, (u32)beam0.size()};
+  ScHost sc;
+  Plan plan = build_plan(lat, first, last, eng, bh, sc);
+  if (!plan.error.empty()) { fprintf(stderr, "plan: %s\n", plan.error.c_str()); return 2; }
+  std::vector<OpC> opc(plan.ops.size());
+  for (size_t k = 0; k < plan.ops.size(); ++k) { memset(&opc[k], 0, sizeof(OpC)); prepare_op(plan.ops[k], opc[k], mass, charge); }
+  std::vector<Pt> A = beam0, B = beam0;
+  for (int variant = 0; variant < 2; ++variant) {
+    std::vector<Pt>& P = variant ? B : A;
+    for (size_t i = 0; i < P.size(); ++i) {
+      Pt p = P[i];
+      for (size_t k = 0; k < plan.ops.size() && p.loss == 0; ++k) {
+        const Op& op = plan.ops[k];
+        const double* q = op.p; const double* c = opc[k].c;
+        switch (op.type) {
+          case OP_DRIFT: if (variant) op_drift_f(p, q, c, op.elem, inv_mass); else op_drift<MathLib>(p, q, c, op.elem, mass, inv_mass); break;
+          case OP_QUAD_HALF: if (variant) op_quad_half_f(p, q, c, op.elem, inv_mass); else op_quad_half<MathLib>(p, q, c, op.elem, mass, inv_mass); break;
+          case OP_GAP_FIRST: if (variant) op_gap_first_f(p, q, c, op.flag != 0, inv_mass); else op_gap_first<MathLib>(p, q, c, op.flag != 0, mass, inv_mass); break;
+          case OP_GAP_SECOND: if (variant) op_gap_second_f(p, q, c, op.flag != 0, inv_mass); else op_gap_second<MathLib>(p, q, c, op.flag != 0, mass, inv_mass); break;
+          case OP_DIPOLE_FIRST: op_dipole(p, q, false, mass); break;
+          case OP_DIPOLE_SECOND: op_dipole(p, q, true, mass); break;
+          case OP_BUNCHER: op_buncher(p, q, op.elem, mass, charge); break;
+          case OP_ROTATION: {
+            const double cosa = c[R_COS], sina = c[R_SIN];
+            const double x = p.x, y = p.y, xp = p.xp, yp = p.yp;
+            p.x = x * cosa + y * sina; p.y = y * cosa - x * sina; p.xp = xp * cosa + yp * sina; p.yp = yp * cosa - xp * sina;
+            break;
+          }
+          case OP_STEERER: {
+            const double gm1 = p.w / mass;
+            const double pm = sqrt(gm1 * (gm1 + 2.0)) * mass / K_CLIGHT;
+            if (q[0] > 1e-10) p.xp += q[0] * charge / pm;
+            if (q[1] > 1e-10) p.yp += q[1] * charge / pm;
+            break;
+          }
+          case OP_CAPERTURE: if (i > 0 && p.x * p.x + p.y * p.y > q[0] * q[0]) p.loss = op.elem; break;
+          case OP_FREQ_CHANGE: p.phi *= q[0]; break;
+          default: break;
+        }
+      }
+      P[i] = p;
+    }
+  }
+  // deviation of B (fast) from A (reference order), relative to the rms extent of each coordinate
+  double Pt::*fld[6] = {&Pt::x, &Pt::xp, &Pt::y, &Pt::yp, &Pt::phi, &Pt::w};
+  const char* nm[6] = {"x", "xp", "y", "yp", "phi", "w"};
+  long alive = 0, mism = 0;
+  for (size_t i = 0; i < A.size(); ++i) { if (A[i].loss != B[i].loss) ++mism; else if (A[i].loss == 0) ++alive; }
+  printf("TRACK particles %zu alive %ld loss_mismatch %ld ops %zu\n", A.size(), alive, mism, plan.ops.size());
+  std::vector<double> phis;
+  for (auto& p : A) if (p.loss == 0) phis.push_back(p.phi);
+  std::sort(phis.begin(), phis.end());
+  const double phi_med = phis[phis.size() / 2], phi_mean = phi_med;
+  for (int k = 0; k < 6; ++k) {
+    double m = 0, m2 = 0;
+    for (size_t i = 0; i < A.size(); ++i) if (A[i].loss == 0 && B[i].loss == 0) { m += A[i].*fld[k]; m2 += (A[i].*fld[k]) * (A[i].*fld[k]); }
+    m /= alive; const double sd = sqrt(fmax(m2 / alive - m * m, 1e-300));
+    std::vector<double> e;
+    long big = 0, big_core = 0, core = 0;
+    for (size_t i = 0; i < A.size(); ++i) if (A[i].loss == 0 && B[i].loss == 0) {
+      const double d = fabs(A[i].*fld[k] - B[i].*fld[k]) / sd;
+      e.push_back(d);
+      const bool in_core = fabs(A[i].phi - phi_mean) < 1.0;
+      core += in_core;
+      if (d > 1e-9) { ++big; big_core += in_core; if (k == 0) printf("   outlier i=%zu dphi=%.3f w=%.6g (design %.4g) dev=%.2e\n", i, A[i].phi - phi_med, A[i].w, bh.design_w, d); }
+    }
+    std::sort(e.begin(), e.end());
+    printf("%-3s sd %.3e median %.2e p99 %.2e max %.2e  >1e-9: %ld (in core |dphi|<1: %ld of %ld)\n", nm[k], sd, e[e.size() / 2], e[e.size() * 99 / 100], e.back(), big, big_core, core);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && strcmp(argv[1], "track") == 0) return track_main(argc, argv);
   if (argc < 6) { fprintf(stderr, "usage: host_maps lattice first last n seed\n"); return 2; }
   std::vector<hps_elem> lat;
   if (!read_lattice(argv[1], lat)) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
@@ -88,10 +189,10 @@ int main(int argc, char** argv) {
       if (i == 0) { a.x = a.y = a.xp = a.yp = 0.0; }  // the reference particle sits on the axis
       Pt b = a;
       switch (op.type) {
-        case OP_DRIFT: op_drift(a, op.p, oc.c, op.elem, mass); op_drift_f(b, op.p, oc.c, op.elem, inv_mass); break;
-        case OP_QUAD_HALF: op_quad_half(a, op.p, oc.c, op.elem, mass); op_quad_half_f(b, op.p, oc.c, op.elem, inv_mass); break;
-        case OP_GAP_FIRST: op_gap_first(a, op.p, oc.c, op.flag != 0, mass); op_gap_first_f(b, op.p, oc.c, op.flag != 0, inv_mass); break;
-        case OP_GAP_SECOND: op_gap_second(a, op.p, oc.c, op.flag != 0, mass); op_gap_second_f(b, op.p, oc.c, op.flag != 0, inv_mass); break;
+        case OP_DRIFT: op_drift<MathLib>(a, op.p, oc.c, op.elem, mass, inv_mass); op_drift_f(b, op.p, oc.c, op.elem, inv_mass); break;
+        case OP_QUAD_HALF: op_quad_half<MathLib>(a, op.p, oc.c, op.elem, mass, inv_mass); op_quad_half_f(b, op.p, oc.c, op.elem, inv_mass); break;
+        case OP_GAP_FIRST: op_gap_first<MathLib>(a, op.p, oc.c, op.flag != 0, mass, inv_mass); op_gap_first_f(b, op.p, oc.c, op.flag != 0, inv_mass); break;
+        case OP_GAP_SECOND: op_gap_second<MathLib>(a, op.p, oc.c, op.flag != 0, mass, inv_mass); op_gap_second_f(b, op.p, oc.c, op.flag != 0, inv_mass); break;
         default: continue;
       }
       dev[op.type].add(b, a);
@@ -126,7 +227,7 @@ int main(int argc, char** argv) {
         a.w = wavg * (1.0 + 0.01 * U(rng));
         a.loss = 0;
         Pt b = a;
-        op_sc_kick(a, 0u, k, fld.data(), mass);
+        op_sc_kick<MathLib>(a, 0u, k, fld.data(), mass, inv_mass);
         op_sc_kick_f(b, 0u, k, fld.data(), inv_mass);
         dev[OP_SC_KICK].add(b, a);
       }

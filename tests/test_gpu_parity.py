@@ -69,19 +69,39 @@ def test_dtl_space_charge_vs_reference_fixture():
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (reference CUDA) was not built")
+@pytest.mark.parametrize("math", ["fast", "reference", "reference_nvcc"])
 @pytest.mark.parametrize("last,sc,tol_rms", [("spch_comp_7", True, 1e-9), ("04QM30", False, 1e-9), ("08DT", False, 5e-9)])
-def test_live_reference_strict(tmp_path, last, sc, tol_rms):
-    """Loss flags bit-exact; coordinates within 1e-9 RELATIVE (north star) and within tol_rms of an rms
-    extent (the stricter house measure; 1 555 elements deep into the CCL the phase error, which the
-    maps accumulate additively, reaches 1.6e-9 of the bunch length while it is 1e-13 of the phase)."""
+def test_live_reference_strict(tmp_path, last, sc, tol_rms, math):
+    """Loss flags bit-exact; coordinates within 1e-9 RELATIVE (north star); rms moments within 1e-9.
+
+    math == "reference" (the default, what bench.py runs: the reference's expression order with IEEE-exact
+    division and sqrt) and "reference_nvcc": EVERY surviving particle within 1e-9 relative and
+    within tol_rms of an rms extent (the stricter house measure; 1 555 elements deep into the CCL the phase
+    error, which the maps accumulate additively, reaches 1.6e-9 of the bunch length while it is 1e-13 of the
+    phase).
+    math == "fast" (opt-in, hps_ctx_set_math): results move by a few ulp per map, and the dynamics
+    amplify that -- without bound for particles that dropped out of the RF bucket (hundreds of RF periods behind
+    the bunch at a fraction of the design energy, tests/host_maps.cu `track` shows them).  Gate: the median
+    particle within 1e-11, 99.9 % of the surviving particles within 1e-9, none beyond 1e-5."""
     n = 32768
     ref, _ = H.run_reference(str(tmp_path), n, "TBDB02", last, sc=sc, double=True)
-    _, st, _ = run(H.cuda_lib(), n, "TBDB02", last, sc)
+    with H.math_mode(math):
+        c, st, _ = run(H.cuda_lib(), n, "TBDB02", last, sc)
+        m = c.moments()
     rep = H.compare(st, ref, 1e-9)
-    print("REP", last, rep)
+    print("REP", math, last, rep)
     assert rep["loss_equal"] and rep["lloss_equal"], rep
-    assert rep["worst_rel"] < 1e-9, rep
-    assert rep["worst"] < tol_rms, rep
+    rs = dict(zip(H.REF_STATS, ref["stats"]))
+    if not sc:
+        for k in ("x_sig", "y_sig", "w_avg", "phi_avg", "ex", "ey"):
+            assert abs(m[k] - rs[k]) <= (1e-9 if math != "fast" else 1e-8) * abs(rs[k]), (k, m[k], rs[k])
+    if math != "fast":
+        assert rep["worst_rel"] < 1e-9, rep
+        assert rep["worst"] < tol_rms, rep
+    else:
+        assert rep["median_rel"] < 1e-11, rep
+        assert rep["p999_rel"] < 1e-9, rep
+        assert rep["worst_rel"] < 1e-5, rep
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (reference CUDA) was not built")
@@ -196,3 +216,59 @@ def test_statistics_against_oracle():
     for opt in ("absolute", "relative", "longitudinal_good"):
         assert abs(g.beam.get_avg_phi(opt) - o.beam.get_avg_phi(opt)) < 1e-6
         assert abs(g.beam.get_sig_phi(opt) - o.beam.get_sig_phi(opt)) < 1e-6
+
+
+def test_branch_free_arithmetic_is_bit_exact():
+    """hps_math.cuh: division / reciprocal / sqrt / divide-by-constant sequences vs nvcc's operators, 2^30
+    random operand pairs each, bit for bit (tests/gpu_math_check.cu)."""
+    import re
+    import subprocess
+    exe = os.path.join(H.ROOT, "tests", "_build", "gpu_math_check")
+    assert os.path.exists(exe), "build it with __graft_entry__.build()"
+    p = subprocess.run([exe, "30"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    m = re.search(r"MATHCHECK pairs (\d+) div (\d+) rcp (\d+) sqrt (\d+) udiv (\d+)", p.stdout)
+    assert m, p.stdout
+    print(p.stdout)
+    assert [int(m.group(i)) for i in range(2, 6)] == [0, 0, 0, 0], p.stdout
+
+
+def test_reference_order_maps_bit_identical_per_op():
+    """Every drift / quad / RF-gap record of the linac and the space-charge kick, evaluated on the GPU with nvcc's
+    `/` and sqrt and with the branch-free exact arithmetic (tests/gpu_maps_check.cu).  Drift, quadrupole, first gap
+    half and kick must agree bit for bit.  In the second gap half nvcc contracts the multiply-add chains of the
+    transverse update differently in the two template instantiations (the divisions themselves are identical,
+    see test_branch_free_arithmetic_is_bit_exact): a 1-ulp difference in < 0.1 % of the evaluations is accepted."""
+    import re
+    import subprocess
+    exe = os.path.join(H.ROOT, "tests", "_build", "gpu_maps_check")
+    assert os.path.exists(exe), "build it with __graft_entry__.build()"
+    p = subprocess.run([exe, H.LATTICE, "62", "6537", "256"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    print(p.stdout)
+    rows = {m.group(1): (int(m.group(2)), int(m.group(3))) for m in re.finditer(r"^(\w+)\s+evaluated (\d+) not bit-identical (\d+)", p.stdout, re.M)}
+    for name in ("drift", "quad_half", "gap_first", "sc_kick"):
+        assert rows[name][0] > 0 and rows[name][1] == 0, rows
+    assert rows["gap_second"][0] > 0 and rows["gap_second"][1] < 1e-3 * rows["gap_second"][0], rows
+
+
+@pytest.mark.parametrize("sc", [False, True])
+def test_reference_modes_agree(sc):
+    """HPS_MATH_REFERENCE (default: branch-free exact arithmetic) against HPS_MATH_REFERENCE_NVCC (nvcc's `/` and
+    sqrt) on whole runs, 64 Ki particles: bit-identical through the LEBT (drifts, quadrupoles, bunchers, 236
+    space-charge kicks); equal loss flags and rounding-level agreement at the end of the DTL."""
+    out = {}
+    for last in ("spch_comp_7", "04QM30"):
+        for mode in ("reference", "reference_nvcc"):
+            with H.math_mode(mode):
+                _, out[mode], _ = run(H.cuda_lib(), 65536, "TBDB02", last, sc)
+        a, b = out["reference"], out["reference_nvcc"]
+        if last == "spch_comp_7":
+            for k in a:
+                assert np.array_equal(a[k], b[k]), k
+        else:
+            rep = H.compare(a, b, 1e-9)
+            assert rep["loss_equal"] and rep["lloss_equal"], rep
+            assert rep["median_rel"] < (1e-13 if not sc else 1e-9), rep
+            if not sc:
+                assert rep["p999_rel"] < 1e-11, rep
