@@ -43,7 +43,10 @@ struct hps_ctx {
   unsigned seg_grid_cap = 0;  // resident blocks of the segment kernel variant in use
   unsigned seg_grid_cap_full = 0;
   int seg_variant = 20;  // HPS_MATH_REFERENCE, 2 particles per thread (seg_kernel() in hps_kernels.cu)
-  int fused = 1;   // moments + deposit + field solve in one launch (k_scheff) where the exchange mode allows it
+  // moments + deposit + field solve in ONE launch (k_scheff, two grid barriers): opt-in with HPSIM_FUSED=1.  Measured
+  // on C2 it loses to the three PDL-chained kernels (48.2 vs 44.2 ms per pass): the 64-register cap of a fully
+  // resident grid spills in the deposit loop, and a grid barrier costs as much as a programmatic kernel boundary.
+  int fused = 0;
   // program upload buffers
   Op* d_ops = nullptr;
   OpC* d_opc = nullptr;  // device-prepared constants, parallel to d_ops
@@ -932,6 +935,11 @@ int hps_scheff_phase_cycles(hps_scheff* s, uint64_t out[8]) {
   for (int i = 0; i < 8; ++i) out[i] = h.phase_clk[i];
   return HPS_OK;
 }
+int hps_debug_scheff_stamps(hps_ctx* c, uint64_t* out) {
+  CK(c, cudaStreamSynchronize(c->stream));
+  copy_scheff_stamps(reinterpret_cast<unsigned long long*>(out));
+  return HPS_OK;
+}
 int hps_scheff_download_tables(hps_scheff* s, double* bins, double* field, double* dr_dz) {
   hps_ctx* c = s->ctx;
   cudaSetDevice(c->device);
@@ -1034,7 +1042,8 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     int rc = HPS_OK;
     if (c->fused && c->xr.mode != XR_NCCL && sc->fused_cap > 0) {
       // the whole chain in one resident grid: every block with particles, and enough blocks for the field items
-      const unsigned want = std::max((((unsigned)b->n + 1) / 2 + 511) / 512, scheff_items(s.kp));
+      const unsigned blk = (unsigned)scheff_block();
+      const unsigned want = std::max((((unsigned)b->n + 1) / 2 + blk - 1) / blk, scheff_items(s.kp));
       const unsigned grid = std::max(1u, std::min(want, sc->fused_cap));
       prof_mark(c, HPS_PROF_MOMENTS);
       cudaError_t e = launch_scheff(l, grid, v, b->st, sc->dev, sc->bins, sc->field, sc->field_part, sc->field_tickets, s.kp, ++c->mesh_seq);

@@ -1,5 +1,6 @@
 // hps_kernels.cu -- __global__ kernels + their launch wrappers (see hps_launch.h).
 #include <algorithm>
+#include <cstdlib>
 #include "hps_kernels.cuh"
 #include "hps_launch.h"
 
@@ -554,6 +555,7 @@ __device__ __forceinline__ void bin_add(u32* s_lo, u32* s_hi, int k, double w, d
 
 struct DepCtx {
   double phimc, xbar, ybar, epsq, ref, dr, dzg, hl, c2, drdr, scale;
+  double r_epsq, r_dr, r_dzg, r_drdr;  // correctly rounded reciprocals for udiv (hps_math.cuh)
   int nx, nz;
 };
 
@@ -570,8 +572,9 @@ __device__ __forceinline__ u32 deposit_one(const DepCtx& d, u32 l, u32 ll, doubl
   if (ll != 0) return 0;
   const int nx = d.nx, nz = d.nz;
   const double dr = d.dr, dzg = d.dzg, drdr = d.drdr;
-  const double rsq_sh = (x - d.xbar) * (x - d.xbar) / d.epsq + (y - d.ybar) * (y - d.ybar) * d.epsq;
-  const int i = (int)(sqrt(rsq_sh) / dr + 1);
+  // divisions and square roots: the IEEE-exact branch-free forms (same bits as `/` and sqrt, hps_math.cuh)
+  const double rsq_sh = udiv((x - d.xbar) * (x - d.xbar), d.epsq, d.r_epsq) + (y - d.ybar) * (y - d.ybar) * d.epsq;
+  const int i = (int)(udiv(sqrt_nr(rsq_sh), dr, d.r_dr) + 1);
   if (!(i <= nx)) return 0;
   double ddz = pr - d.phimc;
   while (ddz > K_PI || ddz < -K_PI) {
@@ -580,7 +583,7 @@ __device__ __forceinline__ u32 deposit_one(const DepCtx& d, u32 l, u32 ll, doubl
   const double z = -d.c2 * ddz;
   if (!(fabs(z) < d.hl)) return 0;
   const double zz = z + d.hl;
-  const int jm1 = (int)(zz / dzg + 1);
+  const int jm1 = (int)(udiv(zz, dzg, d.r_dzg) + 1);
   int i1 = i + 1;
   if (rsq_sh < 0.5 * drdr * (double)(i * i + (i - 1) * (i - 1))) i1 = i - 1;
   if (i1 < 1) i1 = 1;
@@ -592,14 +595,17 @@ __device__ __forceinline__ u32 deposit_one(const DepCtx& d, u32 l, u32 ll, doubl
   double a;
   if (i1 == i) a = 1.0;
   else {
-    const double sqrtmp = sqrt(4.0 * rsq_sh / drdr - 1.0);
+    const double sqrtmp = sqrt_nr(udiv(4.0 * rsq_sh, drdr, d.r_drdr) - 1.0);
     const double rminsq = 0.25 * drdr * (sqrtmp - 1.0) * (sqrtmp - 1.0);
     const double rmaxsq = rminsq + sqrtmp * drdr;
-    if (i1 < i) a = (rmaxsq - (i - 1) * (i - 1) * drdr) / (rmaxsq - rminsq);
-    else a = ((i1 - 1) * (i1 - 1) * drdr - rminsq) / (rmaxsq - rminsq);
+    if (i1 < i) a = div_nr(rmaxsq - (i - 1) * (i - 1) * drdr, rmaxsq - rminsq);
+    else a = div_nr((i1 - 1) * (i1 - 1) * drdr - rminsq, rmaxsq - rminsq);
   }
   double cc = 1.0;
-  if (j1 != jm1) cc = (zz - (j1 - 1 + 0.5) * dzg) / ((jm1 - j1) * dzg);
+  if (j1 != jm1) {  // the divisor is +dzg or -dzg: x / (-dzg) == -(x / dzg) exactly
+    const double q = udiv(zz - (j1 - 1 + 0.5) * dzg, dzg, d.r_dzg);
+    cc = jm1 > j1 ? q : -q;
+  }
   const double bb = 1.0 - a, dd = 1.0 - cc;
   // jm1 can reach nz+1 when zz/dzg rounds up to nz exactly; the reference then writes one row past
   // its table.  Such a particle is dropped here instead (it carries weight cc = 1 into nowhere).
@@ -640,6 +646,7 @@ __device__ __forceinline__ void deposit_phase(const BeamView& b, DevStats* st, S
     d.hl = d.nz * 0.5 * d.dzg;
     d.c2 = beta * gm * wave_len / K_TWOPI;
     d.drdr = d.dr * d.dr;
+    d.r_epsq = 1.0 / d.epsq; d.r_dr = 1.0 / d.dr; d.r_dzg = 1.0 / d.dzg; d.r_drdr = 1.0 / d.drdr;
     s_d = d;
   }
   __syncthreads();
@@ -710,17 +717,49 @@ __device__ __forceinline__ void ellip_ke(double g, double& ee, double& ek) {
   ek = 1.38629436 - 0.5 * h + g * (0.1119697 - 0.1213486 * h + g * (0.07253230 - 0.02887472 * h));
 }
 
-struct FieldSmem {  // carve-up of the dynamic shared memory of the field solve (RS source rings per block)
+// debug tap: globaltimer stamps (ns) of every block at the phase boundaries of the LAST re-mesh kick
+__device__ unsigned long long g_scheff_stamps[1024 * 16];
+void copy_scheff_stamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_scheff_stamps, sizeof(g_scheff_stamps)); }
+
+#define FSTAMP(k) if (threadIdx.x == 0 && blockIdx.x < 1024 && gridDim.y == 1) g_scheff_stamps[blockIdx.x * 16 + 8 + (k)] = global_ns();
+// Geometry of the field solve inside one block: RS source rings, TR = blockDim / RS threads per ring.  For the
+// convolution a ring's threads are L lanes (4 adjacent nodes each, L = power of two >= nz / 4) x S source segments.
+struct FieldGeom {
+  u32 RS, TR, L, S, seg, HQ;
+};
+__host__ __device__ inline FieldGeom field_geom(u32 nz, u32 RS, u32 block) {
+  FieldGeom g;
+  g.RS = RS;
+  g.TR = block / RS;
+  g.L = 1;
+  while (g.L * 4 < nz) g.L <<= 1;
+  g.S = g.TR / g.L;  // 0: mesh too long for this block shape
+  if (g.S > nz) g.S = nz;
+  g.seg = g.S ? (nz + g.S - 1) / g.S : 0;
+  g.HQ = (2 * nz + 3) / 4 + 1;
+  return g;
+}
+__host__ __device__ inline size_t field_geom_bytes(const FieldGeom& g, u32 nz, u32 block) {
+  return (size_t)g.RS * nz * sizeof(double) + (size_t)g.RS * 4 * g.HQ * sizeof(double2) + (size_t)g.RS * g.S * nz * sizeof(double2) +
+         (size_t)block * sizeof(double2);
+}
+struct FieldSmem {  // carve-up of the dynamic shared memory of the field solve
   double* s_b;     // [RS][nz] charge of the block's source rings
-  double2* s_g;    // [RS][nz] Green's function slice
-  double2* s_p;    // [RS][nz] ring partials at nodes zp < nz
+  double2* s_h;    // [RS][4][HQ] Green's function of each ring as a Toeplitz kernel h[zs - zp + nz], de-interleaved
+                   //   by (index mod 4) so that lanes owning 4 adjacent nodes each read consecutive words
+  double2* s_q;    // [RS][S][nz] partial fields per source segment at the nodes zp < nz
   double2* s_red;  // [blockDim.x]
+  FieldGeom g;
   __device__ FieldSmem(double* mem, u32 RS, u32 nz) {
+    g = field_geom(nz, RS, blockDim.x);
     s_b = mem;
-    s_g = reinterpret_cast<double2*>(mem + RS * nz);
-    s_p = s_g + RS * nz;
-    s_red = s_p + RS * nz;
+    s_h = reinterpret_cast<double2*>(mem + RS * nz);
+    s_q = s_h + RS * 4 * g.HQ;
+    s_red = s_q + RS * g.S * nz;
   }
+  // h[mp], mp = zs - zp + nz in [0, 2 nz): (Er, -Ez) of offset mp - nz for sources downstream of the node (zs >= zp),
+  // (Er, +Ez) of offset nz - mp - 1 for sources upstream (space_charge_kernel.cu:516-540)
+  __device__ __forceinline__ double2& h(u32 kk, u32 mp) const { return s_h[(kk * 4 + (mp & 3u)) * g.HQ + (mp >> 2)]; }
 };
 
 // Sharded beam, XR_P2P: every block stores its share of the rank-local mesh (+ on-mesh count and max |phi|)
@@ -741,7 +780,7 @@ __device__ __forceinline__ void field_push_mesh(const ScDev* sc, const double* b
   }
 }
 
-// Green's function entry (ring rs0+kk -> radius irp, axial offset (t + 1/2) cells) into s_g; does not depend on
+// Green's function entry (ring rs0+kk -> radius irp, axial offset (t + 1/2) cells) into s_h; does not depend on
 // the charge mesh (space_charge_kernel.cu:39-100)
 __device__ __forceinline__ void field_green(const ScDev* sc, const KickParams& kp, u32 irp, u32 rs0, u32 kk, u32 t, bool live,
                                             const FieldSmem& m) {
@@ -784,7 +823,8 @@ __device__ __forceinline__ void field_green(const ScDev* sc, const KickParams& k
       xi = -xi;
     }
   }
-  m.s_g[kk * nz + t] = make_double2(c1 * er1, c1 * ez1);
+  m.h(kk, nz + t) = make_double2(c1 * er1, -(c1 * ez1));
+  m.h(kk, nz - t - 1) = make_double2(c1 * er1, c1 * ez1);
 }
 
 // Gathers the charge of the block's source rings (folding the R rank-local meshes of a sharded beam), then the
@@ -798,7 +838,7 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
   const u32 nrs = min(RS, nr - rs0);
   const double inv_scale = 1.0 / bin_scale(kp.n_global);          // fixed-point mesh, see k_deposit
   double* s_b = m.s_b;
-  double2 *s_g = m.s_g, *s_p = m.s_p, *s_red = m.s_red;
+  double2* s_red = m.s_red;
   if (xr.nranks <= 1) {
     if (irp == 0 && ch == 0 && threadIdx.x == 0) {
       sc->num_on_mesh_all = ldv(&sc->num_on_mesh);
@@ -838,33 +878,58 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
     }
   }
   __syncthreads();
+  FSTAMP(0)
 
   const size_t nodes_per_rp = nz + 1;
   double2* my_part = part + ((size_t)irp * nch + ch) * nodes_per_rp;
-  double2 last = make_double2(0.0, 0.0);  // this thread's term of node (zp = nz, rp)
-  if (live) {
-    // node (zp = t, rp), sources of ring kk in zs order, even / odd zs in separate chains
-    const u32 zp = t;
-    const double* bk = s_b + kk * nz;
-    const double2* gk = s_g + kk * nz;
-    double tx[2] = {0.0, 0.0}, tz[2] = {0.0, 0.0};
-    for (u32 zs = 0; zs < nz; ++zs) {
-      const double v = bk[zs];
-      if (v == 0.0) continue;  // warp-uniform: the 32 lanes of a warp share ring kk
-      const bool up = zs >= zp;
-      const u32 dz = up ? zs - zp : zp - zs - 1;
-      const double2 g = gk[dz];
-      tx[zs & 1] += v * g.x;
-      tz[zs & 1] += up ? -(v * g.y) : v * g.y;
+  // Nodes zp < nz.  The field of ring kk at node zp is sum_zs v[zs] h[zs - zp + nz]: a Toeplitz product.  A thread
+  // owns 4 adjacent nodes and one segment of the sources and slides a 4-wide window of h through registers: one
+  // shared-memory load per source step serves 8 multiply-adds (the one-node-per-thread form re-read h for every
+  // multiply-add pair and was bound by shared-memory bandwidth: 12.6 us of the 19 us solve).
+  {
+    const FieldGeom& g = m.g;
+    const u32 ck = threadIdx.x / g.TR, cr = threadIdx.x % g.TR, cs = cr / g.L, cl = cr % g.L;
+    if (ck < nrs && cs < g.S && 4 * cl < nz) {
+      const double* bk = s_b + ck * nz;
+      const u32 z0 = cs * g.seg, z1 = min(nz, z0 + g.seg);
+      const int top = 2 * (int)nz - 1;
+      auto H = [&](int mp) -> double2 { return m.h(ck, (u32)max(0, min(mp, top))); };
+      int base = (int)z0 - 4 * (int)cl + (int)nz;  // index of h for the first of the thread's 4 nodes at source z0
+      double2 w0 = H(base), w1 = H(base - 1), w2 = H(base - 2), w3 = H(base - 3);
+      double ax0 = 0.0, ax1 = 0.0, ax2 = 0.0, ax3 = 0.0, az0 = 0.0, az1 = 0.0, az2 = 0.0, az3 = 0.0;
+      u32 zs = z0;
+#define FSTEP(A, B, C, D)                                              \
+  {                                                                    \
+    const double2 nw = H(base + 1);                                    \
+    const double v = bk[zs];                                           \
+    ax0 += v * A.x; az0 += v * A.y; ax1 += v * B.x; az1 += v * B.y;    \
+    ax2 += v * C.x; az2 += v * C.y; ax3 += v * D.x; az3 += v * D.y;    \
+    D = nw; ++base; ++zs;                                              \
+  }
+      while (zs < z1) {
+        FSTEP(w0, w1, w2, w3) if (zs >= z1) break;
+        FSTEP(w3, w0, w1, w2) if (zs >= z1) break;
+        FSTEP(w2, w3, w0, w1) if (zs >= z1) break;
+        FSTEP(w1, w2, w3, w0)
+      }
+#undef FSTEP
+      double2* q = m.s_q + (size_t)(ck * g.S + cs) * nz + 4 * cl;
+      q[0] = make_double2(ax0, az0);
+      if (4 * cl + 1 < nz) q[1] = make_double2(ax1, az1);
+      if (4 * cl + 2 < nz) q[2] = make_double2(ax2, az2);
+      if (4 * cl + 3 < nz) q[3] = make_double2(ax3, az3);
     }
-    s_p[kk * nz + zp] = make_double2(tx[0] + tx[1], tz[0] + tz[1]);
-    // node (zp = nz, rp): every source bin lies upstream (dz = nz - zs - 1); this thread owns zs = t
-    const double v = bk[t];
-    const double2 g = gk[nz - t - 1];
-    last = make_double2(v * g.x, v * g.y);
+  }
+  // node (zp = nz, rp): every source bin lies upstream (h index = zs); thread (kk, t) owns zs = t
+  double2 last = make_double2(0.0, 0.0);
+  if (live) {
+    const double v = s_b[kk * nz + t];
+    const double2 hv = m.h(kk, t);
+    last = make_double2(v * hv.x, v * hv.y);
   }
   s_red[threadIdx.x] = last;
   __syncthreads();
+  FSTAMP(1)
   for (u32 s = blockDim.x >> 1; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       s_red[threadIdx.x].x += s_red[threadIdx.x + s].x;
@@ -872,12 +937,14 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
     }
     __syncthreads();
   }
-  if (threadIdx.x < nz) {  // fold the ring partials of this chunk in ring order
-    double2 a = s_p[threadIdx.x];
-    for (u32 k = 1; k < nrs; ++k) { a.x += s_p[k * nz + threadIdx.x].x; a.y += s_p[k * nz + threadIdx.x].y; }
+  if (threadIdx.x < nz) {  // fold the segment and ring partials of this chunk in a fixed order
+    const u32 np = nrs * m.g.S;
+    double2 a = m.s_q[threadIdx.x];
+    for (u32 k = 1; k < np; ++k) { a.x += m.s_q[(size_t)k * nz + threadIdx.x].x; a.y += m.s_q[(size_t)k * nz + threadIdx.x].y; }
     my_part[threadIdx.x] = a;
   }
   if (threadIdx.x == 0) my_part[nz] = s_red[0];
+  FSTAMP(2)
 
   // last block of this rp folds the chunk partials (fixed order)
   __shared__ u32 s_last;
@@ -888,6 +955,7 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
     s_last = (tk == nch - 1) ? 1u : 0u;
   }
   __syncthreads();
+  FSTAMP(3)
   if (!s_last) return;
   __threadfence();
   for (u32 node = threadIdx.x; node <= nz; node += blockDim.x) {
@@ -938,18 +1006,23 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
 //   field item (independent of the mesh: it hides the flush and the barrier) -> BARRIER -> field solve.
 // A sharded beam (XR_P2P) needs the complete rank-local mesh before it can be pushed to the peers, so there
 // the barrier sits before the push and the Green slice hides the NVLink transfer instead.
-// All blocks are co-resident (grid <= occupancy x SMs, hps_capi.cpp).  blockDim.x = 512 = RS * T.
-__global__ void __launch_bounds__(512, 2)
+// All blocks are co-resident (grid <= occupancy x SMs, hps_capi.cpp).  blockDim.x = BLK >= RS * T: 1024 threads
+// (one block per SM) by default -- half as many block-private meshes to flush with L2 atomics, half as many
+// partials and barrier arrivals as with 512-thread blocks.
+template <int BLK>
+__global__ void __launch_bounds__(BLK, 1024 / BLK)
 k_scheff(BeamView b, DevStats* st, ScDev* sc, double* bins, double2* field, double2* part, u32* tickets, KickParams kp, int T,
          u32 mesh_seq, double* partials, u32* ticket, const __grid_constant__ XrView xr) {
   extern __shared__ __align__(16) unsigned char s_dyn[];  // deposit: 2*nr*nz u32; field: FieldSmem (whichever is larger)
   __shared__ double s_total[MOM_NS];
-  __shared__ double s_scratch[512];
+  __shared__ double s_scratch[BLK];
   pdl_launch_dependents();
   pdl_wait();
   const bool clk = blockIdx.x == 0 && threadIdx.x == 0;
   long long t0 = clock64(), t1;
-#define PHASE(k) if (clk) { t1 = clock64(); sc->phase_clk[k] += (unsigned long long)(t1 - t0); t0 = t1; }
+  if (threadIdx.x == 0 && blockIdx.x < 1024) g_scheff_stamps[blockIdx.x * 16] = global_ns();
+#define PHASE(k) if (clk) { t1 = clock64(); sc->phase_clk[k] += (unsigned long long)(t1 - t0); t0 = t1; } \
+                 if (threadIdx.x == 0 && blockIdx.x < 1024) g_scheff_stamps[blockIdx.x * 16 + k + 1] = global_ns();
   moments_phase(b, st, sc, bins, kp, 1, 1, partials, ticket, s_total, s_scratch, xr);
   PHASE(0)
   grid_barrier(ticket + 2);
@@ -960,7 +1033,7 @@ k_scheff(BeamView b, DevStats* st, ScDev* sc, double* bins, double2* field, doub
   __syncthreads();  // the block-private mesh has been flushed: the shared memory is free again
   PHASE(2)
 
-  const u32 RS = min((u32)HPS_FIELD_RS, blockDim.x / (u32)T);
+  const u32 RS = min((u32)(HPS_FIELD_RS * BLK / 512), blockDim.x / (u32)T);
   const u32 nch = (kp.nr + RS - 1) / RS;
   const u32 nitems = (kp.nr + 1) * nch;
   const u32 kk = threadIdx.x / T, t = threadIdx.x % T;
@@ -1217,8 +1290,8 @@ static unsigned field_rs(const KickParams& kp) {  // source rings per block: RS 
   return t ? std::max(1, std::min(HPS_FIELD_RS, 1024 / t)) : 1;
 }
 size_t field_smem(const KickParams& kp, int /*threads*/) {
-  const size_t rs = field_rs(kp);
-  return rs * kp.nz * (sizeof(double) + 2 * sizeof(double2)) + rs * (size_t)field_threads(kp) * sizeof(double2);
+  const unsigned rs = field_rs(kp), block = rs * (unsigned)field_threads(kp);
+  return field_geom_bytes(field_geom(kp.nz, rs, block), kp.nz, block);
 }
 unsigned field_chunks(const KickParams& kp) { return (kp.nr + field_rs(kp) - 1) / field_rs(kp); }
 cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
@@ -1244,31 +1317,50 @@ cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const doub
   launch_chain(c, k_field, dim3(kp.nr + 1, field_chunks(kp)), dim3(T * field_rs(kp)), smem, st, sc, bins, field, part, tickets, kp, T, mesh_seq, c.xr);
   return cudaSuccess;
 }
-// ---- fused chain (k_scheff): 512 threads = RS * T per block
+// ---- fused chain (k_scheff): BLK threads >= RS * T per block
+static int g_scheff_blk = 0;
+int scheff_block() {
+  if (!g_scheff_blk) {
+    const char* v = getenv("HPSIM_SCHEFF_BLOCK");
+    g_scheff_blk = (v && atoi(v) == 512) ? 512 : 1024;
+  }
+  return g_scheff_blk;
+}
 static unsigned scheff_rs(const KickParams& kp) {
-  const int t = field_threads(kp);
-  return (t && t <= 512) ? std::max(1, std::min(HPS_FIELD_RS, 512 / t)) : 0;
+  const int t = field_threads(kp), blk = scheff_block();
+  return (t && t <= blk) ? std::max(1, std::min(HPS_FIELD_RS * blk / 512, blk / t)) : 0;
 }
 size_t scheff_smem(const KickParams& kp) {
-  const size_t rs = scheff_rs(kp);
-  const size_t fld = rs * kp.nz * (sizeof(double) + 2 * sizeof(double2)) + 512 * sizeof(double2);
-  return std::max(fld, deposit_smem(kp));
+  const unsigned rs = scheff_rs(kp);
+  if (!rs) return 0;
+  const FieldGeom g = field_geom(kp.nz, rs, (u32)scheff_block());
+  return std::max(field_geom_bytes(g, kp.nz, (u32)scheff_block()), deposit_smem(kp));
 }
-bool scheff_supported(const KickParams& kp) { return scheff_rs(kp) != 0 && scheff_smem(kp) <= 200 * 1024; }
+bool scheff_supported(const KickParams& kp) {
+  const unsigned rs = scheff_rs(kp);
+  return rs != 0 && field_geom(kp.nz, rs, (u32)scheff_block()).S != 0 && scheff_smem(kp) <= 200 * 1024;
+}
 unsigned scheff_items(const KickParams& kp) { const unsigned rs = scheff_rs(kp); return rs ? (kp.nr + 1) * ((kp.nr + rs - 1) / rs) : 0; }
 int scheff_occupancy(const KickParams& kp) {
   const size_t smem = scheff_smem(kp);
+  const bool big = scheff_block() == 1024;
   if (smem > 48 * 1024 && !g_scheff_smem_set) {
-    if (cudaFuncSetAttribute(k_scheff, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 0;
+    cudaError_t e = big ? cudaFuncSetAttribute(k_scheff<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                        : cudaFuncSetAttribute(k_scheff<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return 0;
     g_scheff_smem_set = 1;
   }
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scheff, 512, smem);
+  if (big) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scheff<1024>, 1024, smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scheff<512>, 512, smem);
   return nb;
 }
 cudaError_t launch_scheff(const LaunchCfg& c, unsigned grid, const BeamView& b, DevStats* st, ScDev* sc, double* bins, double2* field,
                           double2* part, u32* tickets, const KickParams& kp, u32 mesh_seq) {
-  return launch_chain(c, k_scheff, dim3(grid), dim3(512), scheff_smem(kp), b, st, sc, bins, field, part, tickets, kp, field_threads(kp),
+  if (scheff_block() == 1024)
+    return launch_chain(c, k_scheff<1024>, dim3(grid), dim3(1024), scheff_smem(kp), b, st, sc, bins, field, part, tickets, kp,
+                        field_threads(kp), mesh_seq, c.partials, c.ticket, c.xr);
+  return launch_chain(c, k_scheff<512>, dim3(grid), dim3(512), scheff_smem(kp), b, st, sc, bins, field, part, tickets, kp, field_threads(kp),
                       mesh_seq, c.partials, c.ticket, c.xr);
 }
 void launch_stat(const LaunchCfg& c, const BeamView& b, DevStats* st, const StatReq& rq) {

@@ -272,3 +272,28 @@ def test_reference_modes_agree(sc):
             assert rep["median_rel"] < (1e-13 if not sc else 1e-9), rep
             if not sc:
                 assert rep["p999_rel"] < 1e-11, rep
+
+
+@pytest.mark.parametrize("last,n", [("TBQL05V2", 20000), ("spch_comp_7", 65536), ("01QM05", 65536)])
+def test_scheff_tables_against_oracle(last, n):
+    """The charge mesh and the field table of the last re-mesh kick (hps_scheff_download_tables): the mesh is a
+    fixed-point sum on the GPU and a sequential fp64 sum in the oracle, the field solve sums in a different
+    (fixed) order -- both must agree with the oracle to rounding level, and the cell sizes exactly."""
+    import ctypes as C
+    tabs = {}
+    for name, lib in (("gpu", H.cuda_lib()), ("oracle", H.oracle_lib())):
+        c = H.Case(lib, n=n, sc=True)
+        c.run("TBDB02", last)
+        bins = np.zeros(32 * 128)
+        field = np.zeros(33 * 129 * 2)
+        drdz = np.zeros(2)
+        rc = lib.hps_scheff_download_tables(c.spch.h, K.ptr(bins), K.ptr(field), K.ptr(drdz))
+        assert rc == 0
+        tabs[name] = (bins, field, drdz)
+    bg, fg, dg = tabs["gpu"]
+    bo, fo, do = tabs["oracle"]
+    assert np.allclose(dg, do, rtol=1e-12, atol=0), (dg, do)
+    assert bo.sum() > 0.5 * n * 0.5
+    assert np.abs(bg - bo).max() <= 1e-9 * bo.max(), np.abs(bg - bo).max()
+    assert abs(bg.sum() - bo.sum()) <= 1e-9 * bo.sum()
+    assert np.abs(fg - fo).max() <= 1e-9 * np.abs(fo).max(), (np.abs(fg - fo).max(), np.abs(fo).max())
