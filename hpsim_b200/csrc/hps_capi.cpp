@@ -935,11 +935,6 @@ int hps_scheff_phase_cycles(hps_scheff* s, uint64_t out[8]) {
   for (int i = 0; i < 8; ++i) out[i] = h.phase_clk[i];
   return HPS_OK;
 }
-int hps_debug_scheff_stamps(hps_ctx* c, uint64_t* out) {
-  CK(c, cudaStreamSynchronize(c->stream));
-  copy_scheff_stamps(reinterpret_cast<unsigned long long*>(out));
-  return HPS_OK;
-}
 int hps_scheff_download_tables(hps_scheff* s, double* bins, double* field, double* dr_dz) {
   hps_ctx* c = s->ctx;
   cudaSetDevice(c->device);

@@ -331,9 +331,9 @@ __device__ __forceinline__ void lloss_sweep(const BeamView& b, DevStats* st, ScD
   double acc[LL_NS] = {0.0, 0.0, 0.0, 0.0};
   const u32 npairs = (b.n + 1) >> 1;
   for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
-    const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
-    const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
-    uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
+    const double2 PH = ld_f64x2(b.phi, i2);
+    const uint2 L = ld_u32x2(b.loss, i2);
+    uint2 LL = ld_u32x2(b.lloss, i2);
     const bool v1 = 2 * i2 + 1 < b.n;
     bool changed = false;
     if (PH.x > thr && LL.x != 1u) { LL.x = 1u; changed = true; }
@@ -386,16 +386,17 @@ __device__ __forceinline__ void grid_barrier(u32* bar) {
 //        6 sum y^2  7 sum w (all good)  8 MAX (x-x_avg)^2+(y-y_avg)^2 over loss==0
 __device__ void scheff_policy(DevStats* st, ScDev* sc, const KickParams& kp, double r2max) {
   // space_charge.cpp:82-139.  This is HOST arithmetic in the reference (x86-64, no FMA), hence the
-  // explicit round-to-nearest intrinsics: nvcc must not contract these into FMAs.
+  // explicit round-to-nearest intrinsics: nvcc must not contract these into FMAs.  Divisions and square roots are
+  // the IEEE-exact branch-free sequences of hps_math.cuh (this runs in ONE thread on the critical path of every kick).
   const u32 good_cnt = st->num_good;
   const double sigphi = st->v[HPS_STAT_PHI_SIG_GOOD];
   const double sigx = st->v[HPS_STAT_X_SIG_GOOD], sigy = st->v[HPS_STAT_Y_SIG_GOOD];
   const double ke = st->v[HPS_STAT_W_AVG_GOOD];
-  const double gamma = __dadd_rn(__ddiv_rn(ke, kp.mass), 1.0);
-  const double beta = __dsqrt_rn(__dsub_rn(1.0, __ddiv_rn(1.0, __dmul_rn(gamma, gamma))));
-  const double lmbd = __ddiv_rn(299.792458, kp.freq);
-  const double sigz = __dmul_rn(__dmul_rn(__ddiv_rn(__dmul_rn(sigphi, 0.5), 3.14159265), beta), lmbd);
-  const double sigr = __dsqrt_rn(__dadd_rn(__dmul_rn(sigx, sigx), __dmul_rn(sigy, sigy)));
+  const double gamma = __dadd_rn(div_nr(ke, kp.mass), 1.0);
+  const double beta = sqrt_nr(__dsub_rn(1.0, div_nr(1.0, __dmul_rn(gamma, gamma))));
+  const double lmbd = div_nr(299.792458, kp.freq);
+  const double sigz = __dmul_rn(__dmul_rn(div_nr(__dmul_rn(sigphi, 0.5), 3.14159265), beta), lmbd);
+  const double sigr = sqrt_nr(__dadd_rn(__dmul_rn(sigx, sigx), __dmul_rn(sigy, sigy)));
   const double cratior = __dmul_rn(sigr, sigz);
   const double cratioz = __dmul_rn(__dmul_rn(__dmul_rn(sigz, sigz), gamma), gamma);
   const double cratior_old = __dmul_rn(sc->sigr_old, sc->sigz_old);
@@ -405,8 +406,8 @@ __device__ void scheff_policy(DevStats* st, ScDev* sc, const KickParams& kp, dou
   sc->beta = beta;
   sc->n_kicks++;
   const bool remesh = cratior_old == 0.0 || cratioz_old == 0.0 ||
-                      __ddiv_rn(fabs(__dsub_rn(cratior, cratior_old)), cratior_old) > kp.remesh_val ||
-                      __ddiv_rn(fabs(__dsub_rn(cratioz, cratioz_old)), cratioz_old) > kp.remesh_val;
+                      div_nr(fabs(__dsub_rn(cratior, cratior_old)), cratior_old) > kp.remesh_val ||
+                      div_nr(fabs(__dsub_rn(cratioz, cratioz_old)), cratioz_old) > kp.remesh_val;
   sc->remesh = remesh ? 1 : 0;
   if (remesh) {
     sc->n_remesh++;
@@ -479,29 +480,48 @@ __device__ __forceinline__ void moments_phase(const BeamView& b, DevStats* st, S
 #pragma unroll
   for (int s = 0; s < MOM_NS; ++s) acc[s] = 0.0;
   const u32 npairs = (b.n + 1) >> 1;
-  for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
-    const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
-    const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
-    const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
-    const double2 W = reinterpret_cast<const double2*>(b.w)[i2];
-    const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
-    const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
-    const double x[2] = {X.x, X.y}, y[2] = {Y.x, Y.y}, ph[2] = {PH.x, PH.y}, w[2] = {W.x, W.y};
-    const u32 l[2] = {L.x, L.y}, ll[2] = {LL.x, LL.y};
+  // Software-pipelined sweep: the loads of the NEXT pair are issued before the current pair is accumulated, so
+  // one L2 round trip per iteration is all that is ever exposed.  (Left to itself ptxas issued the last of the six
+  // loads of an iteration only after the first results had been consumed -- two dependent round trips, 15 us
+  // per sweep instead of 4.)  A particle that fails a filter contributes an exact +0.0.
+  struct MomPair { uint2 L, LL; double2 PH, X, Y, W; };
+  auto load_pair = [&](u32 i2) {
+    MomPair p;
+    p.L = ld_u32x2(b.loss, i2); p.LL = ld_u32x2(b.lloss, i2);
+    p.PH = ld_f64x2(b.phi, i2); p.X = ld_f64x2(b.x, i2); p.Y = ld_f64x2(b.y, i2); p.W = ld_f64x2(b.w, i2);
+    return p;
+  };
+  const u32 stride = gridDim.x * blockDim.x;
+  u32 i2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i2 < npairs) {
+    MomPair cur = load_pair(i2);
+    for (;;) {
+      const u32 nx = i2 + stride;
+      const bool more = nx < npairs;
+      MomPair nxt = cur;
+      if (more) nxt = load_pair(nx);
+      const double x[2] = {cur.X.x, cur.X.y}, y[2] = {cur.Y.x, cur.Y.y}, ph[2] = {cur.PH.x, cur.PH.y}, w[2] = {cur.W.x, cur.W.y};
+      const u32 l[2] = {cur.L.x, cur.L.y}, ll[2] = {cur.LL.x, cur.LL.y};
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (j == 1 && !(2 * i2 + 1 < b.n)) continue;
-      if (l[j] != 0) continue;
-      const double pr = rel_phi(ph[j], ref);
-      acc[0] += pr;
-      const double tx = x[j] - xa, ty = y[j] - ya;
-      acc[8] = fmax(acc[8], tx * tx + ty * ty);
-      if (ll[j] == 0) {
-        acc[1] += pr; acc[2] += pr * pr;
-        acc[3] += x[j]; acc[4] += x[j] * x[j];
-        acc[5] += y[j]; acc[6] += y[j] * y[j];
-        acc[7] += w[j];
+      for (int j = 0; j < 2; ++j) {
+        const bool alive = l[j] == 0 && (j == 0 || 2 * i2 + 1 < b.n);
+        const bool good = alive && ll[j] == 0;
+        const double pr = rel_phi(ph[j], ref);
+        acc[0] += alive ? pr : 0.0;
+        const double tx = x[j] - xa, ty = y[j] - ya;
+        const double r2 = tx * tx + ty * ty;
+        acc[8] = alive ? fmax(acc[8], r2) : acc[8];
+        acc[1] += good ? pr : 0.0;
+        acc[2] = good ? fma(pr, pr, acc[2]) : acc[2];  // fused like the reference build's sum2 += v * v
+        acc[3] += good ? x[j] : 0.0;
+        acc[4] = good ? fma(x[j], x[j], acc[4]) : acc[4];
+        acc[5] += good ? y[j] : 0.0;
+        acc[6] = good ? fma(y[j], y[j], acc[6]) : acc[6];
+        acc[7] += good ? w[j] : 0.0;
       }
+      if (!more) break;
+      cur = nxt;
+      i2 = nx;
     }
   }
   if (!grid_reduce<MOM_NS>(acc, 1u << 8, partials, ticket, s_total, s_scratch, xr)) return;
@@ -652,16 +672,31 @@ __device__ __forceinline__ void deposit_phase(const BeamView& b, DevStats* st, S
   __syncthreads();
   u32 cnt = 0;
   double pmax = 0.0;
-  // two adjacent particles per thread, every array read with one 128/64-bit access issued up front
+  // two adjacent particles per thread, every array read with one 128/64-bit access; software-pipelined like the
+  // moment sweep: the next pair's loads are in flight while the current pair is deposited
   const u32 npairs = (b.n + 1) >> 1;
-  for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
-    const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
-    const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
-    const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
-    const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
-    const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
-    cnt += deposit_one(s_d, L.x, LL.x, X.x, Y.x, PH.x, s_lo, s_hi, pmax);
-    if (2 * i2 + 1 < b.n) cnt += deposit_one(s_d, L.y, LL.y, X.y, Y.y, PH.y, s_lo, s_hi, pmax);
+  struct DepPair { uint2 L, LL; double2 PH, X, Y; };
+  auto load_pair = [&](u32 i2) {
+    DepPair p;
+    p.L = ld_u32x2(b.loss, i2); p.LL = ld_u32x2(b.lloss, i2);
+    p.PH = ld_f64x2(b.phi, i2); p.X = ld_f64x2(b.x, i2); p.Y = ld_f64x2(b.y, i2);
+    return p;
+  };
+  const u32 stride = gridDim.x * blockDim.x;
+  u32 i2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i2 < npairs) {
+    DepPair cur = load_pair(i2);
+    for (;;) {
+      const u32 nx = i2 + stride;
+      const bool more = nx < npairs;
+      DepPair nxt = cur;
+      if (more) nxt = load_pair(nx);
+      cnt += deposit_one(s_d, cur.L.x, cur.LL.x, cur.X.x, cur.Y.x, cur.PH.x, s_lo, s_hi, pmax);
+      if (2 * i2 + 1 < b.n) cnt += deposit_one(s_d, cur.L.y, cur.LL.y, cur.X.y, cur.Y.y, cur.PH.y, s_lo, s_hi, pmax);
+      if (!more) break;
+      cur = nxt;
+      i2 = nx;
+    }
   }
   __syncthreads();
   for (u32 k = threadIdx.x; k < nb; k += blockDim.x) {
@@ -717,11 +752,6 @@ __device__ __forceinline__ void ellip_ke(double g, double& ee, double& ek) {
   ek = 1.38629436 - 0.5 * h + g * (0.1119697 - 0.1213486 * h + g * (0.07253230 - 0.02887472 * h));
 }
 
-// debug tap: globaltimer stamps (ns) of every block at the phase boundaries of the LAST re-mesh kick
-__device__ unsigned long long g_scheff_stamps[1024 * 16];
-void copy_scheff_stamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_scheff_stamps, sizeof(g_scheff_stamps)); }
-
-#define FSTAMP(k) if (threadIdx.x == 0 && blockIdx.x < 1024 && gridDim.y == 1) g_scheff_stamps[blockIdx.x * 16 + 8 + (k)] = global_ns();
 // Geometry of the field solve inside one block: RS source rings, TR = blockDim / RS threads per ring.  For the
 // convolution a ring's threads are L lanes (4 adjacent nodes each, L = power of two >= nz / 4) x S source segments.
 struct FieldGeom {
@@ -878,7 +908,6 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
     }
   }
   __syncthreads();
-  FSTAMP(0)
 
   const size_t nodes_per_rp = nz + 1;
   double2* my_part = part + ((size_t)irp * nch + ch) * nodes_per_rp;
@@ -929,7 +958,6 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
   }
   s_red[threadIdx.x] = last;
   __syncthreads();
-  FSTAMP(1)
   for (u32 s = blockDim.x >> 1; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       s_red[threadIdx.x].x += s_red[threadIdx.x + s].x;
@@ -944,7 +972,6 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
     my_part[threadIdx.x] = a;
   }
   if (threadIdx.x == 0) my_part[nz] = s_red[0];
-  FSTAMP(2)
 
   // last block of this rp folds the chunk partials (fixed order)
   __shared__ u32 s_last;
@@ -955,7 +982,6 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
     s_last = (tk == nch - 1) ? 1u : 0u;
   }
   __syncthreads();
-  FSTAMP(3)
   if (!s_last) return;
   __threadfence();
   for (u32 node = threadIdx.x; node <= nz; node += blockDim.x) {
@@ -1020,9 +1046,7 @@ k_scheff(BeamView b, DevStats* st, ScDev* sc, double* bins, double2* field, doub
   pdl_wait();
   const bool clk = blockIdx.x == 0 && threadIdx.x == 0;
   long long t0 = clock64(), t1;
-  if (threadIdx.x == 0 && blockIdx.x < 1024) g_scheff_stamps[blockIdx.x * 16] = global_ns();
-#define PHASE(k) if (clk) { t1 = clock64(); sc->phase_clk[k] += (unsigned long long)(t1 - t0); t0 = t1; } \
-                 if (threadIdx.x == 0 && blockIdx.x < 1024) g_scheff_stamps[blockIdx.x * 16 + k + 1] = global_ns();
+#define PHASE(k) if (clk) { t1 = clock64(); sc->phase_clk[k] += (unsigned long long)(t1 - t0); t0 = t1; }
   moments_phase(b, st, sc, bins, kp, 1, 1, partials, ticket, s_total, s_scratch, xr);
   PHASE(0)
   grid_barrier(ticket + 2);

@@ -57,6 +57,20 @@ __device__ __forceinline__ void warp_reduce(double (&v)[NS], unsigned max_mask) 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Loads the compiler may neither sink into a later branch nor reorder: the statistic sweeps test the loss flag of
+// a particle before they touch its coordinates, and nvcc then moves the coordinate loads behind that branch --
+// two or three dependent L2 round trips per iteration instead of one (the moment sweep took 15 us instead of 4).
+__device__ __forceinline__ double2 ld_f64x2(const double* base, u32 i2) {
+  double2 v;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(reinterpret_cast<const double2*>(base) + i2));
+  return v;
+}
+__device__ __forceinline__ uint2 ld_u32x2(const u32* base, u32 i2) {
+  uint2 v;
+  asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(reinterpret_cast<const uint2*>(base) + i2));
+  return v;
+}
+
 // ---- cross-rank exchange over peer memory (XrBox, hps_internal.h) ------------------------------
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -171,16 +185,16 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, 
     const bool mx = (max_mask >> s) & 1u;
     double a = mx ? -DBL_MAX : 0.0;
     if (s < NS) {
-      // batches of 8 loads in flight before the (ordered) folds: the tail is L2-latency bound
-      for (u32 k0 = g; k0 < gridDim.x; k0 += 8 * G) {
-        double t[8];
+      // batches of 16 loads in flight before the (ordered) folds: the tail is L2-latency bound
+      for (u32 k0 = g; k0 < gridDim.x; k0 += 16 * G) {
+        double t[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const u32 k = k0 + j * G;
           t[j] = k < gridDim.x ? __ldcg(&partials[(size_t)k * NS + s]) : (mx ? -DBL_MAX : 0.0);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a = mx ? fmax(a, t[j]) : a + t[j];
+        for (int j = 0; j < 16; ++j) a = mx ? fmax(a, t[j]) : a + t[j];
       }
     }
     __syncthreads();  // scratch (blockDim.x doubles) is free again
@@ -871,14 +885,31 @@ HPS_HD void op_gap_second_f(Pt& p, const double* q, const double* c, bool ccl, d
   }
 }
 
+// fmod(t, 2 pi) for 0 <= t: the exact remainder (fmod never rounds) from one division estimate and one fused
+// multiply-add instead of libdevice's bit-serial loop (12 % of the instructions of the moment sweep: every warp that
+// holds one particle outside the bucket took it).  With n = floor(t / 2pi) possibly off by one, t - n * 2pi is
+// computed with a single rounding; a result outside [0, 2pi) reveals the wrong n and the retry with the right one is
+// exact because the true remainder is representable.  Same bits as fmod().
+HPS_HD double fmod_twopi(double t) {
+#ifdef __CUDA_ARCH__
+  if (!(t < 4.0e9)) return fmod(t, K_TWOPI);  // n must stay exactly representable with room to spare (also NaN / inf)
+  const double n = floor(t * (1.0 / K_TWOPI));
+  double r = __fma_rn(-n, K_TWOPI, t);
+  if (r < 0.0) r = __fma_rn(-(n - 1.0), K_TWOPI, t);
+  else if (r >= K_TWOPI) r = __fma_rn(-(n + 1.0), K_TWOPI, t);
+  return r;
+#else
+  return fmod(t, K_TWOPI);
+#endif
+}
+
 // relative phase (beam_kernel.cu:1506-1522)
 HPS_HD double rel_phi(double phi, double ref) {
   double tmp = phi - ref + K_PI;
   double sign = 1.0;
   if (tmp < 0) { sign = -1.0; tmp = -tmp; }
-  // fmod(t, 2pi) == t exactly for 0 <= t < 2pi (the case of every particle inside the bunch); the
-  // library call, a multi-iteration loop in fp64, is only taken by particles a full turn away
-  const double m = tmp < K_TWOPI ? tmp : fmod(tmp, K_TWOPI);
+  // fmod(t, 2pi) == t exactly for 0 <= t < 2pi (the case of every particle inside the bunch)
+  const double m = tmp < K_TWOPI ? tmp : fmod_twopi(tmp);
   return sign * (m - K_PI);
 }
 

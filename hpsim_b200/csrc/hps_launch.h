@@ -57,7 +57,6 @@ cudaError_t launch_field(const LaunchCfg&, DevStats*, ScDev*, const double* bins
                          u32* tickets, const KickParams&, u32 mesh_seq);
 unsigned field_chunks(const KickParams&);
 // fused moments + deposit + field solve (k_scheff); grid must not exceed scheff_occupancy() x SM count
-void copy_scheff_stamps(unsigned long long* out);  // debug: [1024][8] globaltimer stamps of the last re-mesh kick
 int scheff_block();  // threads per block of k_scheff (1024; HPSIM_SCHEFF_BLOCK=512 for the 2-blocks-per-SM form)
 bool scheff_supported(const KickParams&);
 int scheff_occupancy(const KickParams&);

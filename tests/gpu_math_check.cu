@@ -7,7 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "../hpsim_b200/csrc/hps_math.cuh"
+#include "../hpsim_b200/csrc/hps_kernels.cuh"
 
 using namespace hps;
 
@@ -29,8 +29,10 @@ __device__ __forceinline__ double operand(unsigned long long r, unsigned long lo
   return __longlong_as_double((long long)(((unsigned long long)e << 52) | mant));
 }
 
+__device__ __forceinline__ double uni52(unsigned long long r) { return (double)(r >> 11) * (1.0 / 9007199254740992.0); }
+
 __global__ void check(unsigned long long n, unsigned long long seed, unsigned long long* bad) {
-  unsigned long long local[4] = {0, 0, 0, 0};
+  unsigned long long local[5] = {0, 0, 0, 0, 0};
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long r1 = mix(seed + 2 * i), r2 = mix(seed + 2 * i + 1), m = mix(seed ^ i);
     const double a = (r1 >> 63 ? -1.0 : 1.0) * operand(r1, m), b = operand(r2, m >> 3);
@@ -40,20 +42,24 @@ __global__ void check(unsigned long long n, unsigned long long seed, unsigned lo
     if (__double_as_longlong(sqrt_nr(b)) != __double_as_longlong(sqrt(b))) local[2]++;
     const double rb = 1.0 / bs;  // correctly rounded reciprocal, prepared "once"
     if (__double_as_longlong(udiv(a, bs, rb)) != __double_as_longlong(a / bs)) local[3]++;
+    // fmod_twopi: arguments from 2 pi up to 2^31 (a particle tens of millions of RF periods away), dense near multiples of 2 pi
+    const double tq = (double)(r1 % 2000000ull) * K_TWOPI + ((m >> 12) & 3 ? uni52(r2) * K_TWOPI : (uni52(r2) - 0.5) * 1e-9);
+    const double tt = tq < K_TWOPI ? tq + K_TWOPI : tq;
+    if (__double_as_longlong(fmod_twopi(tt)) != __double_as_longlong(fmod(tt, K_TWOPI))) local[4]++;
   }
-  for (int k = 0; k < 4; ++k) if (local[k]) atomicAdd(&bad[k], local[k]);
+  for (int k = 0; k < 5; ++k) if (local[k]) atomicAdd(&bad[k], local[k]);
 }
 
 int main(int argc, char** argv) {
   const int lg = argc > 1 ? atoi(argv[1]) : 30;
   const unsigned long long n = 1ull << lg;
   unsigned long long* bad;
-  if (cudaMalloc(&bad, 4 * sizeof(unsigned long long)) != cudaSuccess) { fprintf(stderr, "no CUDA device\n"); return 2; }
-  cudaMemset(bad, 0, 4 * sizeof(unsigned long long));
+  if (cudaMalloc(&bad, 5 * sizeof(unsigned long long)) != cudaSuccess) { fprintf(stderr, "no CUDA device\n"); return 2; }
+  cudaMemset(bad, 0, 5 * sizeof(unsigned long long));
   check<<<148 * 8, 256>>>(n, 0x1234567ull, bad);
-  unsigned long long h[4];
+  unsigned long long h[5];
   if (cudaMemcpy(h, bad, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) { fprintf(stderr, "kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 2; }
   // sqrt(0), and the reference particle's r = 0
-  printf("MATHCHECK pairs %llu div %llu rcp %llu sqrt %llu udiv %llu\n", n, h[0], h[1], h[2], h[3]);
+  printf("MATHCHECK pairs %llu div %llu rcp %llu sqrt %llu udiv %llu fmod %llu\n", n, h[0], h[1], h[2], h[3], h[4]);
   return 0;
 }

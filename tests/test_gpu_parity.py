@@ -219,18 +219,19 @@ def test_statistics_against_oracle():
 
 
 def test_branch_free_arithmetic_is_bit_exact():
-    """hps_math.cuh: division / reciprocal / sqrt / divide-by-constant sequences vs nvcc's operators, 2^30
-    random operand pairs each, bit for bit (tests/gpu_math_check.cu)."""
+    """hps_math.cuh: division / reciprocal / sqrt / divide-by-constant sequences vs nvcc's operators, and the
+    one-step fmod(t, 2 pi) of the relative phase vs libdevice's fmod: 2^30 random operands each, bit for bit
+    (tests/gpu_math_check.cu)."""
     import re
     import subprocess
     exe = os.path.join(H.ROOT, "tests", "_build", "gpu_math_check")
     assert os.path.exists(exe), "build it with __graft_entry__.build()"
     p = subprocess.run([exe, "30"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
-    m = re.search(r"MATHCHECK pairs (\d+) div (\d+) rcp (\d+) sqrt (\d+) udiv (\d+)", p.stdout)
+    m = re.search(r"MATHCHECK pairs (\d+) div (\d+) rcp (\d+) sqrt (\d+) udiv (\d+) fmod (\d+)", p.stdout)
     assert m, p.stdout
     print(p.stdout)
-    assert [int(m.group(i)) for i in range(2, 6)] == [0, 0, 0, 0], p.stdout
+    assert [int(m.group(i)) for i in range(2, 7)] == [0, 0, 0, 0, 0], p.stdout
 
 
 def test_reference_order_maps_bit_identical_per_op():
