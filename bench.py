@@ -15,8 +15,9 @@ One step = restore the intermediate beam + one simulate(01QM00U, 04QM30).
   cpu_baseline : the CPU oracle (oracle/, OpenMP, all host cores) on a bounded sample
 
 N > 1 (torchrun): weak scaling -- ONE beam of N x 1 Mi particles, particle-sharded over the N GPUs
-(contiguous index blocks); every kick exchanges three small moment vectors and the 32 KB charge mesh
-between the ranks inside the reducing kernels (peer stores over NVLink; NCCL all-gather as fallback).
+(interleaved ownership: global particle i lives on rank i mod N); every kick exchanges three small moment
+vectors and the 32 KB charge mesh between the ranks inside the reducing kernels (peer stores over NVLink;
+NCCL all-gather as fallback).
 --replicas instead tracks one independent 1 Mi-particle beam per GPU (scan style, BASELINE configs[4]).
 `--impl reference` runs the reference's own CUDA code (oracle/_ref/ref_driver, sm_100 rebuild of
 the unmodified sources) on the same workload; the reference has no CPU implementation.
@@ -45,6 +46,10 @@ N_PER_GPU = 1 << 20
 METRIC = "particle_element_steps_per_sec"
 UNIT = "particle-element steps/s"
 SEG_BYTES = 112  # per particle per fused sweep: 6 fp64 + 2 u32 read and written
+# DRAM traffic of one k_segment launch at 1 Mi particles from the `ncu --set full` capture committed as
+# profiles/r1b_ncu_k_segment.txt (dram__bytes_read.sum + dram__bytes_write.sum; ncu flushes the L2 before every
+# replay, so this is the cold-cache figure: the sweep re-reads the whole 59 MB beam, its writes stay in L2)
+SEG_TRAFFIC_1MI = 58888448 + 1375744
 
 
 def peaks():
@@ -140,7 +145,7 @@ def cpu_baseline(nel_range, budget_s=20.0):
     from hpsim_b200 import HPSim
     HPSim.print_timing = False
     lib = H.oracle_lib()
-    n = 16384
+    n = 524288
     c = H.Case(lib, n=n, sc=True)
     c.run(*PRE)
     c.beam.save_intermediate_beam()
@@ -163,6 +168,7 @@ def main():
     ap.add_argument("--ref-float", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fast", action="store_true", help="skip the informational HPS_MATH_FAST timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -266,6 +272,14 @@ def main():
                 pinned[k][1][:] = e2e_in[k]
             te += timed(e2e_once, 1)
     clocks = sampler.summary()
+    # ---- informational: the same resident step with the opt-in fast maps (hps_ctx_set_math)
+    tf = None
+    math_mode = HPSim.get_math()
+    if not args.no_fast and math_mode != "fast":
+        HPSim.set_math("fast")
+        step_resident()
+        tf = timed(step_resident, max(2, args.steps // 2)) / max(2, args.steps // 2)
+        HPSim.set_math(math_mode)
 
     # ---- one profiled step for the roofline of the dominant kernel
     lib.hps_ctx_set_profile(ctx.h, 1)
@@ -308,8 +322,9 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2: DTL tanks 1-4 (01QM00U->04QM30, 349 elements, %d SC kicks), %d particles/GPU, SCHEFF 32x128, "
                                "interval 0.025 m, adj_bunch 3; input = C1 DC beam tracked TBDB02->spch_comp_7 (untimed)" % (run["kicks"], n),
+                   "math": math_mode + " (the reference's expression order, IEEE-exact division / sqrt)" if math_mode == "reference" else math_mode,
                    "parallelism": ("single GPU" if world == 1 else
-                                   "one beam of %d particles sharded over %d GPUs (contiguous index blocks); per kick 3 moment "
+                                   "one beam of %d particles sharded over %d GPUs (interleaved ownership); per kick 3 moment "
                                    "exchanges + the 32 KB r-z mesh, mode=%s" % (n * world, world, xr_mode) if sharded else
                                    "1 independent beam per GPU (replicas, no communication)"),
                    "l2": "L2 flushed (384 MB memset) before every timed step; inside a step the %.0f MB beam is swept ~%d times "
@@ -321,7 +336,9 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_segment", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peak, "traffic": SEG_TRAFFIC_1MI if n == N_PER_GPU else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, cold L2 (profiles/r1b_ncu_k_segment.txt)",
+                     "peak_kind": peak_kind,
                      "avg_launch_us": seg_us, "launches_per_step": seg["launches"],
                      "whole_step": {"bytes_alg": bytes_alg, "achieved_gbs": bytes_alg / (1e-3 * run["device_ms"]) / 1e9,
                                     "frac": bytes_alg / (1e-3 * run["device_ms"]) / 1e9 / peak},
@@ -332,6 +349,9 @@ def main():
         mhz = clocks.get("sm_mhz") or 1965.0
         names = ("moment_sweep", "reduce_policy_barrier", "deposit_flush", "green_slice", "barrier", "field_solve")
         line["roofline"]["scheff_phase_ms"] = {nm: (ph1[i] - ph0[i]) / (mhz * 1e3) for i, nm in enumerate(names)}
+    if tf:
+        line["fast_math"] = {"ms_per_step": 1e3 * tf, "value": total_particles * nel / tf, "unit": UNIT,
+                             "note": "informational: hps_ctx_set_math(HPS_MATH_FAST), device-resident step; not the benched default"}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(nel)
     print(json.dumps(line))
