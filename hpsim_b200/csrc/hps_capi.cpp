@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <ctime>
 #include <string>
@@ -109,6 +110,9 @@ struct hps_scheff {
   u32* field_tickets = nullptr;   // [nr+1]
   double bin_scale = 0.0;         // fixed-point scale of the last simulate() (depends on the beam size)
   unsigned fused_cap = 0;         // co-resident blocks of k_scheff for this mesh (0: fused chain not available)
+  // energy-dependent mesh: SetInterval() overrides what the last kick derived until the next kick has run
+  bool interval_user_set = false;
+  uint64_t interval_valid_after = 0;
 };
 
 namespace {
@@ -894,7 +898,7 @@ void hps_scheff_destroy(hps_scheff* s) {
 }
 int hps_scheff_set(hps_scheff* s, int p, double v) {
   switch (p) {
-    case HPS_SC_INTERVAL: s->h.interval = v; s->interval_init = v; break;
+    case HPS_SC_INTERVAL: s->h.interval = v; s->interval_init = v; s->interval_user_set = true; break;
     case HPS_SC_ADJ_BUNCH: s->h.adj_bunch = (u32)(int)v; break;
     case HPS_SC_ADJ_BUNCH_CUTOFF_W: s->h.adj_bunch_w = v; break;
     case HPS_SC_MESH_CUTOFF_W: s->mesh_w = v; break;
@@ -912,8 +916,17 @@ int hps_scheff_get(hps_scheff* s, int p, double* v) {
     case HPS_SC_MESH_CUTOFF_W: *v = s->mesh_w; break;
     case HPS_SC_REMESH_THRESHOLD: *v = s->h.remesh_val; break;
     case HPS_SC_FRACTION: *v = s->h.fraction; break;
-    case HPS_SC_NR: *v = s->h.nr; break;
-    case HPS_SC_NZ: *v = s->h.nz; break;
+    case HPS_SC_NR:
+    case HPS_SC_NZ: {  // GetNx / GetNz report the mesh in force: with the energy cutoff on it lives on the device
+      *v = p == HPS_SC_NR ? s->h.nr : s->h.nz;
+      if (s->mesh_w != 0.0) {
+        ScDev h;
+        CK(s->ctx, cudaMemcpyAsync(&h, s->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, s->ctx->stream));
+        CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+        if (h.nr != 0u) *v = p == HPS_SC_NR ? h.nr : h.nz;
+      }
+      break;
+    }
     default: return fail(s->ctx, HPS_ERR_ARG, "unknown parameter");
   }
   return HPS_OK;
@@ -925,6 +938,8 @@ int hps_scheff_set_mesh_size(hps_scheff* s, uint32_t nr, uint32_t nz) {  // spac
   cudaSetDevice(s->ctx->device);
   CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
   s->h.nr = nr; s->h.nz = nz;
+  // the device copy of "mesh in force" (energy-dependent mesh) falls back to the configured size
+  CK(s->ctx, cudaMemsetAsync(reinterpret_cast<char*>(s->dev) + offsetof(ScDev, nr), 0, 2 * sizeof(u32), s->ctx->stream));
   return scheff_alloc(s);
 }
 int hps_scheff_phase_cycles(hps_scheff* s, uint64_t out[8]) {
@@ -964,19 +979,14 @@ int hps_engine_reset(hps_ctx* c, hps_beam* b) {  // simulation_engine.cu:101-111
   return HPS_OK;
 }
 
-int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint32_t first, uint32_t last,
-                 hps_run_stats* out) {
-  if (!c || !b || !lat) return fail(c, HPS_ERR_ARG, "null handle");
-  if (last >= lat->e.size()) return fail(c, HPS_ERR_ARG, "element index out of range");
-  if (sc && sc->mesh_w != 0.0)
-    return fail(c, HPS_ERR_ARG, "mesh_size_cutoff_w != 0 (energy-dependent mesh halving, space_charge.cpp:107-117) is not supported yet");
-  if (sc && !(b->h.n_global > 2)) return fail(c, HPS_ERR_ARG, "space charge needs more than 2 particles");
-  if (!(b->h.freq > 0.0)) return fail(c, HPS_ERR_STATE, "beam frequency is not set");
-  cudaSetDevice(c->device);
-
+// One planned stretch of elements [first, last]: build the program, upload it, launch the chain.  Accumulates the
+// sweep / launch counters of the enclosing hps_simulate call.
+static int run_range(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint32_t first, uint32_t last, uint64_t* sweeps_io,
+                     uint64_t* extra_io) {
   ScHost off;
   ScHost& sh = sc ? sc->h : off;
   sh.on = sc != nullptr;
+  if (sc) sh.mesh_w = sc->mesh_w;
   Plan plan = build_plan(lat->e, first, last, c->eng, b->h, sh);
   if (!plan.error.empty()) return fail(c, HPS_ERR_LATTICE, plan.error);
 
@@ -991,37 +1001,17 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     CK(c, cudaMalloc(&c->d_opc, c->ops_cap * sizeof(OpC)));
     CK(c, cudaHostAlloc(&c->h_ops, c->ops_cap * sizeof(Op), cudaHostAllocDefault));
   }
-  CK(c, cudaStreamSynchronize(c->stream));  // h_ops may still feed the previous call's copy
+  CK(c, cudaStreamSynchronize(c->stream));  // h_ops may still feed the previous copy
   if (nops) {
     std::memcpy(c->h_ops, plan.ops.data(), nops * sizeof(Op));
     CK(c, cudaMemcpyAsync(c->d_ops, c->h_ops, nops * sizeof(Op), cudaMemcpyHostToDevice, c->stream));
   }
 
-  ScDev before;
-  std::memset(&before, 0, sizeof(before));
-  if (sc) CK(c, cudaMemcpyAsync(&before, sc->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
-
-  if (c->l2_persist && b->slab && (c->l2_window_base != b->slab || c->l2_window_bytes != b->slab_bytes)) {
-    cudaStreamAttrValue av;
-    std::memset(&av, 0, sizeof(av));
-    const size_t win = std::min(b->slab_bytes, c->l2_window_max);
-    av.accessPolicyWindow.base_ptr = b->slab;
-    av.accessPolicyWindow.num_bytes = win;
-    av.accessPolicyWindow.hitRatio = win ? (float)std::min(1.0, (double)c->l2_persist_max / (double)win) : 0.f;
-    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) { cudaGetLastError(); c->l2_persist = 0; }
-    c->l2_window_base = b->slab;
-    c->l2_window_bytes = b->slab_bytes;
-  }
   const LaunchCfg l = cfg(c, b);
   const BeamView v = view(b);
-  if (sc) { int e = 0; while (e < 32 && (1ull << e) < (unsigned long long)b->h.n_global) ++e; sc->bin_scale = (double)(1ull << (62 - e)); }
-  const uint64_t launches0 = c->launches;
   launch_prepare_ops(l, c->d_ops, c->d_opc, (int)nops, b->h.mass, b->h.charge);
   c->launches++;
   uint64_t sweeps = 0, extra = 0;
-  CK(c, cudaEventRecord(c->ev0, c->stream));
   for (const Segment& s : plan.segs) {
     const int dirty = dirty_mask(plan.ops.data() + s.op_begin, s.op_count);
     prof_mark(c, HPS_PROF_SEGMENT);
@@ -1035,7 +1025,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     }
     if (!s.kick_follows) { extra++; continue; }
     int rc = HPS_OK;
-    if (c->fused && c->xr.mode != XR_NCCL && sc->fused_cap > 0) {
+    if (c->fused && c->xr.mode != XR_NCCL && sc->fused_cap > 0 && sc->mesh_w == 0.0) {
       // the whole chain in one resident grid: every block with particles, and enough blocks for the field items
       const unsigned blk = (unsigned)scheff_block();
       const unsigned want = std::max((((unsigned)b->n + 1) / 2 + blk - 1) / blk, scheff_items(s.kp));
@@ -1072,9 +1062,74 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     if (e != cudaSuccess) return fail(c, HPS_ERR_CUDA, std::string("kick launch: ") + cudaGetErrorString(e));
     c->launches += 3;
   }
+  *sweeps_io += sweeps;
+  *extra_io += extra;
+  return HPS_OK;
+}
+
+int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint32_t first, uint32_t last,
+                 hps_run_stats* out) {
+  if (!c || !b || !lat) return fail(c, HPS_ERR_ARG, "null handle");
+  if (last >= lat->e.size()) return fail(c, HPS_ERR_ARG, "element index out of range");
+  if (sc && sc->mesh_w != 0.0 && c->xr.mode == XR_NCCL)
+    return fail(c, HPS_ERR_ARG, "mesh_size_cutoff_w != 0 is not supported with the NCCL all-gather exchange (HPSIM_XR=nccl)");
+  if (sc && !(b->h.n_global > 2)) return fail(c, HPS_ERR_ARG, "space charge needs more than 2 particles");
+  if (!(b->h.freq > 0.0)) return fail(c, HPS_ERR_STATE, "beam frequency is not set");
+  cudaSetDevice(c->device);
+
+  ScDev before;
+  std::memset(&before, 0, sizeof(before));
+  if (sc) CK(c, cudaMemcpyAsync(&before, sc->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
+
+  if (c->l2_persist && b->slab && (c->l2_window_base != b->slab || c->l2_window_bytes != b->slab_bytes)) {
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof(av));
+    const size_t win = std::min(b->slab_bytes, c->l2_window_max);
+    av.accessPolicyWindow.base_ptr = b->slab;
+    av.accessPolicyWindow.num_bytes = win;
+    av.accessPolicyWindow.hitRatio = win ? (float)std::min(1.0, (double)c->l2_persist_max / (double)win) : 0.f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) { cudaGetLastError(); c->l2_persist = 0; }
+    c->l2_window_base = b->slab;
+    c->l2_window_bytes = b->slab_bytes;
+  }
+  if (sc) { int e = 0; while (e < 32 && (1ull << e) < (unsigned long long)b->h.n_global) ++e; sc->bin_scale = (double)(1ull << (62 - e)); }
+  const uint64_t launches0 = c->launches;
+  uint64_t sweeps = 0, extra = 0;
+  CK(c, cudaEventRecord(c->ev0, c->stream));
+  if (!sc || sc->mesh_w == 0.0) {
+    int rc = run_range(c, b, lat, sc, first, last, &sweeps, &extra);
+    if (rc) return rc;
+  } else {
+    // Energy-dependent mesh (space_charge.cpp:107-117): above the cutoff energy Scheff::Start also quadruples
+    // interval_, which SimulateDrift reads when it STARTS the next drift (simulation_engine.cu:129-131) -- the number
+    // of kicks of a drift depends on <W>_good of the kick before it.  The range is therefore planned in stretches
+    // that begin at a drift; before each the state of the last kick is read back (one host synchronisation per drift
+    // while the option is on; the mesh size itself switches on the device).
+    uint32_t e0 = first;
+    while (e0 <= last) {
+      uint32_t e1 = e0;
+      while (e1 < last && lat->e[e1 + 1].type != HPS_ELEM_DRIFT) ++e1;
+      ScDev now;
+      CK(c, cudaMemcpyAsync(&now, sc->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
+      CK(c, cudaStreamSynchronize(c->stream));
+      if (sc->interval_user_set) { sc->interval_valid_after = now.n_kicks; sc->interval_user_set = false; }
+      if (now.n_kicks > sc->interval_valid_after) sc->h.interval = now.mesh_hi ? sc->interval_init * 4.0 : sc->interval_init;
+      int rc = run_range(c, b, lat, sc, e0, e1, &sweeps, &extra);
+      if (rc) return rc;
+      e0 = e1 + 1;
+    }
+  }
   CK(c, cudaEventRecord(c->ev1, c->stream));
   CK(c, cudaGetLastError());
   prof_finish(c);
+  if (sc && sc->mesh_w != 0.0) {  // interval_ as the reference's getter would report it after the run
+    ScDev now;
+    CK(c, cudaMemcpyAsync(&now, sc->dev, sizeof(ScDev), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (now.n_kicks > sc->interval_valid_after) sc->h.interval = now.mesh_hi ? sc->interval_init * 4.0 : sc->interval_init;
+  }
   if (out) {
     std::memset(out, 0, sizeof(*out));
     ScDev after;

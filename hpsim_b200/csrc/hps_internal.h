@@ -82,6 +82,10 @@ struct ScDev {
   double ratio_r, ratio_z, ratio_q, ratio_g;
   unsigned long long abs_phi_max_bits;
   unsigned long long n_kicks, n_remesh, n_lloss_pass;
+  // energy-dependent mesh (SetMeshSizeCutoffW, space_charge.cpp:107-117); nr == 0 means "the configured size"
+  u32 nr, nz;       // mesh size in force
+  u32 mesh_hi;      // 1: <W>_good of the last kick was above the cutoff (half mesh, interval x 4)
+  u32 mesh_resized; // the last kick changed the mesh size (the reference then holds fresh, zeroed tables)
   // SM-clock cycles block 0 of k_scheff spent in each phase, summed over the kicks (hps_scheff_phase_cycles):
   // 0 moments sweep, 1 reduction + finalisers + barrier, 2 deposit + flush, 3 Green slice, 4 barrier, 5 field solve
   unsigned long long phase_clk[8];
@@ -95,8 +99,9 @@ struct KickParams {
   double remesh_val;
   double adj_bunch_w;
   u32 adj_bunch_cfg;
-  u32 nr, nz;
+  u32 nr, nz;             // configured (= largest) mesh
   u32 n_global;
+  double mesh_w;          // mesh-size cutoff energy [MeV], 0 = off
 };
 
 struct BeamView {

@@ -207,6 +207,7 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       s_k.adj_bunch = sc->adj_bunch; s_k.num_on_mesh = sc->num_on_mesh_all;
     }
     s_k.nr = kp.nr; s_k.nz = kp.nz;
+    if (sc && kp.mesh_w != 0.0 && sc->nr != 0u) { s_k.nr = sc->nr; s_k.nz = sc->nz; }
     // a segment holds at most one kick (its first op); its block-uniform factors are derived here
     for (int k = 0; k < nops; ++k)
       if (ops[k].type == OP_SC_KICK) { kick_prepare(s_k, ops[k].p, b.mass, b.n_global); break; }
@@ -403,6 +404,19 @@ __device__ void scheff_policy(DevStats* st, ScDev* sc, const KickParams& kp, dou
   const double cratioz_old = __dmul_rn(__dmul_rn(__dmul_rn(sc->sigz_old, sc->sigz_old), sc->gm_old), sc->gm_old);
   u32 adj = (kp.adj_bunch_w == 0.0 || ke < kp.adj_bunch_w) ? kp.adj_bunch_cfg : 0u;
   sc->adj_bunch = adj;
+  // space_charge.cpp:107-117: above the cutoff energy the mesh is halved and the kick interval quadrupled (the host
+  // reads mesh_hi back before it plans the next drift).  SetMeshSize frees and re-creates ZEROED tables: until the
+  // next re-mesh the kick then interpolates a zero field (mesh_resized -> the caller clears the field table).
+  u32 nr = kp.nr, nz = kp.nz;
+  sc->mesh_resized = 0u;
+  if (kp.mesh_w != 0.0) {
+    const u32 cur_nr = sc->nr ? sc->nr : kp.nr, cur_nz = sc->nr ? sc->nz : kp.nz;
+    nr = cur_nr; nz = cur_nz;
+    if (ke > kp.mesh_w) { nr = kp.nr / 2; nz = kp.nz / 2; sc->mesh_hi = 1u; }
+    else if (ke <= kp.mesh_w) { nr = kp.nr; nz = kp.nz; sc->mesh_hi = 0u; }
+    if (nr != cur_nr || nz != cur_nz) sc->mesh_resized = 1u;
+    sc->nr = nr; sc->nz = nz;
+  }
   sc->beta = beta;
   sc->n_kicks++;
   const bool remesh = cratior_old == 0.0 || cratioz_old == 0.0 ||
@@ -420,13 +434,13 @@ __device__ void scheff_policy(DevStats* st, ScDev* sc, const KickParams& kp, dou
     if (adj != 0) {
       const double rmax = sqrt(r2max);  // Beam::UpdateMaxRPhi, with the stale x_avg / y_avg (H5)
       st->v[HPS_STAT_R_MAX] = rmax;
-      sc->dr = 1.0 * rmax / kp.nr;
-      sc->dz = bl / kp.nz;
+      sc->dr = 1.0 * rmax / nr;
+      sc->dz = bl / nz;
     } else {
       // H6: the reference picks the sigma by comparing device POINTERS (x_sig_good > y_sig_good is false
       // for its allocation order) -> always y_sig_good.  H8: the 3*sigma > pi clamp is dead code.
-      sc->dr = 3.0 * sigy / kp.nr;
-      sc->dz = 3.0 * bl * sigphi / (kp.nz * K_PI);
+      sc->dr = 3.0 * sigy / nr;
+      sc->dz = 3.0 * bl * sigphi / (nz * K_PI);
     }
   } else {
     sc->ratio_r = sigr / sc->sigr_old;
@@ -456,6 +470,16 @@ __device__ void finalize_moments(const double* t, double ref, u32 n_global, DevS
   }
   st->v[HPS_STAT_W_AVG_GOOD] = ng > 0 ? t[7] / ng : -99999;
   if (do_policy) scheff_policy(st, sc, kp, t[8]);
+}
+
+// mesh size in force (energy-dependent mesh, SetMeshSizeCutoffW): the configured size unless the cutoff is on
+__device__ __forceinline__ KickParams with_mesh_in_force(const KickParams& kp, const ScDev* sc) {
+  KickParams kq = kp;
+  if (kp.mesh_w != 0.0) {
+    const u32 nr = __ldcg(&sc->nr), nz = __ldcg(&sc->nz);
+    if (nr != 0u) { kq.nr = nr; kq.nz = nz; }
+  }
+  return kq;
 }
 
 // loads of values another block may have written earlier in the SAME launch (L1 is not coherent)
@@ -720,12 +744,13 @@ k_deposit(BeamView b, DevStats* st, ScDev* sc, double* bins_raw, KickParams kp, 
   pdl_launch_dependents();
   pdl_wait();
   if (!sc->remesh) return;
-  deposit_phase(b, st, sc, bins_raw, kp, s_words);
+  const KickParams kq = with_mesh_in_force(kp, sc);
+  deposit_phase(b, st, sc, bins_raw, kq, s_words);
   if (xr.mode != XR_NCCL) return;
   // XR_NCCL only: the rank's last block appends the on-mesh count and max |phi| to the mesh, which the host
   // then all-gathers.  (XR_P2P: k_field itself pushes the mesh to the peers, spread over all its blocks.)
   unsigned long long* bins = reinterpret_cast<unsigned long long*>(bins_raw);
-  const u32 nb = kp.nr * kp.nz;
+  const u32 nb = kq.nr * kq.nz;
   __shared__ u32 s_last;
   __threadfence();
   __syncthreads();
@@ -1007,19 +1032,28 @@ k_field(DevStats* st, ScDev* sc, const double* __restrict__ bins, double2* field
   extern __shared__ double s_mem[];
   pdl_launch_dependents();
   pdl_wait();
-  if (!sc->remesh) return;
+  const KickParams kq = with_mesh_in_force(kp, sc);  // the grid is sized for the configured (largest) mesh
+  if (!sc->remesh) {
+    // SetMeshSize left the reference with a fresh, zeroed field table that this kick interpolates as it is
+    if (kp.mesh_w != 0.0 && sc->mesh_resized) {
+      const u32 nf = (kp.nr + 1) * (kp.nz + 1), nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+      for (u32 k = blk * blockDim.x + threadIdx.x; k < nf; k += nblk * blockDim.x) field[k] = make_double2(0.0, 0.0);
+    }
+    return;
+  }
   const u32 RS = blockDim.x / T;
-  const u32 irp = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
+  const u32 irp = blockIdx.x, ch = blockIdx.y, nch = (kq.nr + RS - 1) / RS;
+  if (irp > kq.nr || ch >= nch) return;
   const u32 rs0 = ch * RS;
-  const u32 nrs = min(RS, kp.nr - rs0);
+  const u32 nrs = min(RS, kq.nr - rs0);
   const u32 kk = threadIdx.x / T, t = threadIdx.x % T;
-  const bool live = kk < nrs && t < kp.nz;
-  const FieldSmem m(s_mem, RS, kp.nz);
+  const bool live = kk < nrs && t < kq.nz;
+  const FieldSmem m(s_mem, RS, kq.nz);
   // XR_P2P: the mesh is pushed first; the Green's function slice does not depend on the charge mesh and is
   // computed next, so the peers' meshes travel over NVLink meanwhile; then the R meshes are polled and folded.
-  if (xr.mode == XR_P2P) field_push_mesh(sc, bins, kp, mesh_seq, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, xr);
-  field_green(sc, kp, irp, rs0, kk, t, live, m);
-  field_solve(st, sc, bins, field, part, tickets, kp, irp, ch, nch, RS, kk, t, live, mesh_seq, m, xr);
+  if (xr.mode == XR_P2P) field_push_mesh(sc, bins, kq, mesh_seq, ch * (kq.nr + 1) + irp, (kq.nr + 1) * nch, xr);
+  field_green(sc, kq, irp, rs0, kk, t, live, m);
+  field_solve(st, sc, bins, field, part, tickets, kq, irp, ch, nch, RS, kk, t, live, mesh_seq, m, xr);
 }
 
 // ================================================================================================

@@ -31,6 +31,7 @@ struct Builder {
     kp.nr = sc->nr;
     kp.nz = sc->nz;
     kp.n_global = beam->n_global;
+    kp.mesh_w = sc->mesh_w;
     return kp;
   }
   void close(int fin, bool kick) {

@@ -29,7 +29,7 @@ struct BeamHost {  // host-side members of Beam that the engine reads / writes
 struct ScHost {  // SpaceCharge members (space_charge.h:88-125) that are known on the host
   bool on = false;
   u32 nr = 0, nz = 0, adj_bunch = 0;
-  double fraction = 1.0, interval = 0.01, adj_bunch_w = 0.0, remesh_val = 0.05;
+  double fraction = 1.0, interval = 0.01, adj_bunch_w = 0.0, remesh_val = 0.05, mesh_w = 0.0;
 };
 
 struct Segment {

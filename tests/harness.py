@@ -194,7 +194,8 @@ REF_STATS = ["loss", "lloss", "good", "x_avg", "x_sig", "y_avg", "y_sig", "phi_a
 
 
 def run_reference(workdir, n, first, last, sc=True, double=True, nr=32, nz=128, interval=0.025, adj_bunch=3,
-                  cutoff_w=0.8, remesh=0.02, seed=SEED, beam_in=None, design_w=None, freq=FREQ, repeats=1, timeout=900):
+                  cutoff_w=0.8, remesh=0.02, seed=SEED, beam_in=None, design_w=None, freq=FREQ, repeats=1, timeout=900,
+                  mesh_cutoff_w=None):
     """Runs oracle/_ref/ref_driver{,_dp} (the reference's own CUDA code) and returns (state, log)."""
     exe = REF_DP if double else REF_SP
     os.makedirs(workdir, exist_ok=True)
@@ -203,6 +204,8 @@ def run_reference(workdir, n, first, last, sc=True, double=True, nr=32, nz=128, 
            f"sc {1 if sc else 0}", f"nr {nr}", f"nz {nz}", f"interval {interval}", f"adj_bunch {adj_bunch}",
            f"adj_bunch_cutoff_w {cutoff_w}", f"remesh_threshold {remesh}", f"first {first}", f"last {last}",
            f"beam_out {out}", f"repeats {repeats}"]
+    if mesh_cutoff_w is not None:
+        cfg.append(f"mesh_cutoff_w {float(mesh_cutoff_w)!r}")
     if beam_in is None:
         cfg += ["gen dc", f"seed {seed}", f"freq {FREQ}", f"ref_w {REF_W}", f"ref_phi {PHI_OFFSET!r}", f"shift_phi {PHI_OFFSET!r}"]
         for k, v in DC.items():

@@ -298,3 +298,44 @@ def test_scheff_tables_against_oracle(last, n):
     assert np.abs(bg - bo).max() <= 1e-9 * bo.max(), np.abs(bg - bo).max()
     assert abs(bg.sum() - bo.sum()) <= 1e-9 * bo.sum()
     assert np.abs(fg - fo).max() <= 1e-9 * np.abs(fo).max(), (np.abs(fg - fo).max(), np.abs(fo).max())
+
+
+@pytest.mark.parametrize("mesh_w,last", [(0.5, "spch_comp_7"), (2.0, "01QM30"), (50.0, "TREM01")])
+def test_mesh_size_cutoff_against_oracle(mesh_w, last):
+    """SetMeshSizeCutoffW (space_charge.cpp:107-117): above the cutoff energy the mesh is halved (on the device) and
+    the kick interval quadrupled (host re-plans at every drift).  0.5 MeV: above the cutoff from the first kick (LEBT
+    drifts with 4 x interval, 16 x 64 mesh); 2 MeV: the switch happens inside DTL tank 1; 50 MeV: inside tank 3, with
+    the drifts of the transition region behind it."""
+    n = 8192
+    out = {}
+    for name, lib in (("gpu", H.cuda_lib()), ("oracle", H.oracle_lib())):
+        c = H.Case(lib, n=n, sc=True)
+        c.spch.set_mesh_size_cutoff_w(mesh_w)
+        r = c.run("TBDB02", last)
+        c.beam.get_loss_num("l")
+        out[name] = (c.state(), r, c.spch.get_interval(), c.spch.get_mesh_size())
+    (sg, rg, ig, mg), (so, ro, io, mo) = out["gpu"], out["oracle"]
+    assert rg["kicks"] == ro["kicks"] and rg["remesh"] == ro["remesh"], (rg, ro)
+    assert ig == io and list(mg) == list(mo), (ig, io, mg, mo)
+    rep = H.compare(sg, so, 1e-9)
+    assert rep["loss_equal"] and rep["lloss_equal"], rep
+    if last == "TREM01":  # through the whole DTL with space charge the tracking is chaotic (see the module docstring)
+        assert rep["median_rel"] < 1e-5 and rep["worst"] < 2e-2, rep  # same band as the DTL fixture test above
+    else:
+        assert rep["worst"] < (1e-9 if last == "spch_comp_7" else 1e-6), rep
+    if mesh_w == 0.5:
+        assert ig == 0.1 and list(mg) == [16.0, 64.0]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (reference CUDA) was not built")
+def test_mesh_size_cutoff_live_reference(tmp_path):
+    """The same option against the reference's own CUDA code (LEBT, cutoff below the injection energy)."""
+    n = 32768
+    ref, _ = H.run_reference(str(tmp_path), n, "TBDB02", "spch_comp_7", sc=True, double=True, mesh_cutoff_w=0.5)
+    c = H.Case(H.cuda_lib(), n=n, sc=True)
+    c.spch.set_mesh_size_cutoff_w(0.5)
+    c.run("TBDB02", "spch_comp_7")
+    c.beam.get_loss_num("l")
+    rep = H.compare(c.state(), ref, 1e-9)
+    assert rep["loss_equal"] and rep["lloss_equal"], rep
+    assert rep["worst"] < 1e-9, rep
