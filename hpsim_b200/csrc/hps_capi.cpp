@@ -60,6 +60,17 @@ struct hps_ctx {
   void* xr_mapped[HPS_XR_MAXR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   int pdl = 1;       // HPSIM_PDL=0 turns programmatic dependent launch off
+  // CUDA graphs: the launch sequence of a planned range is captured once and replayed for every later simulate() of
+  // the same program on the same objects (scans, benchmarks, optimisation loops re-run one range thousands of times).
+  struct GraphEntry {
+    uint64_t key = 0, stamp = 0, sweeps = 0, extra = 0, launches = 0;
+    cudaGraphExec_t exec = nullptr;
+    Op* d_ops = nullptr;
+    OpC* d_opc = nullptr;
+  };
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_stamp = 0;
+  int use_graphs = 0;  // HPSIM_GRAPH=1 turns them on (default off until validated on the GPU)
   // L2 residency (opt-in, HPSIM_L2_PERSIST=1): the particle slab of the beam being tracked becomes the stream's
   // access-policy window (persisting lines).  Measured on C2: no gain (48.7 vs 48.0 ms per pass) -- the sweeps
   // are bound by fp64 latency, not by where the 59 MB beam is read from -- so it is off by default.
@@ -366,6 +377,7 @@ hps_ctx* hps_ctx_create(int device) {
     c->seg_variant = math_variant(c->seg_variant % 10, v[0] == 'r' ? HPS_MATH_REFERENCE : (v[0] == 'n' ? HPS_MATH_REFERENCE_NVCC : HPS_MATH_FAST));
   if (const char* v = getenv("HPSIM_PDL")) c->pdl = atoi(v);
   if (const char* v = getenv("HPSIM_FUSED")) c->fused = atoi(v);
+  if (const char* v = getenv("HPSIM_GRAPH")) c->use_graphs = atoi(v);
   if (const char* v = getenv("HPSIM_L2_PERSIST")) c->l2_persist = atoi(v);
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
@@ -399,6 +411,7 @@ void hps_ctx_destroy(hps_ctx* c) {
   cudaFree(c->xr_box); cudaFree(c->xr.bins_gather);
   comm_destroy(c->comm);
   cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_ops); cudaFree(c->d_opc); cudaFreeHost(c->h_ops);
+  for (auto& g : c->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); cudaFree(g.d_ops); cudaFree(g.d_opc); }
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->user_ev) if (e) cudaEventDestroy(e);
   cudaFree(c->flush_buf);
@@ -856,6 +869,7 @@ static int scheff_alloc(hps_scheff* s) {
   const size_t chunks = std::max<size_t>(field_chunks(kp), scheff_supported(kp) ? scheff_items(kp) / (s->h.nr + 1) : 0);
   CK(c, cudaMalloc(&s->field_part, nf * chunks * sizeof(double2)));
   s->fused_cap = scheff_supported(kp) ? (unsigned)std::max(0, scheff_occupancy(kp)) * (unsigned)c->num_sms : 0u;
+  CK(c, prepare_chain_attributes(kp));
   CK(c, cudaMalloc(&s->field_tickets, (s->h.nr + 1) * sizeof(u32)));
   CK(c, cudaMemsetAsync(s->field_tickets, 0, (s->h.nr + 1) * sizeof(u32), c->stream));
   CK(c, cudaMemsetAsync(s->bins, 0, (nb + 2) * sizeof(double), c->stream));
@@ -979,43 +993,24 @@ int hps_engine_reset(hps_ctx* c, hps_beam* b) {  // simulation_engine.cu:101-111
   return HPS_OK;
 }
 
-// One planned stretch of elements [first, last]: build the program, upload it, launch the chain.  Accumulates the
-// sweep / launch counters of the enclosing hps_simulate call.
-static int run_range(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint32_t first, uint32_t last, uint64_t* sweeps_io,
-                     uint64_t* extra_io) {
-  ScHost off;
-  ScHost& sh = sc ? sc->h : off;
-  sh.on = sc != nullptr;
-  if (sc) sh.mesh_w = sc->mesh_w;
-  Plan plan = build_plan(lat->e, first, last, c->eng, b->h, sh);
-  if (!plan.error.empty()) return fail(c, HPS_ERR_LATTICE, plan.error);
+static uint64_t fnv(uint64_t h, const void* p, size_t n) {
+  const unsigned char* q = static_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; ++i) { h ^= q[i]; h *= 1099511628211ull; }
+  return h;
+}
 
-  // upload the program
-  const size_t nops = plan.ops.size();
-  if (nops > c->ops_cap) {
-    CK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_ops); cudaFree(c->d_opc); cudaFreeHost(c->h_ops);
-    c->d_ops = nullptr; c->d_opc = nullptr; c->h_ops = nullptr;
-    c->ops_cap = nops * 2;
-    CK(c, cudaMalloc(&c->d_ops, c->ops_cap * sizeof(Op)));
-    CK(c, cudaMalloc(&c->d_opc, c->ops_cap * sizeof(OpC)));
-    CK(c, cudaHostAlloc(&c->h_ops, c->ops_cap * sizeof(Op), cudaHostAllocDefault));
-  }
-  CK(c, cudaStreamSynchronize(c->stream));  // h_ops may still feed the previous copy
-  if (nops) {
-    std::memcpy(c->h_ops, plan.ops.data(), nops * sizeof(Op));
-    CK(c, cudaMemcpyAsync(c->d_ops, c->h_ops, nops * sizeof(Op), cudaMemcpyHostToDevice, c->stream));
-  }
-
+// The launch sequence of one plan on the context's stream (directly, or into a stream capture).
+static int launch_plan(hps_ctx* c, hps_beam* b, hps_scheff* sc, const Plan& plan, const Op* d_ops, OpC* d_opc, uint64_t* sweeps_io,
+                       uint64_t* extra_io) {
   const LaunchCfg l = cfg(c, b);
   const BeamView v = view(b);
-  launch_prepare_ops(l, c->d_ops, c->d_opc, (int)nops, b->h.mass, b->h.charge);
+  launch_prepare_ops(l, d_ops, d_opc, (int)plan.ops.size(), b->h.mass, b->h.charge);
   c->launches++;
   uint64_t sweeps = 0, extra = 0;
   for (const Segment& s : plan.segs) {
     const int dirty = dirty_mask(plan.ops.data() + s.op_begin, s.op_count);
     prof_mark(c, HPS_PROF_SEGMENT);
-    launch_segment(l, v, plan.ops.data() + s.op_begin, c->d_ops + s.op_begin, c->d_opc + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
+    launch_segment(l, v, plan.ops.data() + s.op_begin, d_ops + s.op_begin, d_opc + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
                    sc ? sc->field : nullptr, s.kp);
     c->launches++;
     sweeps++;
@@ -1065,6 +1060,102 @@ static int run_range(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, 
   *sweeps_io += sweeps;
   *extra_io += extra;
   return HPS_OK;
+}
+
+// One planned stretch of elements [first, last]: build the program, upload it, launch the chain (or replay the graph
+// captured for the same program earlier).  Accumulates the sweep / launch counters of the enclosing hps_simulate call.
+static int run_range(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint32_t first, uint32_t last, uint64_t* sweeps_io,
+                     uint64_t* extra_io) {
+  ScHost off;
+  ScHost& sh = sc ? sc->h : off;
+  sh.on = sc != nullptr;
+  if (sc) sh.mesh_w = sc->mesh_w;
+  Plan plan = build_plan(lat->e, first, last, c->eng, b->h, sh);
+  if (!plan.error.empty()) return fail(c, HPS_ERR_LATTICE, plan.error);
+  const size_t nops = plan.ops.size();
+
+  // ---- CUDA graph path: single GPU, no per-launch profiling, no drift-wise re-planning
+  if (c->use_graphs && c->xr.nranks <= 1 && !c->profile && (!sc || sc->mesh_w == 0.0) && nops > 0) {
+    uint64_t key = 1469598103934665603ull;
+    key = fnv(key, plan.ops.data(), nops * sizeof(Op));
+    for (const Segment& s : plan.segs) {
+      const uint64_t d[4] = {s.op_begin, s.op_count, (uint64_t)s.fin_mode, (uint64_t)s.kick_follows};
+      key = fnv(key, d, sizeof(d));
+      if (s.kick_follows || (s.op_count && plan.ops[s.op_begin].type == OP_SC_KICK)) {
+        const double kd[6] = {s.kp.freq, s.kp.mass, s.kp.current_frac, s.kp.remesh_val, s.kp.adj_bunch_w, s.kp.mesh_w};
+        const uint64_t ku[4] = {s.kp.adj_bunch_cfg, s.kp.nr, s.kp.nz, s.kp.n_global};
+        key = fnv(fnv(key, kd, sizeof(kd)), ku, sizeof(ku));
+      }
+    }
+    const uint64_t env[12] = {(uint64_t)(uintptr_t)b->slab, (uint64_t)(uintptr_t)b->st, b->n, b->offset, (uint64_t)(uintptr_t)(sc ? sc->dev : nullptr),
+                              (uint64_t)(uintptr_t)(sc ? sc->bins : nullptr), (uint64_t)(uintptr_t)(sc ? sc->field : nullptr),
+                              (uint64_t)c->seg_variant, (uint64_t)c->fused, (uint64_t)c->compat, (uint64_t)c->pdl,
+                              (uint64_t)(uintptr_t)(sc ? sc->field_part : nullptr)};
+    key = fnv(key, env, sizeof(env));
+    const double bm[2] = {b->h.mass, b->h.charge};
+    key = fnv(key, bm, sizeof(bm));
+    for (auto& g : c->graphs)
+      if (g.key == key && g.exec) {
+        g.stamp = ++c->graph_stamp;
+        CK(c, cudaGraphLaunch(g.exec, c->stream));
+        c->launches += g.launches;
+        *sweeps_io += g.sweeps;
+        *extra_io += g.extra;
+        return HPS_OK;
+      }
+    // new program: own copy of the op records, capture, instantiate
+    if (c->graphs.size() >= 16) {  // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].stamp < c->graphs[lru].stamp) lru = i;
+      CK(c, cudaStreamSynchronize(c->stream));
+      if (c->graphs[lru].exec) cudaGraphExecDestroy(c->graphs[lru].exec);
+      cudaFree(c->graphs[lru].d_ops); cudaFree(c->graphs[lru].d_opc);
+      c->graphs.erase(c->graphs.begin() + (long)lru);
+    }
+    hps_ctx::GraphEntry g;
+    g.key = key;
+    CK(c, cudaMalloc(&g.d_ops, nops * sizeof(Op)));
+    CK(c, cudaMalloc(&g.d_opc, nops * sizeof(OpC)));
+    CK(c, cudaMemcpy(g.d_ops, plan.ops.data(), nops * sizeof(Op), cudaMemcpyHostToDevice));
+    const uint64_t l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    CK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_plan(c, b, sc, plan, g.d_ops, g.d_opc, &g.sweeps, &g.extra);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc == HPS_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != HPS_OK || e != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(g.d_ops); cudaFree(g.d_opc);
+      c->launches = l0;
+      c->use_graphs = 0;  // fall through to direct launches from now on
+    } else {
+      g.launches = c->launches - l0;
+      g.stamp = ++c->graph_stamp;
+      c->graphs.push_back(g);
+      CK(c, cudaGraphLaunch(g.exec, c->stream));
+      *sweeps_io += g.sweeps;
+      *extra_io += g.extra;
+      return HPS_OK;
+    }
+  }
+
+  // ---- direct launches
+  if (nops > c->ops_cap) {
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_ops); cudaFree(c->d_opc); cudaFreeHost(c->h_ops);
+    c->d_ops = nullptr; c->d_opc = nullptr; c->h_ops = nullptr;
+    c->ops_cap = nops * 2;
+    CK(c, cudaMalloc(&c->d_ops, c->ops_cap * sizeof(Op)));
+    CK(c, cudaMalloc(&c->d_opc, c->ops_cap * sizeof(OpC)));
+    CK(c, cudaHostAlloc(&c->h_ops, c->ops_cap * sizeof(Op), cudaHostAllocDefault));
+  }
+  CK(c, cudaStreamSynchronize(c->stream));  // h_ops may still feed the previous copy
+  if (nops) {
+    std::memcpy(c->h_ops, plan.ops.data(), nops * sizeof(Op));
+    CK(c, cudaMemcpyAsync(c->d_ops, c->h_ops, nops * sizeof(Op), cudaMemcpyHostToDevice, c->stream));
+  }
+  return launch_plan(c, b, sc, plan, c->d_ops, c->d_opc, sweeps_io, extra_io);
 }
 
 int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint32_t first, uint32_t last,

@@ -1352,6 +1352,21 @@ size_t field_smem(const KickParams& kp, int /*threads*/) {
   return field_geom_bytes(field_geom(kp.nz, rs, block), kp.nz, block);
 }
 unsigned field_chunks(const KickParams& kp) { return (kp.nr + field_rs(kp) - 1) / field_rs(kp); }
+// sets the dynamic-shared-memory opt-in of the chain kernels for a mesh (done at SCHEFF allocation, so that no
+// function attribute has to change while a stream capture is in progress)
+cudaError_t prepare_chain_attributes(const KickParams& kp) {
+  if (deposit_smem(kp) > 48 * 1024 && !g_deposit_smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    g_deposit_smem_set = 1;
+  }
+  if (field_smem(kp, field_threads(kp)) > 48 * 1024 && !g_field_smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    g_field_smem_set = 1;
+  }
+  return cudaSuccess;
+}
 cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
                            const KickParams& kp) {
   const size_t smem = deposit_smem(kp);

@@ -52,6 +52,7 @@ void launch_lloss_pass(const LaunchCfg&, const BeamView&, DevStats*, ScDev*);
 void launch_moments(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&, int do_policy,
                     int with_lloss);
 int moments_occupancy();
+cudaError_t prepare_chain_attributes(const KickParams&);
 cudaError_t launch_deposit(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&);
 cudaError_t launch_field(const LaunchCfg&, DevStats*, ScDev*, const double* bins, double2* field, double2* part,
                          u32* tickets, const KickParams&, u32 mesh_seq);
