@@ -70,7 +70,7 @@ struct hps_ctx {
   };
   std::vector<GraphEntry> graphs;
   uint64_t graph_stamp = 0;
-  int use_graphs = 0;  // HPSIM_GRAPH=1 turns them on (default off until validated on the GPU)
+  int use_graphs = 1;  // HPSIM_GRAPH=0 turns them off
   // L2 residency (opt-in, HPSIM_L2_PERSIST=1): the particle slab of the beam being tracked becomes the stream's
   // access-policy window (persisting lines).  Measured on C2: no gain (48.7 vs 48.0 ms per pass) -- the sweeps
   // are bound by fp64 latency, not by where the 59 MB beam is read from -- so it is off by default.

@@ -21,11 +21,11 @@ fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   # launch list of the whole run (lead-in, warm-up step, timed step, profiled step); tools/launch_summary.py
   # summarises the LAST C2 pass (1 626 launches)
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-9000} --csv \
+  HPSIM_GRAPH=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-9000} --csv \
      --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-fast > gpurun_out/ncu_list.log 2>&1
   echo "ncu list rc=$?"
   for K in ${NCU_KERNELS:-k_segment}; do
-    timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s ${NCU_FULL_SKIP:-700} -c ${NCU_FULL_COUNT:-3} \
+    HPSIM_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s ${NCU_FULL_SKIP:-700} -c ${NCU_FULL_COUNT:-3} \
        -f -o gpurun_out/prof_$K python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-fast > gpurun_out/ncu_full_$K.log 2>&1
     echo "ncu full $K rc=$?"
   done
