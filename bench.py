@@ -49,7 +49,7 @@ SEG_BYTES = 112  # per particle per fused sweep: 6 fp64 + 2 u32 read and written
 # DRAM traffic of one k_segment launch at 1 Mi particles from the `ncu --set full` capture committed as
 # profiles/r1b_ncu_k_segment.txt (dram__bytes_read.sum + dram__bytes_write.sum; ncu flushes the L2 before every
 # replay, so this is the cold-cache figure: the sweep re-reads the whole 59 MB beam, its writes stay in L2)
-SEG_TRAFFIC_1MI = 58888448 + 1375744
+SEG_TRAFFIC_1MI = 58888704 + 486656
 
 
 def peaks():
