@@ -45,6 +45,25 @@ def cuda_lib():
     return K.load()
 
 
+def build_tool(name):
+    """Path of a helper executable under tests/_build (built by __graft_entry__.build()); compiled on demand with nvcc
+    when it is missing or older than its sources."""
+    import shutil
+    srcs = {"gpu_math_check": ["tests/gpu_math_check.cu"],
+            "gpu_maps_check": ["tests/gpu_maps_check.cu", "hpsim_b200/csrc/hps_plan.cpp"],
+            "host_maps": ["tests/host_maps.cu", "hpsim_b200/csrc/hps_plan.cpp"]}[name]
+    srcs = [os.path.join(ROOT, s) for s in srcs]
+    deps = srcs + [os.path.join(ROOT, "hpsim_b200", "csrc", h) for h in ("hps_kernels.cuh", "hps_math.cuh", "hps_internal.h")]
+    exe = os.path.join(ROOT, "tests", "_build", name)
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        flags = ["-O2", "-std=c++17", "-x", "cu", "-arch=sm_100a"] if name == "host_maps" else \
+                ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo"]
+        subprocess.check_call([nvcc] + flags + ["-o", exe] + srcs)
+    return exe
+
+
 class math_mode:
     """with math_mode("reference"): ... -- arithmetic of the segment kernel on the current device (hps_ctx_set_math)."""
 

@@ -224,8 +224,7 @@ def test_branch_free_arithmetic_is_bit_exact():
     (tests/gpu_math_check.cu)."""
     import re
     import subprocess
-    exe = os.path.join(H.ROOT, "tests", "_build", "gpu_math_check")
-    assert os.path.exists(exe), "build it with __graft_entry__.build()"
+    exe = H.build_tool("gpu_math_check")
     p = subprocess.run([exe, "30"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     m = re.search(r"MATHCHECK pairs (\d+) div (\d+) rcp (\d+) sqrt (\d+) udiv (\d+) fmod (\d+)", p.stdout)
@@ -242,8 +241,7 @@ def test_reference_order_maps_bit_identical_per_op():
     see test_branch_free_arithmetic_is_bit_exact): a 1-ulp difference in < 0.1 % of the evaluations is accepted."""
     import re
     import subprocess
-    exe = os.path.join(H.ROOT, "tests", "_build", "gpu_maps_check")
-    assert os.path.exists(exe), "build it with __graft_entry__.build()"
+    exe = H.build_tool("gpu_maps_check")
     p = subprocess.run([exe, H.LATTICE, "62", "6537", "256"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     print(p.stdout)

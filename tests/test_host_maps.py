@@ -16,13 +16,8 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 @pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
 def test_fast_maps_match_reference_order_maps():
-    out_dir = os.path.join(ROOT, "tests", "_build")
-    os.makedirs(out_dir, exist_ok=True)
-    exe = os.path.join(out_dir, "host_maps")
-    srcs = [os.path.join(ROOT, "tests", "host_maps.cu"), os.path.join(ROOT, "hpsim_b200", "csrc", "hps_plan.cpp")]
-    deps = srcs + [os.path.join(ROOT, "hpsim_b200", "csrc", "hps_kernels.cuh")]
-    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-        subprocess.check_call([NVCC, "-O2", "-std=c++17", "-x", "cu", "-arch=sm_100a", "-o", exe] + srcs)
+    import harness as H
+    exe = H.build_tool("host_maps")
     # TBDB02 .. 48DT: every drift, quad and RF-gap record of the LANSCE linac, 16 random particles each
     p = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "lansce.lat"), "62", "6537", "16", "7"],
                        capture_output=True, text=True, timeout=600)
