@@ -153,8 +153,32 @@ static int track_main(int argc, char** argv) {
   return 0;
 }
 
+// planner only: host_maps plan <lattice> <first> <last> <interval> -- counts of the program hps_simulate would launch
+static int plan_main(int argc, char** argv) {
+  std::vector<hps_elem> lat;
+  if (argc < 6 || !read_lattice(argv[2], lat)) { fprintf(stderr, "plan: bad arguments\n"); return 2; }
+  EngineState eng;
+  BeamHost bh = {939.294, -1.0, 0.015, 201.25, 0.75, 1u << 16};
+  ScHost sc;
+  sc.on = true; sc.nr = 32; sc.nz = 128; sc.adj_bunch = 3; sc.interval = atof(argv[5]); sc.adj_bunch_w = 0.8; sc.remesh_val = 0.02;
+  Plan plan = build_plan(lat, (u32)atoi(argv[3]), (u32)atoi(argv[4]), eng, bh, sc);
+  if (!plan.error.empty()) { fprintf(stderr, "plan: %s\n", plan.error.c_str()); return 2; }
+  size_t kick_segs = 0, max_ops = 0, fin_aper = 0;
+  for (const Segment& s : plan.segs) {
+    kick_segs += s.kick_follows;
+    max_ops = s.op_count > max_ops ? s.op_count : max_ops;
+    fin_aper += (s.fin_mode & 3) == FIN_APERTURE;
+  }
+  size_t nkick_ops = 0, ngap = 0;
+  for (const Op& op : plan.ops) { nkick_ops += op.type == OP_SC_KICK; ngap += op.type == OP_GAP_FIRST; }
+  printf("PLAN ops %zu segments %zu kicks %u kick_segments %zu kick_ops %zu gaps %zu aperture_syncs %zu max_ops_per_segment %zu "
+         "freq %.4f design_w %.6f\n", plan.ops.size(), plan.segs.size(), plan.n_kicks, kick_segs, nkick_ops, ngap, fin_aper, max_ops, bh.freq, bh.design_w);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc > 1 && strcmp(argv[1], "track") == 0) return track_main(argc, argv);
+  if (argc > 1 && strcmp(argv[1], "plan") == 0) return plan_main(argc, argv);
   if (argc < 6) { fprintf(stderr, "usage: host_maps lattice first last n seed\n"); return 2; }
   std::vector<hps_elem> lat;
   if (!read_lattice(argv[1], lat)) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }

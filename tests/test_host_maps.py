@@ -28,3 +28,25 @@ def test_fast_maps_match_reference_order_maps():
     assert int(m.group(2)) == 0, p.stdout
     for name in ("drift", "quad_half", "gap_first", "gap_second", "sc_kick"):
         assert re.search(rf"^{name}\s+ops\s+\d+", p.stdout, re.M), p.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+@pytest.mark.parametrize("first,last,kicks,gaps", [(62, 6537, 8894, 5124), (62, 129, 236, 0), (130, 478, 406, None), (62, 710, 967, None)])
+def test_planner_counts(first, last, kicks, gaps):
+    """The host planner (hps_plan.cpp) on the LANSCE lattice at interval 0.025 m: the kick counts SURVEY.md 8d derives
+    from the reference's element loop (drifts ceil(L / interval) kicks, every quad / gap / dipole one), the RF gaps of
+    the full linac, one segment per kick plus the sweeps that end at an "in" aperture or at the end of the range, and
+    the state the engine leaves behind (805 MHz and the 800 MeV design energy after the last CCL gap)."""
+    import harness as H
+    exe = H.build_tool("host_maps")
+    p = subprocess.run([exe, "plan", os.path.join(ROOT, "tests", "golden", "lansce.lat"), str(first), str(last), "0.025"],
+                       capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    m = dict(re.findall(r"(\w+) ([0-9.]+)", p.stdout))
+    assert int(m["kicks"]) == kicks == int(m["kick_segments"]) == int(m["kick_ops"]), p.stdout
+    if gaps is not None:
+        assert int(m["gaps"]) == gaps, p.stdout
+    assert int(m["segments"]) == kicks + 1 + int(m["aperture_syncs"]), p.stdout
+    assert int(m["max_ops_per_segment"]) <= 24
+    if last == 6537:
+        assert abs(float(m["freq"]) - 805.0) < 1e-9 and 795.0 < float(m["design_w"]) < 805.0, p.stdout
