@@ -3,7 +3,7 @@ run of the same beam -- loss flags bit-exact, coordinates to 1e-9 of an rms (the
 summation order of the moment / mesh reductions).  Rank 0 prints one JSON line.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-      tests/sharded_check.py [n] [first] [last]
+      tests/sharded_check.py [n] [first] [last] [mesh_size_cutoff_w]
 """
 import json
 import os
@@ -23,6 +23,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
     first = sys.argv[2] if len(sys.argv) > 2 else "TBDB02"
     last = sys.argv[3] if len(sys.argv) > 3 else "01QM10"
+    mesh_w = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0   # optional: SetMeshSizeCutoffW
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -33,6 +34,8 @@ def main():
     mode = HPSim.init_sharding(rank, world, ids[0])
 
     case = H.Case(lib, n=n, sc=True)
+    if mesh_w:
+        case.spch.set_mesh_size_cutoff_w(mesh_w)
     run = case.run(first, last)
     st = case.state()            # same call sequence as the single-GPU run below: every Update* call can
     mom = case.moments()         # mark more longitudinal losses (H3), so the order matters
@@ -48,6 +51,8 @@ def main():
     # single-GPU run of the same beam on a context without a communicator
     HPSim._ctx_cache.clear()  # the sharded objects keep their own context alive
     one = H.Case(lib, n=n, sc=True)
+    if mesh_w:
+        one.spch.set_mesh_size_cutoff_w(mesh_w)
     run1 = one.run(first, last)
     ref = one.state()
     rep = H.compare(full, ref, 1e-9)

@@ -140,3 +140,42 @@ def test_dbconnection_and_beamline_from_db():
         assert len(conn.get_epics_channels()) > 0
     finally:
         HPSim._use_library(None)
+
+
+def test_set_db_epics_and_set_db_model_reach_the_lattice():
+    """hps.set_db_epics / set_db_model: a PV write fires the database triggers (they need the
+    vendored sqlite math extension), the *_model columns are re-read and the changed element is pushed down through
+    hps_lattice_update_elem.  PV TDDB001E04 is the amplitude set point of the main buncher TDDB01 (the scan script's PV)."""
+    import os
+    db = "/root/reference/db"
+    if not os.path.isdir(db):
+        pytest.skip("reference databases are not on this machine")
+    HPSim._use_library(H.oracle_lib())
+    try:
+        conn = HPSim.DBConnection(os.path.join(db, "tbtd.db"))
+        conn.load_lib(os.path.join(db, "lib", "libsqliteext.so"))
+        conn.clear_model_index()
+        bl = HPSim.BeamLine(conn)
+        i = bl.index("TDDB01")
+        lib = bl._c.lib
+        e0 = K.Elem()
+        assert lib.hps_lattice_get_elem(bl.h, i, e0) == 0
+        v0 = float(HPSim.get_db_epics("TDDB001E04", conn))
+        HPSim.set_db_epics("TDDB001E04", str(v0 * 1.05), conn, bl)
+        assert abs(float(HPSim.get_db_epics("TDDB001E04", conn)) - v0 * 1.05) < 1e-9
+        e1 = K.Elem()
+        assert lib.hps_lattice_get_elem(bl.h, i, e1) == 0
+        assert e1.p[0] != e0.p[0] and abs(e1.p[0] / e0.p[0] - 1.0) < 0.2     # buncher voltage_model follows the PV
+        assert [e1.p[k] for k in range(1, 6)] == [e0.p[k] for k in range(1, 6)]
+        HPSim.set_db_epics("TDDB001E04", str(v0), conn, bl)
+        e2 = K.Elem()
+        lib.hps_lattice_get_elem(bl.h, i, e2)
+        assert e2.p[0] == e0.p[0]
+        # set_db_model writes a *_model column directly
+        f0 = HPSim.get_db_model("TDDB01", "phase_offset_cal", conn)
+        HPSim.set_db_model("TDDB01", "phase_offset_cal", "12.5", conn, bl)
+        assert float(HPSim.get_db_model("TDDB01", "phase_offset_cal", conn)) == 12.5
+        if f0 != "":
+            HPSim.set_db_model("TDDB01", "phase_offset_cal", f0, conn, bl)
+    finally:
+        HPSim._use_library(None)
