@@ -267,14 +267,26 @@ class Beam:
     def restore_intermediate_beam(self): self._c.check(self._c.lib.hps_beam_restore(self.h, 1))
 
     def print_to(self, file: str, msg: str = "") -> None:
-        """Beam::PrintToFile (beam.cpp:670-707)"""
+        """Beam::PrintToFile (beam.cpp:670-707): the five labelled header lines the reference's reader looks for
+        (`Info`, `Charge`, `Mass`, `Current`, `Frequency`; header values with the default 6 significant digits of an
+        ostream), then one row of 15-significant-digit coordinates + the two loss flags per particle."""
+        if self.n_local != self.n:
+            raise K.HpsError(K.ERR_STATE, "print_to of a particle-sharded beam would write this rank's shard only; gather the arrays "
+                             "(Beam.offset / Beam.stride) and write them from one rank")
         d = self._arrays()
+
+        def num(v):  # the reference's ContainOnlyNumbers (utility.cpp:98-110) does not accept a '+' in a row
+            return f"{v:.15g}".replace("e+", "e")
         with open(file, "w") as f:
-            if msg:
-                f.write(msg + "\n")
-            f.write(f"{self.get_mass()} {self.get_charge()} {self._c.lib.hps_beam_get_current(self.h)} {self.get_frequency()}\n")
+            f.write(f"Info {msg}\n")
+            f.write(f"Charge  {self.get_charge():g}\n")
+            f.write(f"Mass {self.get_mass():g}\n")
+            f.write(f"Current {self._c.lib.hps_beam_get_current(self.h):g}\n")
+            f.write(f"Frequency {self.get_frequency():g}\n")
+            cols = [d[k] for k in ("x", "xp", "y", "yp", "phi", "w")]
+            loss, lloss = d["loss"], d["lloss"]
             for i in range(self.n_local):
-                f.write(" ".join(f"{d[k][i]:.15g}" for k in ("x", "xp", "y", "yp", "phi", "w")) + f" {d['loss'][i]} {d['lloss'][i]}\n")
+                f.write("  ".join(num(c[i]) for c in cols) + f"  {loss[i]}  {lloss[i]}\n")
 
     def set_ref_w(self, w): self._c.check(self._c.lib.hps_beam_set_ref_w(self.h, float(w)))
     def set_ref_phi(self, phi): self._c.check(self._c.lib.hps_beam_set_ref_phi(self.h, float(phi)))
@@ -403,31 +415,44 @@ class Beam:
         self._c.check(self._c.lib.hps_beam_shift(self.h, m[axis], float(val)))
 
 
+def _only_numbers(line: str) -> bool:
+    """ContainOnlyNumbers (util/src/utility.cpp:98-110): digits, '.', '-', 'e' / 'E' and blanks"""
+    t = line.replace(" ", "")
+    return bool(t) and all(ch.isdigit() or ch in ".-eE" for ch in t)
+
+
+def _first_number(line: str) -> float:
+    """GetFirstNumberInString (util/src/utility.cpp:31-85): the first signed decimal number of a line"""
+    import re
+    m = re.search(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?", line)
+    return float(m.group(0)) if m else 0.0
+
+
 def _read_beam_file(path):
-    """Beam::InitBeamFromFile / UpdateBeamFromFile (beam.cpp:179-298): optional comment lines,
-    a header line `mass charge current [freq]`, then >= 6 columns per particle."""
-    rows, head = [], None
+    """Beam::InitBeamFromFile / UpdateBeamFromFile (beam.cpp:179-298): header lines are found by keyword, case-insensitive
+    (`charge`, `mass`, `current`, `frequency`; the first number on the line is the value) and each of them is mandatory;
+    every line made of numbers only is a particle row with at least 6 columns (+ loss, + lloss)."""
+    head, rows = {}, []
     with open(path) as f:
         for line in f:
-            t = line.split()
-            if not t:
-                continue
-            try:
-                vals = [float(v) for v in t]
-            except ValueError:
-                continue
-            if head is None and len(vals) < 6:
-                head = vals
-            else:
-                rows.append(vals)
-    a = np.array([r[:6] for r in rows], dtype=np.float64)
-    has_loss = all(len(r) >= 8 for r in rows)
+            line = line.rstrip("\n")
+            low = line.lower()
+            for key in ("charge", "mass", "current", "frequency"):
+                if key in low and any(ch.isdigit() for ch in line):
+                    head[key] = _first_number(line)
+            if _only_numbers(line):
+                rows.append(line.split())
+    for key in ("charge", "mass", "current", "frequency"):
+        if key not in head:
+            raise ValueError(f"Beam input file error: must define {key} value!")  # the reference prints this and exits
+    if not rows:
+        raise ValueError("Beam input file error: no particle rows")
+    a = np.array([[float(v) for v in r[:6]] for r in rows], dtype=np.float64)
+    ncol = len(rows[-1])  # like the reference, the width of the last row decides which flag columns are used
     out = {k: a[:, i].copy() for i, k in enumerate(("x", "xp", "y", "yp", "phi", "w"))}
-    out["loss"] = np.array([r[6] for r in rows], dtype=np.uint32) if has_loss else None
-    out["lloss"] = np.array([r[7] for r in rows], dtype=np.uint32) if has_loss else None
-    head = head or [0.0, 0.0, 0.0]
-    out["mass"], out["charge"], out["current"] = head[0], head[1], head[2]
-    out["freq"] = head[3] if len(head) > 3 else 0.0
+    out["loss"] = np.array([int(float(r[6])) for r in rows], dtype=np.uint32) if ncol > 6 else None
+    out["lloss"] = np.array([int(float(r[7])) for r in rows], dtype=np.uint32) if ncol > 7 else None
+    out["mass"], out["charge"], out["current"], out["freq"] = head["mass"], head["charge"], head["current"], head["frequency"]
     return out
 
 

@@ -238,6 +238,8 @@ int main(int argc, char** argv) {
       beam.GetAvgRelativePhi(), beam.GetSigRelativePhi(), beam.GetRefEnergy(), beam.GetRefPhase(),
       beam.freq, beam.current, beam.design_w};
   WriteBeamFile(S(cfg, "beam_out", "beam_out.bin"), beam, stats);
+  // optional: the reference's own text dump (Beam::PrintToFile, beam.cpp:670-707)
+  if (cfg.count("print_to")) beam.PrintToFile(S(cfg, "print_to", "beam.txt"), S(cfg, "print_msg", "ref_driver"));
   std::cout << "ref_driver: loss=" << stats[0] << " lloss=" << stats[1] << " good=" << stats[2] << std::endl;
   return 0;
 }

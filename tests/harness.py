@@ -20,6 +20,10 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libhpsim_oracle.so")
 REF_DP = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dp")
 REF_SP = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 LATTICE = os.path.join(ROOT, "tests", "golden", "lansce.lat")
+# the reference's linac databases + the sqlite math extension their triggers need, vendored as test data
+DB_DIR = os.path.join(ROOT, "tests", "golden", "db")
+SQLITE_EXT = os.path.join(DB_DIR, "libsqliteext.so")
+DB_FILES = [os.path.join(DB_DIR, f) for f in ("tbtd.db", "dtl.db", "trst.db", "ccl.db")]
 
 # C1 beam recipe
 DC = dict(ax=0.095, bx=47.0, ex=0.00327, ay=-0.102, by=60.0, ey=0.002514, dphi=np.pi, sync_phi=0.0, sync_w=0.7518)
@@ -233,6 +237,23 @@ def run_reference(workdir, n, first, last, sc=True, double=True, nr=32, nz=128, 
         cfg += [f"beam_in {beam_in}", f"freq {float(freq)!r}"]
         if design_w is not None:
             cfg.append(f"design_w {float(design_w)!r}")  # float(): repr(np.float64) is not a C number
+    path = os.path.join(workdir, "ref.cfg")
+    with open(path, "w") as f:
+        f.write("\n".join(cfg) + "\n")
+    p = subprocess.run([exe, path], capture_output=True, text=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError(f"ref_driver failed ({p.returncode}): {p.stdout[-2000:]} {p.stderr[-2000:]}")
+    return read_beam_file(out), p.stdout
+
+
+def run_reference_cfg(workdir, n, beam_lines, first, last, sc=True, double=True, extra=(), timeout=900):
+    """ref_driver with an explicit beam recipe (`beam_lines`: config lines such as "gen waterbag", "seed 1", ...)."""
+    exe = REF_DP if double else REF_SP
+    os.makedirs(workdir, exist_ok=True)
+    out = os.path.join(workdir, "ref_out.bin")
+    cfg = [f"lattice {LATTICE}", f"n {n}", f"mass {MASS}", f"charge {CHARGE}", f"current {CURRENT}", f"sc {1 if sc else 0}",
+           "nr 32", "nz 128", "interval 0.025", "adj_bunch 3", "adj_bunch_cutoff_w 0.8", "remesh_threshold 0.02",
+           f"first {first}", f"last {last}", f"beam_out {out}"] + list(beam_lines) + list(extra)
     path = os.path.join(workdir, "ref.cfg")
     with open(path, "w") as f:
         f.write("\n".join(cfg) + "\n")

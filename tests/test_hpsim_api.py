@@ -115,9 +115,7 @@ def test_oracle_kick_count_matches_planner_formula():
 
 def test_lattice_loader_against_reference_dbs():
     import os
-    db = "/root/reference/db"
-    if not os.path.isdir(db):
-        pytest.skip("reference databases are not on this machine")
+    db = H.DB_DIR
     t = L.load_from_dbs([os.path.join(db, f) for f in ("tbtd.db", "dtl.db", "trst.db", "ccl.db")])
     g = H.lattice()
     assert len(t) == len(g) and np.array_equal(t, g)
@@ -125,9 +123,7 @@ def test_lattice_loader_against_reference_dbs():
 
 def test_dbconnection_and_beamline_from_db():
     import os
-    db = "/root/reference/db"
-    if not os.path.isdir(db):
-        pytest.skip("reference databases are not on this machine")
+    db = H.DB_DIR
     HPSim._use_library(H.oracle_lib())
     try:
         conn = HPSim.DBConnection(os.path.join(db, "tbtd.db"))
@@ -147,13 +143,11 @@ def test_set_db_epics_and_set_db_model_reach_the_lattice():
     vendored sqlite math extension), the *_model columns are re-read and the changed element is pushed down through
     hps_lattice_update_elem.  PV TDDB001E04 is the amplitude set point of the main buncher TDDB01 (the scan script's PV)."""
     import os
-    db = "/root/reference/db"
-    if not os.path.isdir(db):
-        pytest.skip("reference databases are not on this machine")
+    db = H.DB_DIR
     HPSim._use_library(H.oracle_lib())
     try:
         conn = HPSim.DBConnection(os.path.join(db, "tbtd.db"))
-        conn.load_lib(os.path.join(db, "lib", "libsqliteext.so"))
+        conn.load_lib(H.SQLITE_EXT)
         conn.clear_model_index()
         bl = HPSim.BeamLine(conn)
         i = bl.index("TDDB01")
