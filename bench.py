@@ -61,10 +61,10 @@ _t = os.path.join(ROOT, "profiles", "r2_seg_traffic.json")
 if os.path.exists(_t):
     for _k, _v in json.load(open(_t)).items():
         SEG_TRAFFIC[int(_k)] = (_v["bytes"], _v["source"])
-# particle count of the reference arm on a full-linac range: the reference needs ~0.1 ms per kick per 10 Ki particles
-# (double-precision tables) on top of ~0.4 ms of launch latency per kick, and --steps + --warmup passes must end within a
-# few minutes
-REF_N = {"c4": 1 << 16, "c1": 1 << 16, "c3": 1 << 19, "c2": 1 << 20, "c5": 1 << 19}
+# particle count of the reference arm.  Measured on B200 (profiles/r2_reference_sweep.txt), TBDB02->48DT, double tables:
+# 64 Ki particles 5.1 s per pass (8.3e7 steps/s), 256 Ki 11.7 s (1.45e8 steps/s): the reference is launch-bound below and
+# atomics-bound above; 25 passes (--steps 20 --warmup 5) at 256 Ki take ~5 min, 1 Mi would take ~15
+REF_N = {"c4": 1 << 18, "c1": 1 << 16, "c3": 1 << 19, "c2": 1 << 20, "c5": 1 << 19}
 
 
 def peaks():

@@ -406,6 +406,13 @@ class Beam:
     def get_emittance_y(self): return self._emit("y_emit")
     def get_emittance_z(self): return self._emit("z_emit")
 
+    def moment_stats(self):
+        """Diagnostics of the fused moment chain (hps_beam_moment_stats; no reference counterpart)."""
+        out = (C.c_uint64 * 3)()
+        err, m = C.c_double(), C.c_double()
+        self._c.check(self._c.lib.hps_beam_moment_stats(self.h, out, C.byref(err), C.byref(m)))
+        return {"fused": int(out[0]), "fallback": int(out[1]), "deferred": int(out[2]), "pivot_err_max": err.value, "pivot_margin": m.value}
+
     def apply_cut(self, coord, lo, hi):
         m = {"x": K.X, "y": K.Y, "w": K.W, "p": K.PHI}
         self._c.check(self._c.lib.hps_beam_cut(self.h, m[coord.lower()], float(lo), float(hi)))

@@ -108,6 +108,7 @@ PROTOTYPES = {
     "hps_beam_cut": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double]),
     "hps_beam_update": (C.c_int, [_vp, C.c_int]),
     "hps_beam_get": (C.c_int, [_vp, C.c_int, _dp]),
+    "hps_beam_moment_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), _dp, _dp]),
     "hps_lattice_create": (_vp, [_vp, _vp, C.c_uint32]),
     "hps_lattice_destroy": (None, [_vp]),
     "hps_lattice_size": (C.c_uint32, [_vp]),

@@ -48,6 +48,9 @@ struct hps_ctx {
   // on C2 it loses to the three PDL-chained kernels (48.2 vs 44.2 ms per pass): the 64-register cap of a fully
   // resident grid spills in the deposit loop, and a grid barrier costs as much as a programmatic kernel boundary.
   int fused = 0;
+  // the whole moment chain of a kick in the epilogue of the sweep before it (FIN_KICK_FUSED); HPSIM_FUSED_MOMENTS=0 keeps
+  // the stand-alone moment kernel of round 1 (k_moments re-reads 40 B/particle per kick)
+  int fused_moments = 1;
   // program upload buffers
   Op* d_ops = nullptr;
   OpC* d_opc = nullptr;  // device-prepared constants, parallel to d_ops
@@ -99,6 +102,7 @@ struct hps_beam {
   double* c[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   u32 *loss = nullptr, *lloss = nullptr;
   DevStats* st = nullptr;
+  DeferList* defer = nullptr;  // side list of the fused-moment epilogue (hps_internal.h)
   double* tmp = nullptr;  // n doubles of scratch (relative-phase download)
   struct Slot { char* slab = nullptr; bool valid = false; double design_w, freq, current; } slot[2];
   size_t slab_bytes = 0;
@@ -282,11 +286,11 @@ void UpdateStatForSpaceCharge(hps_beam* b) {
   KickParams kp;
   std::memset(&kp, 0, sizeof(kp));
   kp.n_global = b->h.n_global; kp.mass = b->h.mass;
-  launch_segment(l, v, nullptr, c->d_ops, c->d_opc, 0, FIN_KICK, 0, c->compat, b->st, nullptr, nullptr, kp);
+  launch_segment(l, v, nullptr, c->d_ops, c->d_opc, 0, FIN_KICK, 0, c->compat, b->st, nullptr, nullptr, kp, nullptr, nullptr);
   xr_after_reduce(c, l, FK_SEGMENT, FIN_KICK, 0, nullptr, nullptr, v, b->st, nullptr, nullptr);
   launch_lloss_pass(l, v, b->st, nullptr);
   xr_after_reduce(c, l, FK_LLOSS, 0, 0, nullptr, nullptr, v, b->st, nullptr, nullptr);
-  launch_moments(l, v, b->st, nullptr, nullptr, kp, 0, 0);
+  launch_moments(l, v, b->st, nullptr, nullptr, kp, 0, 0, 0);
   xr_after_reduce(c, l, FK_MOMENTS, 0, 0, nullptr, &kp, v, b->st, nullptr, nullptr);
   c->launches += 3;
 }
@@ -377,6 +381,7 @@ hps_ctx* hps_ctx_create(int device) {
     c->seg_variant = math_variant(c->seg_variant % 10, v[0] == 'r' ? HPS_MATH_REFERENCE : (v[0] == 'n' ? HPS_MATH_REFERENCE_NVCC : HPS_MATH_FAST));
   if (const char* v = getenv("HPSIM_PDL")) c->pdl = atoi(v);
   if (const char* v = getenv("HPSIM_FUSED")) c->fused = atoi(v);
+  if (const char* v = getenv("HPSIM_FUSED_MOMENTS")) c->fused_moments = atoi(v);
   if (const char* v = getenv("HPSIM_GRAPH")) c->use_graphs = atoi(v);
   if (const char* v = getenv("HPSIM_L2_PERSIST")) c->l2_persist = atoi(v);
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
@@ -560,10 +565,11 @@ hps_beam* hps_beam_create(hps_ctx* c, uint64_t n_global, double mass, double cha
   b->slab_bytes = 6 * da + 2 * ua;
   bool ok = cudaMalloc(&b->slab, b->slab_bytes) == cudaSuccess && cudaMemsetAsync(b->slab, 0, b->slab_bytes, c->stream) == cudaSuccess &&
             cudaMalloc(&b->st, sizeof(DevStats)) == cudaSuccess && cudaMemsetAsync(b->st, 0, sizeof(DevStats), c->stream) == cudaSuccess &&
+            cudaMalloc(&b->defer, sizeof(DeferList)) == cudaSuccess && cudaMemsetAsync(b->defer, 0, 8, c->stream) == cudaSuccess &&
             cudaMalloc(&b->tmp, (size_t)b->n_alloc * sizeof(double)) == cudaSuccess;
   if (!ok) {
     fail(c, HPS_ERR_CUDA, std::string("beam allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
-    cudaFree(b->slab); cudaFree(b->st); cudaFree(b->tmp);
+    cudaFree(b->slab); cudaFree(b->st); cudaFree(b->tmp); cudaFree(b->defer);
     delete b;
     return nullptr;
   }
@@ -582,7 +588,7 @@ void hps_beam_destroy(hps_beam* b) {
     b->ctx->l2_window_base = nullptr;
     b->ctx->l2_window_bytes = 0;
   }
-  cudaFree(b->slab); cudaFree(b->st); cudaFree(b->tmp);
+  cudaFree(b->slab); cudaFree(b->st); cudaFree(b->tmp); cudaFree(b->defer);
   for (auto& s : b->slot) cudaFree(s.slab);
   delete b;
 }
@@ -815,6 +821,17 @@ int hps_beam_update(hps_beam* b, int id) {
   }
   return HPS_OK;
 }
+int hps_beam_moment_stats(hps_beam* b, uint64_t out[3], double* pivot_err_max, double* pivot_margin) {
+  hps_ctx* c = b->ctx;
+  cudaSetDevice(c->device);
+  DevStats h;
+  CK(c, cudaMemcpyAsync(&h, b->st, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (out) { out[0] = h.n_fused; out[1] = h.n_fallback; out[2] = h.n_deferred; }
+  if (pivot_err_max) *pivot_err_max = h.pivot_err_max;
+  if (pivot_margin) *pivot_margin = h.pivot_m;
+  return HPS_OK;
+}
 int hps_beam_get(hps_beam* b, int id, double* out) {
   hps_ctx* c = b->ctx;
   if (id < 0 || id >= HPS_STAT_COUNT) return fail(c, HPS_ERR_ARG, "unknown stat id");
@@ -1007,14 +1024,18 @@ static int launch_plan(hps_ctx* c, hps_beam* b, hps_scheff* sc, const Plan& plan
   launch_prepare_ops(l, d_ops, d_opc, (int)plan.ops.size(), b->h.mass, b->h.charge);
   c->launches++;
   uint64_t sweeps = 0, extra = 0;
+  // fused moments: the sweep in front of a kick finishes the kick's statistics and the Scheff::Start policy itself
+  const bool fused_mom = c->fused_moments && sc && !c->fused && c->xr.mode != XR_NCCL;
   for (const Segment& s : plan.segs) {
     const int dirty = dirty_mask(plan.ops.data() + s.op_begin, s.op_count);
+    const bool fm = fused_mom && s.kick_follows && (s.fin_mode & 3) == FIN_KICK;
+    const int fin_mode = fm ? ((s.fin_mode & ~3) | FIN_KICK_FUSED) : s.fin_mode;
     prof_mark(c, HPS_PROF_SEGMENT);
-    launch_segment(l, v, plan.ops.data() + s.op_begin, d_ops + s.op_begin, d_opc + s.op_begin, (int)s.op_count, s.fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
-                   sc ? sc->field : nullptr, s.kp);
+    launch_segment(l, v, plan.ops.data() + s.op_begin, d_ops + s.op_begin, d_opc + s.op_begin, (int)s.op_count, fin_mode, dirty, c->compat, b->st, sc ? sc->dev : nullptr,
+                   sc ? sc->field : nullptr, s.kp, sc ? sc->bins : nullptr, b->defer);
     c->launches++;
     sweeps++;
-    if (s.fin_mode != FIN_NONE) {
+    if (s.fin_mode != FIN_NONE && !fm) {
       int rc = xr_after_reduce(c, l, FK_SEGMENT, s.fin_mode, 0, nullptr, nullptr, v, b->st, sc ? sc->dev : nullptr, nullptr);
       if (rc) return rc;
     }
@@ -1032,7 +1053,7 @@ static int launch_plan(hps_ctx* c, hps_beam* b, hps_scheff* sc, const Plan& plan
       continue;
     }
     const int merged = c->xr.mode != XR_NCCL;  // K2 rides inside K3 (grid barrier) unless its finaliser is a separate kernel
-    if (!merged) {
+    if (!merged) {  // (XR_NCCL never runs the fused epilogue)
       prof_mark(c, HPS_PROF_LLOSS);
       launch_lloss_pass(l, v, b->st, sc->dev);
       c->launches++;
@@ -1040,7 +1061,7 @@ static int launch_plan(hps_ctx* c, hps_beam* b, hps_scheff* sc, const Plan& plan
       if (rc) return rc;
     }
     prof_mark(c, HPS_PROF_MOMENTS);
-    launch_moments(l, v, b->st, sc->dev, sc->bins, s.kp, 1, merged);
+    launch_moments(l, v, b->st, sc->dev, sc->bins, s.kp, 1, merged, fm ? 1 : 0);
     rc = xr_after_reduce(c, l, FK_MOMENTS, 0, 1, nullptr, &s.kp, v, b->st, sc->dev, sc->bins);
     if (rc) return rc;
     prof_mark(c, HPS_PROF_DEPOSIT);
@@ -1089,7 +1110,7 @@ static int run_range(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, 
     }
     const uint64_t env[12] = {(uint64_t)(uintptr_t)b->slab, (uint64_t)(uintptr_t)b->st, b->n, b->offset, (uint64_t)(uintptr_t)(sc ? sc->dev : nullptr),
                               (uint64_t)(uintptr_t)(sc ? sc->bins : nullptr), (uint64_t)(uintptr_t)(sc ? sc->field : nullptr),
-                              (uint64_t)c->seg_variant, (uint64_t)c->fused, (uint64_t)c->compat, (uint64_t)c->pdl,
+                              (uint64_t)c->seg_variant, (uint64_t)(c->fused | (c->fused_moments << 4)), (uint64_t)c->compat, (uint64_t)c->pdl,
                               (uint64_t)(uintptr_t)(sc ? sc->field_part : nullptr)};
     key = fnv(key, env, sizeof(env));
     const double bm[2] = {b->h.mass, b->h.charge};

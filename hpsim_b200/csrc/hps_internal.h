@@ -59,6 +59,8 @@ enum FinMode {
   FIN_NONE = 0,
   FIN_KICK = 1,      // first stage of Beam::UpdateStatForSpaceCharge (good count, <phi>_good, lloss trigger)
   FIN_APERTURE = 2,  // Beam::UpdateLoss + UpdateAvgXY ahead of an "in" aperture
+  FIN_KICK_FUSED = 3 // the WHOLE of Beam::UpdateStatForSpaceCharge + the Scheff::Start policy in the sweep's epilogue
+                     // (moment sums about a predicted pivot phase, exact re-centring; hps_kernels.cu, "fused moments")
 };
 #define FIN_FREQ 4   // OR-ed in: segment contains OP_FREQ_CHANGE -> refresh phi_avg like Beam::ChangeFrequency
 
@@ -67,6 +69,28 @@ struct DevStats {
   u32 num_loss, num_lloss, num_good;
   u32 need_lloss_pass;       // set by FIN_KICK when some particle crosses <phi>_good + 3 pi
   double phi_r_ref;          // reference phase of the (virtual) relative-phase array
+  // fused moments (FIN_KICK_FUSED): the epilogue sums the relative phase about a PREDICTED <phi>_good (a pilot particle
+  // carried through the segment's maps) and re-centres exactly afterwards; particles within `pivot_m` of a decision
+  // boundary (2 pi wrap of the relative phase, the <phi>_good + 3 pi longitudinal-loss threshold) are deferred to a
+  // side list and resolved with the true <phi>_good.  When the prediction misses by more than pivot_m, or the list
+  // overflows, moments_fallback asks the stand-alone moment kernel (k_moments) to redo the kick's statistics.
+  u32 moments_fallback;
+  u32 pad0;
+  double pivot_m;            // margin in force [rad]; adapted from the prediction errors seen
+  double pivot_err_max;      // largest |<phi>_good - pivot| of the fused kicks so far (diagnostics)
+  unsigned long long n_fused, n_fallback, n_deferred;  // kicks finished in the epilogue / by k_moments; deferred particles
+};
+
+// side list of the fused-moment epilogue: particles whose classification needs the true <phi>_good
+#define HPS_DEFER_CAP 65536u
+struct DeferEntry {
+  double phi, x, y, w;
+  unsigned long long tag;  // local particle index | flags << 32  (1 alive, 2 lloss already set, 4 lloss candidate)
+};
+struct DeferList {
+  u32 count;   // entries appended by the sweep (may exceed HPS_DEFER_CAP: overflow)
+  u32 pad;
+  DeferEntry e[HPS_DEFER_CAP];
 };
 
 struct ScDev {
@@ -125,7 +149,7 @@ struct BeamView {
 // flag, no system-scope fence, one one-way trip of latency.  Two parity buffers suffice: a rank can run
 // at most one exchange ahead of its slowest peer.
 #define HPS_XR_MAXR 8
-#define HPS_XR_NS 16            // doubles per small-reduction slot (>= every kernel's NS)
+#define HPS_XR_NS 24            // doubles per small-reduction slot (>= every kernel's NS)
 #define HPS_XR_BINS_CAP 25608   // nr*nz + 2 (count, max|phi|) 64-bit values; 8*nr*nz <= 200 KB
 struct XrBox {
   unsigned long long data[2][HPS_XR_MAXR][2 * HPS_XR_NS];       // LL words: payload | seq << 32

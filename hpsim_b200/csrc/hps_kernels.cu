@@ -6,7 +6,7 @@
 
 namespace hps {
 
-enum { SEG_NS = 8, MOM_NS = 12, LL_NS = 4, STAT_NS = 8 };
+enum { SEG_NS = 16, MOM_NS = 12, LL_NS = 4, STAT_NS = 8 };
 
 // ================================================================================================
 // K1: fused segment sweep
@@ -154,14 +154,298 @@ __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const 
 #undef EACH_ALIVE
 }
 
-__device__ __forceinline__ void seg_accumulate(double (&acc)[SEG_NS], const Pt& p, u32 ll, double phi_fc, bool live_fc) {
+// The epilogue's partial sums live in SHARED memory, one column per thread ([slot][thread], conflict-free): the sweep's
+// body holds two particles and the temporaries of the RF-gap map in registers right at the 128-register budget of two
+// resident blocks per SM; 16 accumulators carried across that body would cost 32 more.
+struct AccCol {
+  volatile double* a;  // this thread's column: a[slot * HPS_BLOCK]
+  __device__ __forceinline__ void add(int slot, double v) const { a[slot * HPS_BLOCK] += v; }
+  __device__ __forceinline__ void fma2(int slot, double v) const { a[slot * HPS_BLOCK] = fma(v, v, a[slot * HPS_BLOCK]); }
+  __device__ __forceinline__ void mx(int slot, double v) const { a[slot * HPS_BLOCK] = fmax(a[slot * HPS_BLOCK], v); }
+};
+
+__device__ __forceinline__ void seg_accumulate(const AccCol& acc, const Pt& p, u32 ll, double phi_fc, bool live_fc) {
   const bool alive = p.loss == 0, good = alive && ll == 0;
-  if (good) { acc[0] += 1.0; acc[1] += p.phi; }
-  if (ll == 0) acc[2] = fmax(acc[2], p.phi);
-  else acc[6] += 1.0;
-  if (alive) { acc[4] += p.x; acc[5] += p.y; }
-  else acc[3] += 1.0;
-  if (live_fc) acc[7] += phi_fc;
+  if (good) { acc.add(0, 1.0); acc.add(1, p.phi); }
+  if (ll == 0) acc.mx(2, p.phi);
+  else acc.add(6, 1.0);
+  if (alive) { acc.add(4, p.x); acc.add(5, p.y); }
+  else acc.add(3, 1.0);
+  if (live_fc) acc.add(7, phi_fc);
+}
+
+// ---- fused moments (FIN_KICK_FUSED) ---------------------------------------------------------------------------------
+// Beam::UpdateStatForSpaceCharge (beam.cpp:1003-1016) is a chain of dependent reductions: <phi>_good -> longitudinal-loss
+// marking against <phi>_good + 3 pi -> <phi>_good again -> relative phases about it -> their moments.  The reference (and
+// round 1 of this code) re-reads the particles for every link.  Here the sweep that moves the particles also sums
+//   u = rel_phi(phi, P)      about a PREDICTED pivot P (a pilot particle at (<phi>_good, <W>_good) of the previous kick,
+//                            carried through the segment's maps by thread 0 of every block),
+// and the last block re-centres exactly once the true R = <phi>_good is known: with delta = R - P,
+//   sum phi_r = sum u - n delta,   sum phi_r^2 = sum u^2 - 2 delta sum u + n delta^2
+// for every particle whose classification cannot change within |delta| <= m.  The others -- within m of the 2 pi wrap of
+// the relative phase, or within m of the marking threshold P + 3 pi -- are appended to a side list (DeferList) and
+// resolved one by one with the true R, their contributions summed in 64-bit FIXED POINT so that the (arbitrary) list
+// order cannot change a bit of the result.  A prediction that misses by more than m, or a list overflow, hands the kick
+// to the stand-alone moment kernel (k_moments, DevStats::moments_fallback).
+// slots: 0 n_good before marking (all particles)   1 sum phi over good, non-deferred      2 n_lloss != 0 (all)
+//        3 sum phi right after OP_FREQ_CHANGE (loss == 0)   4 n alive, non-deferred       5 sum u alive, non-deferred
+//        6 n good non-deferred   7 sum u   8 sum u^2   9 sum x   10 sum x^2   11 sum y   12 sum y^2   13 sum w (good, non-def.)
+//        14 MAX (x-x_avg)^2+(y-y_avg)^2 over loss == 0 (all)    15 deferred particles
+enum { KF_NGOOD = 0, KF_SPHI, KF_NLLOSS, KF_SPHI_FC, KF_NALIVE_M, KF_SU_ALIVE, KF_NGOOD_M, KF_SU, KF_SU2, KF_SX, KF_SX2, KF_SY,
+       KF_SY2, KF_SW, KF_R2MAX, KF_NDEFER };
+struct FusedCtx {
+  double pivot, m, cand_thr, amb_thr, xa, ya;
+};
+
+__device__ __forceinline__ void seg_accumulate_fused(const AccCol& acc, const Pt& p, u32 ll, double phi_fc, bool live_fc, const FusedCtx& f,
+                                                     DeferList* dl, u32 local_idx) {
+  const bool alive = p.loss == 0, good = alive && ll == 0;
+  if (ll != 0) acc.add(KF_NLLOSS, 1.0);
+  if (live_fc) acc.add(KF_SPHI_FC, phi_fc);
+  if (good) acc.add(KF_NGOOD, 1.0);
+  // beam_kernel.cu:1556 marks `phi > <phi>_good + 3 pi && lloss != 1` whatever the transverse loss flag says
+  const bool cand = ll != 1u && (p.phi - f.pivot > f.cand_thr);
+  double u = 0.0;
+  bool amb = false;
+  if (alive) {
+    u = rel_phi(p.phi, f.pivot);
+    amb = !(fabs(u) <= f.amb_thr);  // also catches NaN
+    const double tx = p.x - f.xa, ty = p.y - f.ya;
+    acc.mx(KF_R2MAX, tx * tx + ty * ty);
+  }
+  if (cand || amb) {
+    const u32 k = atomicAdd(&dl->count, 1u);
+    if (k < HPS_DEFER_CAP) {
+      DeferEntry& e = dl->e[k];
+      e.phi = p.phi; e.x = p.x; e.y = p.y; e.w = p.w;
+      e.tag = (unsigned long long)local_idx | ((unsigned long long)((alive ? 1u : 0u) | (ll != 0 ? 2u : 0u) | (cand ? 4u : 0u)) << 32);
+    }
+    acc.add(KF_NDEFER, 1.0);
+  } else if (alive) {
+    acc.add(KF_NALIVE_M, 1.0);
+    acc.add(KF_SU_ALIVE, u);
+    if (good) {
+      acc.add(KF_NGOOD_M, 1.0);
+      acc.add(KF_SPHI, p.phi);
+      acc.add(KF_SU, u); acc.fma2(KF_SU2, u);
+      acc.add(KF_SX, p.x); acc.fma2(KF_SX2, p.x);
+      acc.add(KF_SY, p.y); acc.fma2(KF_SY2, p.y);
+      acc.add(KF_SW, p.w);
+    }
+  }
+}
+
+// The pilot: one on-axis particle at (<phi>_good, <W>_good) of the previous kick through the segment's maps (the
+// reference-order maps with nvcc's operators; accuracy is irrelevant here, the result is only a pivot).  One copy in the
+// module (noinline), run by thread 0 of every block ahead of the sweep.
+__device__ __noinline__ double pilot_phase(const Op* ops, const OpC* opcs, int nops, double phi, double w, double mass, double charge) {
+  Pt p = {0.0, 0.0, 0.0, 0.0, phi, w, 0u};
+  const double inv_mass = 1.0 / mass;
+  for (int k = 0; k < nops; ++k) {
+    const Op& op = ops[k];
+    const double* q = op.p;
+    const double* c = opcs[k].c;
+    switch (op.type) {
+      case OP_DRIFT: p.phi += c[D_TWOPI_HL] / (q[2] * beta_of<MathLib>(p.w, mass, inv_mass)); break;
+      case OP_QUAD_HALF: p.phi += c[Q_TWOPI_LEN_HALF] / (q[3] * beta_of<MathLib>(p.w, mass, inv_mass)); break;
+      case OP_GAP_FIRST: op_gap_first<MathLib>(p, q, c, op.flag != 0, mass, inv_mass); break;
+      case OP_GAP_SECOND: op_gap_second<MathLib>(p, q, c, op.flag != 0, mass, inv_mass); break;
+      case OP_DIPOLE_FIRST: op_dipole(p, q, false, mass); break;
+      case OP_DIPOLE_SECOND: op_dipole(p, q, true, mass); break;
+      case OP_BUNCHER: op_buncher(p, q, op.elem, mass, charge); break;
+      case OP_FREQ_CHANGE: p.phi *= q[0]; break;
+      default: break;  // kick (no field on the axis at the bunch centre), rotation, steerer, apertures
+    }
+  }
+  return p.phi;
+}
+
+__device__ __forceinline__ long long to_fix(double v, double scale) { return __double2ll_rn(v * scale); }
+
+// sum of NV 64-bit integers per thread over the block -> s_out[0..NV) (shared); every thread of the block calls it
+template <int NV>
+__device__ __forceinline__ void block_sum_i64(long long (&v)[NV], long long* s_warp /* shared [8][NV] */, long long* s_out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int s = 0; s < NV; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[s] += __shfl_xor_sync(0xffffffffu, v[s], o);
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NV; ++s) s_warp[wid * NV + s] = v[s];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NV) {
+    long long a = 0;
+    for (int k = 0; k < nw; ++k) a += s_warp[k * NV + threadIdx.x];
+    s_out[threadIdx.x] = a;
+  }
+  __syncthreads();
+}
+
+__device__ void scheff_policy(DevStats* st, ScDev* sc, const KickParams& kp, double r2max);
+__device__ void finalize_moments(const double* t, double ref, u32 n_global, DevStats* st, ScDev* sc, const KickParams& kp, int do_policy);
+
+// fixed-point scales of the deferred particles' contributions: 2^62 / (entries x bound of the summand)
+// (8 ranks x 2^16 entries: a summand may use 43 bits)
+#define FX_DPHI 4294967296.0           /* 2^32: |phi - P| < 2^11 */
+#define FX_PR 2199023255552.0          /* 2^41: |phi_r| <= pi */
+#define FX_PR2 549755813888.0          /* 2^39: phi_r^2 < 16 */
+#define FX_X 70368744177664.0          /* 2^46: |x|, |y| < 2^-3 m */
+#define FX_X2 562949953421312.0        /* 2^49: x^2 < 2^-6 */
+#define FX_W 8589934592.0              /* 2^33: w < 2^10 MeV */
+
+// Last block of a FIN_KICK_FUSED sweep; every thread of the block calls it with this rank's totals in t[0..16) (shared).
+// Ends with DevStats / ScDev exactly as Beam::UpdateStatForSpaceCharge + Scheff::Start's policy leave them, or with
+// st->moments_fallback != 0 (1: redo the whole chain, 2: longitudinal losses are marked, redo the moment sums only).
+__device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
+                                    const KickParams& kp, DeferList* dl, const XrView& xr, int fin_mode) {
+  __shared__ long long s_warp[8 * 12];
+  __shared__ long long s_i[12];
+  __shared__ double s_g[HPS_XR_NS];   // round 1: totals over all ranks
+  __shared__ double s_x[HPS_XR_NS];   // rounds 2 and 3
+  __shared__ double s_R1, s_R2, s_SG0, s_nG1, s_nnew;
+  __shared__ u32 s_code, s_Kall, s_ncand;
+  const bool p2p = xr.mode == XR_P2P;
+  const double P = f.pivot;
+  const u32 cnt = __ldcg(&dl->count);
+  const u32 K = min(cnt, HPS_DEFER_CAP);
+  // ---- pass 1: the deferred members of the good set, the candidates
+  {
+    long long v[4] = {0, 0, 0, (threadIdx.x == 0 && cnt > HPS_DEFER_CAP) ? 1 : 0};  // n good, sum (phi - P), candidates, bad
+    for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
+      const DeferEntry& e = dl->e[k];
+      const u32 fl = (u32)(__ldcg(&e.tag) >> 32);
+      const double d = __ldcg(&e.phi) - P;
+      if ((fl & 3u) == 1u) {
+        v[0] += 1;
+        if (!(fabs(d) < 2048.0)) v[3] += 1; else v[1] += to_fix(d, FX_DPHI);
+      }
+      if (fl & 4u) v[2] += 1;
+    }
+    block_sum_i64<4>(v, s_warp, s_i);
+  }
+  if (threadIdx.x < SEG_NS) s_g[threadIdx.x] = t[threadIdx.x];
+  if (threadIdx.x == 0) {
+    s_g[16] = (double)s_i[0]; s_g[17] = __longlong_as_double(s_i[1]); s_g[18] = (double)s_i[2]; s_g[19] = (double)s_i[3];
+    s_g[20] = (double)K;
+  }
+  __syncthreads();
+  if (p2p) xr_exchange_p2p(s_g, 21, 1u << KF_R2MAX, xr, 1u << 17);
+  if (threadIdx.x == 0) {
+    // Beam::ChangeFrequency -> UpdateAvgPhi() (beam.cpp:1666; divides by N - num_loss, stale count)
+    if (fin_mode & FIN_FREQ) st->v[HPS_STAT_PHI_AVG] = s_g[KF_SPHI_FC] / (double)(u32)(b.n_global - st->num_loss);
+    const double n_g0 = s_g[KF_NGOOD], nl = s_g[16];
+    const double sg0 = s_g[KF_SPHI] + nl * P + (double)__double_as_longlong(s_g[17]) * (1.0 / FX_DPHI);
+    const double r1 = n_g0 > 0.0 ? sg0 / n_g0 : -99999.0;
+    u32 code = 0u;
+    if (s_g[19] != 0.0 || !(n_g0 > 0.0) || !(fabs(r1 - P) <= f.m) || n_g0 != s_g[KF_NGOOD_M] + nl) code = 1u;
+    s_R1 = r1; s_R2 = r1; s_SG0 = sg0; s_nG1 = n_g0; s_nnew = 0.0; s_code = code; s_Kall = (u32)s_g[20]; s_ncand = (u32)s_g[18];
+  }
+  __syncthreads();
+  if (s_code == 0u && s_ncand != 0u) {
+    // ---- pass 2: Beam::UpdateLongitudinalLoss (beam_kernel.cu:1549-1559) on the candidates
+    const double thr = s_R1 + K_TWOPI + K_PI;
+    long long v[3] = {0, 0, 0};  // newly non-zero lloss, marked members of the good set, their sum (phi - P)
+    for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
+      DeferEntry& e = dl->e[k];
+      const unsigned long long tag = __ldcg(&e.tag);
+      const u32 fl = (u32)(tag >> 32);
+      const double phi = __ldcg(&e.phi);
+      if ((fl & 4u) && phi > thr) {
+        b.lloss[(u32)tag] = 1u;
+        if (!(fl & 2u)) v[0] += 1;
+        if ((fl & 3u) == 1u) { v[1] += 1; v[2] += to_fix(phi - P, FX_DPHI); }
+        e.tag = tag | (2ull << 32);
+      }
+    }
+    block_sum_i64<3>(v, s_warp, s_i);
+    if (threadIdx.x == 0) { s_x[0] = (double)s_i[0]; s_x[1] = (double)s_i[1]; s_x[2] = __longlong_as_double(s_i[2]); }
+    __syncthreads();
+    if (p2p) xr_exchange_p2p(s_x, 3, 0u, xr, 1u << 2);
+    if (threadIdx.x == 0) {
+      const double n_mark = s_x[1];
+      const double s_mark = n_mark * P + (double)__double_as_longlong(s_x[2]) * (1.0 / FX_DPHI);
+      const double n_g1 = s_g[KF_NGOOD] - n_mark;
+      s_nnew = s_x[0];
+      s_nG1 = n_g1;
+      s_R2 = n_g1 > 0.0 ? (s_SG0 - s_mark) / n_g1 : -99999.0;
+      if (s_x[0] > 0.0) sc->n_lloss_pass++;
+      if (!(n_g1 > 0.0)) s_code = 2u;
+    }
+    __syncthreads();
+  }
+  const double R2 = s_R2, delta = R2 - P;
+  if (threadIdx.x == 0 && s_code == 0u && !(fabs(delta) <= f.m)) s_code = 2u;  // (marks are written: only the sums are redone)
+  __syncthreads();
+  // ---- pass 3: the deferred particles' relative phases about the true <phi>_good, summed in fixed point
+  if (s_code == 0u && s_Kall != 0u) {
+    long long v[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // n alive, sum pr alive, n good, sum pr, pr^2, x, x^2, y, y^2, w, bad
+    for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
+      const DeferEntry& e = dl->e[k];
+      const u32 fl = (u32)(__ldcg(&e.tag) >> 32);
+      if (!(fl & 1u)) continue;
+      const double pr = rel_phi(__ldcg(&e.phi), R2);
+      v[0] += 1; v[1] += to_fix(pr, FX_PR);
+      if (fl & 2u) continue;
+      const double x = __ldcg(&e.x), y = __ldcg(&e.y), w = __ldcg(&e.w);
+      if (!(fabs(x) < 0.125 && fabs(y) < 0.125 && fabs(w) < 1024.0)) { v[10] += 1; continue; }
+      v[2] += 1; v[3] += to_fix(pr, FX_PR); v[4] += to_fix(pr * pr, FX_PR2);
+      v[5] += to_fix(x, FX_X); v[6] += to_fix(x * x, FX_X2); v[7] += to_fix(y, FX_X); v[8] += to_fix(y * y, FX_X2);
+      v[9] += to_fix(w, FX_W);
+    }
+    block_sum_i64<12>(v, s_warp, s_i);
+    if (threadIdx.x < 12) s_x[threadIdx.x] = __longlong_as_double(s_i[threadIdx.x]);
+    __syncthreads();
+    if (p2p) xr_exchange_p2p(s_x, 12, 0u, xr, 0xfffu);
+  } else {
+    if (threadIdx.x < 12) s_x[threadIdx.x] = 0.0;  // bit pattern of the integer 0
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    auto I = [&](int k) { return (double)__double_as_longlong(s_x[k]); };
+    u32 code = s_code;
+    if (code == 0u && (I(10) != 0.0 || s_nG1 != s_g[KF_NGOOD_M] + I(2))) code = 2u;
+    if (code != 1u) {  // what the first links of the chain leave behind (beam.cpp:776-782, 1007-1009)
+      st->num_good = (u32)s_nG1;
+      st->v[HPS_STAT_PHI_AVG_GOOD] = R2;
+      st->num_lloss = (u32)(s_g[KF_NLLOSS] + s_nnew);
+    }
+    st->need_lloss_pass = 0u;
+    st->moments_fallback = code;
+    const double err = fmax(fabs(s_R1 - P), fabs(delta));
+    if (code == 0u) {
+      const double nm = s_g[KF_NGOOD_M], na = s_g[KF_NALIVE_M];
+      double m9[9];
+      m9[0] = s_g[KF_SU_ALIVE] - na * delta + I(1) * (1.0 / FX_PR);
+      m9[1] = s_g[KF_SU] - nm * delta + I(3) * (1.0 / FX_PR);
+      m9[2] = s_g[KF_SU2] - 2.0 * delta * s_g[KF_SU] + nm * delta * delta + I(4) * (1.0 / FX_PR2);
+      m9[3] = s_g[KF_SX] + I(5) * (1.0 / FX_X);
+      m9[4] = s_g[KF_SX2] + I(6) * (1.0 / FX_X2);
+      m9[5] = s_g[KF_SY] + I(7) * (1.0 / FX_X);
+      m9[6] = s_g[KF_SY2] + I(8) * (1.0 / FX_X2);
+      m9[7] = s_g[KF_SW] + I(9) * (1.0 / FX_W);
+      m9[8] = s_g[KF_R2MAX];
+      finalize_moments(m9, R2, b.n_global, st, sc, kp, 1);
+      st->n_fused++;
+      st->n_deferred += (unsigned long long)s_Kall;
+      st->pivot_err_max = fmax(st->pivot_err_max, err);
+      // the margin follows the prediction error: generous against the last miss, decaying slowly
+      st->pivot_m = fmin(0.25, fmax(fmax(1.0e-4, 0.5 * f.m), 16.0 * err));
+    } else {
+      st->n_fallback++;
+      st->pivot_m = (err == err) ? fmin(0.25, fmax(2.0 * f.m, 4.0 * err)) : 0.05;
+    }
+    dl->count = 0u;
+    s_code = code;
+  }
+  __syncthreads();
+  if (s_code == 0u && sc->remesh) {  // ResetBinTbl (space_charge.cu:92-105)
+    const u32 nb = kp.nr * kp.nz;
+    for (u32 k = threadIdx.x; k < nb; k += blockDim.x) bins[k] = 0.0;
+  }
 }
 
 // PPT = particles per thread.  PPT == 2 moves two adjacent particles with one 128-bit access per
@@ -172,17 +456,20 @@ __device__ __forceinline__ void seg_accumulate(double (&acc)[SEG_NS], const Pt& 
 template <int PPT, int MINB, bool FULL, int MATH>
 __global__ void __launch_bounds__(HPS_BLOCK, MINB)
 k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
-          DevStats* st, const ScDev* __restrict__ sc, const double2* __restrict__ field, KickParams kp, double* partials,
-          u32* ticket, const __grid_constant__ XrView xr) {
+          DevStats* st, ScDev* sc, const double2* __restrict__ field, KickParams kp, double* partials,
+          u32* ticket, double* bins, DeferList* dl, const __grid_constant__ XrView xr) {
   __shared__ Op s_ops[HPS_MAX_SEG_OPS];
   __shared__ OpC s_opc[HPS_MAX_SEG_OPS];
   __shared__ KickCtx s_k;
+  __shared__ FusedCtx s_f;
   __shared__ double s_cxy[2];
   __shared__ double s_total[SEG_NS];
   __shared__ double s_scratch[HPS_BLOCK];
+  extern __shared__ double s_acc[];  // [SEG_NS][HPS_BLOCK] partial sums of the epilogue, one column per thread
 
   pdl_launch_dependents();
   pdl_wait();  // the op constants (k_prepare_ops) and everything below come from preceding kernels
+  const bool fused = (fin_mode & 3) == FIN_KICK_FUSED;
   {  // stage the segment's op records (block-uniform) in shared memory
     const int nw = nops * (int)(sizeof(Op) / sizeof(double));
     const double* src = reinterpret_cast<const double*>(ops);
@@ -192,6 +479,12 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
     const double* csrc = reinterpret_cast<const double*>(opcs);
     double* cdst = reinterpret_cast<double*>(s_opc);
     for (int i = threadIdx.x; i < nc; i += blockDim.x) cdst[i] = csrc[i];
+  }
+  const AccCol acc = {s_acc + threadIdx.x};
+  if (fin_mode != FIN_NONE) {
+#pragma unroll
+    for (int s = 0; s < SEG_NS; ++s) acc.a[s * HPS_BLOCK] = 0.0;
+    if (!fused) acc.a[2 * HPS_BLOCK] = -DBL_MAX;
   }
   if (threadIdx.x == 0) {
     s_cxy[0] = st->v[HPS_STAT_X_AVG];
@@ -213,11 +506,21 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       if (ops[k].type == OP_SC_KICK) { kick_prepare(s_k, ops[k].p, b.mass, b.n_global); break; }
   }
   __syncthreads();
+  if (fused) {
+    if (threadIdx.x == 0) {
+      FusedCtx f;
+      f.pivot = pilot_phase(s_ops, s_opc, nops, st->v[HPS_STAT_PHI_AVG_GOOD], st->v[HPS_STAT_W_AVG_GOOD], b.mass, b.charge);
+      double m = st->pivot_m;
+      if (!(m >= 1.0e-4 && m <= 0.25)) m = 0.05;
+      f.m = m;
+      f.cand_thr = K_TWOPI + K_PI - m;
+      f.amb_thr = K_PI - m;
+      f.xa = s_cxy[0]; f.ya = s_cxy[1];
+      s_f = f;
+    }
+    __syncthreads();
+  }
 
-  double acc[SEG_NS];
-#pragma unroll
-  for (int s = 0; s < SEG_NS; ++s) acc[s] = 0.0;
-  acc[2] = -DBL_MAX;
   const double inv_mass = 1.0 / b.mass;
 
   if (PPT == 2) {
@@ -249,7 +552,10 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
         if ((dirty & 64) && (p[0].loss != L.x || p[1].loss != L.y))
           reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p[0].loss, p[1].loss);
       }
-      if (fin_mode != FIN_NONE) {
+      if (fused) {
+        seg_accumulate_fused(acc, p[0], ll[0], fc[0], lf[0], s_f, dl, 2 * i2);
+        if (valid[1]) seg_accumulate_fused(acc, p[1], ll[1], fc[1], lf[1], s_f, dl, 2 * i2 + 1);
+      } else if (fin_mode != FIN_NONE) {
         seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
         if (valid[1]) seg_accumulate(acc, p[1], ll[1], fc[1], lf[1]);
       }
@@ -273,15 +579,25 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
         if (dirty & 32) b.w[i] = p[0].w;
         if ((dirty & 64) && p[0].loss != l0) b.loss[i] = p[0].loss;
       }
-      if (fin_mode != FIN_NONE) seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
+      if (fused) seg_accumulate_fused(acc, p[0], ll[0], fc[0], lf[0], s_f, dl, i);
+      else if (fin_mode != FIN_NONE) seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
     }
   }
   if (fin_mode == FIN_NONE) return;
-  if (grid_reduce<SEG_NS>(acc, 1u << 2, partials, ticket, s_total, s_scratch, xr)) {
+  double v[SEG_NS];
+#pragma unroll
+  for (int s = 0; s < SEG_NS; ++s) v[s] = acc.a[s * HPS_BLOCK];
+  if (fused) {
+    if (grid_reduce<SEG_NS>(v, 1u << KF_R2MAX, partials, ticket, s_total, s_scratch, xr, false)) {
+      fused_kick_finalize(s_total, s_f, b, st, sc, bins, kp, dl, xr, fin_mode);
+    }
+    return;
+  }
+  if (grid_reduce<SEG_NS>(v, 1u << 2, partials, ticket, s_total, s_scratch, xr)) {
     if (threadIdx.x == 0) finalize_segment(fin_mode, s_total, st, b.n_global);
   }
 }
-#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, const ScDev*, const double2*, KickParams, double*, u32*, const __grid_constant__ XrView
+#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, ScDev*, const double2*, KickParams, double*, u32*, double*, DeferList*, const __grid_constant__ XrView
 typedef void (*SegKernel)(SEG_ARGS);
 // variant -> kernel.  20 (default): 2 particles/thread, reference-order maps with exact branch-free arithmetic;
 // 0: 2 particles/thread, fast maps; 1 / 2: fast maps, 1 particle/thread at 3 / 4 blocks per SM;
@@ -557,13 +873,49 @@ __device__ __forceinline__ void moments_phase(const BeamView& b, DevStats* st, S
   }
 }
 
+// mode 0: the stand-alone link of the chain (Beam::Update* API path, XR_NCCL, HPSIM_FUSED_MOMENTS=0).
+// mode 1: fallback of the fused-moment epilogue of K1 (DevStats::moments_fallback): 0 -> nothing to do; 1 -> the whole
+//   chain again (good count and <phi>_good, longitudinal-loss pass, moments); 2 -> losses are marked, moments only.
+//   The flag is written by K1's finaliser only, so every block reads the same value for the whole launch.
 __global__ void __launch_bounds__(HPS_BLOCK)
-k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, int with_lloss, double* partials,
+k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, int with_lloss, int mode, double* partials,
           u32* ticket, const __grid_constant__ XrView xr) {
   __shared__ double s_total[MOM_NS];
   __shared__ double s_scratch[HPS_BLOCK];
   pdl_launch_dependents();
   pdl_wait();
+  if (mode == 1) {
+    const u32 code = *(volatile u32*)&st->moments_fallback;
+    if (code == 0u) return;
+    with_lloss = 0;
+    if (code == 1u) {
+      // first link again: Beam::UpdateLongitudinalLoss steps 1-2 (what K1's FIN_KICK epilogue computes)
+      double acc[LL_NS] = {0.0, 0.0, -DBL_MAX, 0.0};  // n_good, sum phi good, MAX phi over lloss == 0, n_lloss
+      const u32 npairs = (b.n + 1) >> 1;
+      for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
+        const double2 PH = ld_f64x2(b.phi, i2);
+        const uint2 L = ld_u32x2(b.loss, i2);
+        const uint2 LL = ld_u32x2(b.lloss, i2);
+        const double ph[2] = {PH.x, PH.y};
+        const u32 l[2] = {L.x, L.y}, ll[2] = {LL.x, LL.y};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j == 1 && !(2 * i2 + 1 < b.n)) continue;
+          if (l[j] == 0 && ll[j] == 0) { acc[0] += 1.0; acc[1] += ph[j]; }
+          if (ll[j] == 0) acc[2] = fmax(acc[2], ph[j]); else acc[3] += 1.0;
+        }
+      }
+      if (grid_reduce<LL_NS>(acc, 1u << 2, partials, ticket, s_total, s_scratch, xr)) {
+        if (threadIdx.x == 0) {
+          const double t8[8] = {s_total[0], s_total[1], s_total[2], 0.0, 0.0, 0.0, s_total[3], 0.0};
+          finalize_segment(FIN_KICK, t8, st, b.n_global);
+          __threadfence();
+        }
+      }
+      grid_barrier(ticket + 2);
+      with_lloss = 1;
+    }
+  }
   moments_phase(b, st, sc, bins, kp, do_policy, with_lloss, partials, ticket, s_total, s_scratch, xr);
 }
 
@@ -1313,23 +1665,24 @@ static cudaError_t launch_chain(const LaunchCfg& c, void (*kernel)(KArgs...), di
 void launch_prepare_ops(const LaunchCfg& c, const Op* ops, OpC* opcs, int nops, double mass, double charge) {
   if (nops > 0) k_prepare_ops<<<(nops + 63) / 64, 64, 0, c.stream>>>(ops, opcs, nops, mass, charge);
 }
+size_t segment_smem() { return (size_t)SEG_NS * HPS_BLOCK * sizeof(double); }
 void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, const Op* ops, const OpC* opcs, int nops,
-                    int fin_mode, int dirty, int compat, DevStats* st, const ScDev* sc, const double2* field,
-                    const KickParams& kp) {
+                    int fin_mode, int dirty, int compat, DevStats* st, ScDev* sc, const double2* field,
+                    const KickParams& kp, double* bins, DeferList* dl) {
   bool full = false;
   for (int k = 0; k < nops; ++k) full |= host_ops[k].type == OP_DIPOLE_FIRST || host_ops[k].type == OP_DIPOLE_SECOND || host_ops[k].type == OP_BUNCHER;
   const unsigned grid1 = c.grid_seg1, grid2 = c.grid_seg;
-#define SEG_CALL b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, c.xr
-  if (full) launch_chain(c, seg_kernel(seg_full_variant(c.seg_variant)), dim3(grid1), dim3(HPS_BLOCK), 0, SEG_CALL);
-  else launch_chain(c, seg_kernel(c.seg_variant), dim3(grid2), dim3(HPS_BLOCK), 0, SEG_CALL);
+#define SEG_CALL b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, bins, dl, c.xr
+  if (full) launch_chain(c, seg_kernel(seg_full_variant(c.seg_variant)), dim3(grid1), dim3(HPS_BLOCK), segment_smem(), SEG_CALL);
+  else launch_chain(c, seg_kernel(c.seg_variant), dim3(grid2), dim3(HPS_BLOCK), segment_smem(), SEG_CALL);
 #undef SEG_CALL
 }
 void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
   k_lloss_pass<<<c.grid_pairs, HPS_BLOCK, 0, c.stream>>>(b, st, sc, c.partials, c.ticket, c.xr);
 }
 void launch_moments(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins, const KickParams& kp,
-                    int do_policy, int with_lloss) {
-  launch_chain(c, k_moments, dim3(c.grid_pairs), dim3(HPS_BLOCK), 0, b, st, sc, bins, kp, do_policy, with_lloss, c.partials, c.ticket, c.xr);
+                    int do_policy, int with_lloss, int mode) {
+  launch_chain(c, k_moments, dim3(c.grid_pairs), dim3(HPS_BLOCK), 0, b, st, sc, bins, kp, do_policy, with_lloss, mode, c.partials, c.ticket, c.xr);
 }
 int moments_occupancy() {
   int nb = 0;
@@ -1472,8 +1825,10 @@ void launch_rel_phi_out(const LaunchCfg& c, const BeamView& b, const DevStats* s
   k_rel_phi_out<<<(b.n + 255) / 256, 256, 0, c.stream>>>(b, st, out);
 }
 int segment_occupancy(int variant) {
+  // static + dynamic shared memory of the sweep exceed the 48 KB default: opt in once per variant and device
+  cudaFuncSetAttribute(seg_kernel(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segment_smem());
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg_kernel(variant), HPS_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg_kernel(variant), HPS_BLOCK, segment_smem());
   return nb;
 }
 int segment_full_variant(int variant) { return seg_full_variant(variant); }

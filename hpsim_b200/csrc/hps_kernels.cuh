@@ -111,7 +111,9 @@ __device__ __forceinline__ unsigned long long ll_recv64(const unsigned long long
 // All threads of ONE block (the rank's last block, >= 2 * nranks * ns threads) call this with the
 // rank-local totals in shared memory; on return total[] holds the fold over all ranks in rank order
 // (bit-identical everywhere).
-__device__ __forceinline__ void xr_exchange_p2p(double* total, int ns, unsigned max_mask, const XrView& xr) {
+// int_mask: slots that carry a signed 64-bit integer (bit pattern in the double) and are summed as integers -- the
+// fixed-point sums of the fused-moment epilogue, exact and order-independent.
+__device__ __forceinline__ void xr_exchange_p2p(double* total, int ns, unsigned max_mask, const XrView& xr, unsigned int_mask = 0u) {
   __shared__ unsigned long long s_seq;
   __shared__ u32 s_recv[HPS_XR_MAXR * 2 * HPS_XR_NS];
   if (threadIdx.x == 0) { s_seq = *xr.seq + 1ull; *xr.seq = s_seq; }
@@ -132,14 +134,17 @@ __device__ __forceinline__ void xr_exchange_p2p(double* total, int ns, unsigned 
   __syncthreads();
   if ((int)threadIdx.x < ns) {
     const int s = threadIdx.x;
-    const bool mx = (max_mask >> s) & 1u;
+    const bool mx = (max_mask >> s) & 1u, as_int = (int_mask >> s) & 1u;
     double a = 0.0;
+    long long ia = 0;
     for (int r = 0; r < xr.nranks; ++r) {
       const u32* q = &s_recv[r * (2 * HPS_XR_NS) + 2 * s];
-      const double t = __longlong_as_double((long long)((unsigned long long)q[0] | ((unsigned long long)q[1] << 32)));
+      const long long bits = (long long)((unsigned long long)q[0] | ((unsigned long long)q[1] << 32));
+      const double t = __longlong_as_double(bits);
+      ia += bits;
       a = r == 0 ? t : (mx ? fmax(a, t) : a + t);
     }
-    total[s] = a;
+    total[s] = as_int ? __longlong_as_double(ia) : a;
   }
   __syncthreads();
 }
@@ -148,10 +153,12 @@ __device__ __forceinline__ void xr_exchange_p2p(double* total, int ns, unsigned 
 // (shared) then holds the result of every slot over the whole (possibly sharded) beam.
 // partials: [gridDim.x][NS].  XR_NCCL: the last block only hands its totals to xr.send and returns
 // false; the host then enqueues an all-gather and k_xr_finalize.
+// do_xr = false: the caller runs the cross-rank exchange itself (fused-moment epilogue); `total` then holds this
+// rank's totals only.
 template <int NS>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, double* partials, u32* ticket,
                                             double* total /* shared, NS */, double* scratch /* shared, blockDim.x doubles */,
-                                            const XrView& xr) {
+                                            const XrView& xr, bool do_xr = true) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   warp_reduce<NS>(v, max_mask);
   if (lane == 0) {
@@ -212,6 +219,7 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, 
   }
   if (threadIdx.x == 0) *ticket = 0u;
   __syncthreads();
+  if (!do_xr) return true;
   if (xr.mode == XR_P2P) xr_exchange_p2p(total, NS, max_mask, xr);
   else if (xr.mode == XR_NCCL) {
     if (threadIdx.x < NS) xr.send[threadIdx.x] = total[threadIdx.x];
@@ -219,39 +227,6 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, 
   }
   return true;
 }
-
-// ------------------------------------------------------------------------------------------------
-// TMA bulk staging of particle tiles (cp.async.bulk global -> shared, completion on an mbarrier)
-// ------------------------------------------------------------------------------------------------
-// The sweeps are latency-bound: a thread loads its pair, computes for ~1 us, stores, loads the next pair.
-// Staging tile t+1 with one bulk copy per array while tile t is being computed takes the global-load
-// latency off the critical path without spending registers on a software prefetch.
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 16-byte aligned source / destination, size a multiple of 16
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, u32 bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // element maps (one particle)

@@ -47,10 +47,11 @@ unsigned reduce_max_mask(int kind);
 
 void launch_prepare_ops(const LaunchCfg&, const Op* ops, OpC* opcs, int nops, double mass, double charge);
 void launch_segment(const LaunchCfg&, const BeamView&, const Op* host_ops, const Op* ops, const OpC* opcs, int nops,
-                    int fin_mode, int dirty, int compat, DevStats*, const ScDev*, const double2* field, const KickParams&);
+                    int fin_mode, int dirty, int compat, DevStats*, ScDev*, const double2* field, const KickParams&,
+                    double* bins, DeferList* defer);
 void launch_lloss_pass(const LaunchCfg&, const BeamView&, DevStats*, ScDev*);
 void launch_moments(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&, int do_policy,
-                    int with_lloss);
+                    int with_lloss, int mode);  // mode 1: only when the fused epilogue of the sweep asked for it
 int moments_occupancy();
 cudaError_t prepare_chain_attributes(const KickParams&);
 cudaError_t launch_deposit(const LaunchCfg&, const BeamView&, DevStats*, ScDev*, double* bins, const KickParams&);

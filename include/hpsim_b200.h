@@ -278,6 +278,13 @@ int hps_scheff_download_tables(hps_scheff*, double* bins, double* field, double*
  * slice, 4 grid barrier (+ mesh push of a sharded beam), 5 field solve; 6-7 unused. */
 int hps_scheff_phase_cycles(hps_scheff*, uint64_t out[8]);
 
+/* Diagnostics of the fused moment chain (no reference counterpart): the reference's Beam::UpdateStatForSpaceCharge
+ * (src/beam/src/beam.cpp:1003-1016) re-reads the particles for every link of its chain; here the sweep in front of a
+ * kick sums the moments about a predicted <phi>_good and re-centres exactly.  out[0] kicks finished that way, out[1]
+ * kicks handed back to the stand-alone moment kernel, out[2] particles that had to be resolved one by one with the
+ * true <phi>_good; *pivot_err_max: largest |<phi>_good - prediction| [rad]; *pivot_margin: margin in force [rad]. */
+int hps_beam_moment_stats(hps_beam*, uint64_t out[3], double* pivot_err_max, double* pivot_margin);
+
 /* ---- simulate ------------------------------------------------------------ */
 typedef struct hps_run_stats {
   uint64_t particles;        /* n_global                                             */

