@@ -51,6 +51,9 @@ struct hps_ctx {
   // the whole moment chain of a kick in the epilogue of the sweep before it (FIN_KICK_FUSED); HPSIM_FUSED_MOMENTS=0 keeps
   // the stand-alone moment kernel of round 1 (k_moments re-reads 40 B/particle per kick)
   int fused_moments = 1;
+  // cp.async staging of the next particle pair in the sweep: -1 = automatic (on when the rank's particle state does not
+  // fit the L2 anyway), 0 / 1 = forced (HPSIM_STAGE)
+  int stage = -1;
   // program upload buffers
   Op* d_ops = nullptr;
   OpC* d_opc = nullptr;  // device-prepared constants, parallel to d_ops
@@ -171,6 +174,7 @@ LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
   l.ticket = c->ticket;
   l.xr = c->xr;
   l.pdl = c->pdl && !c->profile;  // the per-launch events of profile mode sit between the kernels anyway
+  l.stage = c->stage >= 0 ? c->stage : (b->slab_bytes > ((size_t)96 << 20) ? 1 : 0);
   return l;
 }
 
@@ -382,6 +386,7 @@ hps_ctx* hps_ctx_create(int device) {
   if (const char* v = getenv("HPSIM_PDL")) c->pdl = atoi(v);
   if (const char* v = getenv("HPSIM_FUSED")) c->fused = atoi(v);
   if (const char* v = getenv("HPSIM_FUSED_MOMENTS")) c->fused_moments = atoi(v);
+  if (const char* v = getenv("HPSIM_STAGE")) c->stage = atoi(v);
   if (const char* v = getenv("HPSIM_GRAPH")) c->use_graphs = atoi(v);
   if (const char* v = getenv("HPSIM_L2_PERSIST")) c->l2_persist = atoi(v);
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
@@ -1110,7 +1115,7 @@ static int run_range(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, 
     }
     const uint64_t env[12] = {(uint64_t)(uintptr_t)b->slab, (uint64_t)(uintptr_t)b->st, b->n, b->offset, (uint64_t)(uintptr_t)(sc ? sc->dev : nullptr),
                               (uint64_t)(uintptr_t)(sc ? sc->bins : nullptr), (uint64_t)(uintptr_t)(sc ? sc->field : nullptr),
-                              (uint64_t)c->seg_variant, (uint64_t)(c->fused | (c->fused_moments << 4)), (uint64_t)c->compat, (uint64_t)c->pdl,
+                              (uint64_t)c->seg_variant, (uint64_t)(c->fused | (c->fused_moments << 4) | ((c->stage & 3) << 8)), (uint64_t)c->compat, (uint64_t)c->pdl,
                               (uint64_t)(uintptr_t)(sc ? sc->field_part : nullptr)};
     key = fnv(key, env, sizeof(env));
     const double bm[2] = {b->h.mass, b->h.charge};

@@ -157,21 +157,37 @@ __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const 
 // The epilogue's partial sums live in SHARED memory, one column per thread ([slot][thread], conflict-free): the sweep's
 // body holds two particles and the temporaries of the RF-gap map in registers right at the 128-register budget of two
 // resident blocks per SM; 16 accumulators carried across that body would cost 32 more.
-struct AccCol {
-  volatile double* a;  // this thread's column: a[slot * HPS_BLOCK]
-  __device__ __forceinline__ void add(int slot, double v) const { a[slot * HPS_BLOCK] += v; }
-  __device__ __forceinline__ void fma2(int slot, double v) const { a[slot * HPS_BLOCK] = fma(v, v, a[slot * HPS_BLOCK]); }
-  __device__ __forceinline__ void mx(int slot, double v) const { a[slot * HPS_BLOCK] = fmax(a[slot * HPS_BLOCK], v); }
-};
+// The sums of one loop iteration (up to two particles) are formed in registers AFTER the maps -- the maps' temporaries are
+// dead by then -- and folded into the thread's column with one batched read-modify-write: all loads, then all stores
+// (a chain of dependent shared-memory round trips per slot cost 80 us per 16 Mi-particle sweep).
+__device__ __forceinline__ double lds_f64(const double* p) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((u32)__cvta_generic_to_shared(p)));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(double* p, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(p)), "d"(v));
+}
+template <int NS>
+__device__ __forceinline__ void acc_flush(double* col, const double (&c)[NS], unsigned max_mask) {
+  double t[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) t[s] = lds_f64(col + s * HPS_BLOCK);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) t[s] = ((max_mask >> s) & 1u) ? fmax(t[s], c[s]) : t[s] + c[s];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) sts_f64(col + s * HPS_BLOCK, t[s]);
+}
 
-__device__ __forceinline__ void seg_accumulate(const AccCol& acc, const Pt& p, u32 ll, double phi_fc, bool live_fc) {
+enum { SEGL_NS = 8 };  // slots of the legacy epilogues (FIN_KICK / FIN_APERTURE), see finalize_segment
+__device__ __forceinline__ void seg_accumulate(double (&c)[SEGL_NS], const Pt& p, u32 ll, double phi_fc, bool live_fc) {
   const bool alive = p.loss == 0, good = alive && ll == 0;
-  if (good) { acc.add(0, 1.0); acc.add(1, p.phi); }
-  if (ll == 0) acc.mx(2, p.phi);
-  else acc.add(6, 1.0);
-  if (alive) { acc.add(4, p.x); acc.add(5, p.y); }
-  else acc.add(3, 1.0);
-  if (live_fc) acc.add(7, phi_fc);
+  if (good) { c[0] += 1.0; c[1] += p.phi; }
+  if (ll == 0) c[2] = fmax(c[2], p.phi);
+  else c[6] += 1.0;
+  if (alive) { c[4] += p.x; c[5] += p.y; }
+  else c[3] += 1.0;
+  if (live_fc) c[7] += phi_fc;
 }
 
 // ---- fused moments (FIN_KICK_FUSED) ---------------------------------------------------------------------------------
@@ -184,25 +200,34 @@ __device__ __forceinline__ void seg_accumulate(const AccCol& acc, const Pt& p, u
 //   sum phi_r = sum u - n delta,   sum phi_r^2 = sum u^2 - 2 delta sum u + n delta^2
 // for every particle whose classification cannot change within |delta| <= m.  The others -- within m of the 2 pi wrap of
 // the relative phase, or within m of the marking threshold P + 3 pi -- are appended to a side list (DeferList) and
-// resolved one by one with the true R, their contributions summed in 64-bit FIXED POINT so that the (arbitrary) list
-// order cannot change a bit of the result.  A prediction that misses by more than m, or a list overflow, hands the kick
-// to the stand-alone moment kernel (k_moments, DevStats::moments_fallback).
-// slots: 0 n_good before marking (all particles)   1 sum phi over good, non-deferred      2 n_lloss != 0 (all)
-//        3 sum phi right after OP_FREQ_CHANGE (loss == 0)   4 n alive, non-deferred       5 sum u alive, non-deferred
-//        6 n good non-deferred   7 sum u   8 sum u^2   9 sum x   10 sum x^2   11 sum y   12 sum y^2   13 sum w (good, non-def.)
-//        14 MAX (x-x_avg)^2+(y-y_avg)^2 over loss == 0 (all)    15 deferred particles
-enum { KF_NGOOD = 0, KF_SPHI, KF_NLLOSS, KF_SPHI_FC, KF_NALIVE_M, KF_SU_ALIVE, KF_NGOOD_M, KF_SU, KF_SU2, KF_SX, KF_SX2, KF_SY,
-       KF_SY2, KF_SW, KF_R2MAX, KF_NDEFER };
+// resolved one by one with the true R, their contributions summed in two-limb 64-bit FIXED POINT (2^-80 resolution) so
+// that the (arbitrary) list order cannot change a bit of the result.  A prediction that misses by more than m, or a list
+// overflow, hands the kick to the stand-alone moment kernel (k_moments, DevStats::moments_fallback).
+// slots: 0 packed counts A: n_good before marking (all particles) | n_lloss != 0 (all) << 21 | deferred << 42
+//        1 packed counts B: n alive, non-deferred | n good, non-deferred << 21
+//        2 sum phi over good non-deferred   3 sum u alive non-deferred   4 sum u   5 sum u^2   6 sum x   7 sum x^2   8 sum y
+//        9 sum y^2   10 sum w (good, non-deferred)   11 MAX (x-x_avg)^2+(y-y_avg)^2 over loss == 0 (all)
+//        12 sum phi right after OP_FREQ_CHANGE (loss == 0; FIN_FREQ only)
+// The counts are integers packed into the bit pattern of a slot (21-bit fields hold a thread's share of up to 2^32 particles;
+// the block / grid folds unpack them into doubles).
+enum { SEG_ACC = 13 };  // columns of the epilogue's shared-memory accumulator (>= KF_NACC, SEGL_NS)
+enum { KF_CNTA = 0, KF_CNTB, KF_SPHI, KF_SU_ALIVE, KF_SU, KF_SU2, KF_SX, KF_SX2, KF_SY, KF_SY2, KF_SW, KF_R2MAX, KF_SPHI_FC, KF_NACC };
+// totals after the grid fold (doubles): the unpacked counts follow the sums
+enum { KT_NGOOD = 0, KT_NLLOSS, KT_NDEFER, KT_NALIVE_M, KT_NGOOD_M, KT_SPHI, KT_SU_ALIVE, KT_SU, KT_SU2, KT_SX, KT_SX2, KT_SY, KT_SY2,
+       KT_SW, KT_R2MAX, KT_SPHI_FC };
 struct FusedCtx {
   double pivot, m, cand_thr, amb_thr, xa, ya;
 };
+struct FusedAcc {  // sums of one loop iteration (registers)
+  unsigned long long ca, cb;
+  double s[KF_NACC];
+};
 
-__device__ __forceinline__ void seg_accumulate_fused(const AccCol& acc, const Pt& p, u32 ll, double phi_fc, bool live_fc, const FusedCtx& f,
+__device__ __forceinline__ void seg_accumulate_fused(FusedAcc& c, const Pt& p, u32 ll, double phi_fc, bool live_fc, const FusedCtx& f,
                                                      DeferList* dl, u32 local_idx) {
   const bool alive = p.loss == 0, good = alive && ll == 0;
-  if (ll != 0) acc.add(KF_NLLOSS, 1.0);
-  if (live_fc) acc.add(KF_SPHI_FC, phi_fc);
-  if (good) acc.add(KF_NGOOD, 1.0);
+  c.ca += (good ? 1ull : 0ull) | ((ll != 0 ? 1ull : 0ull) << 21);
+  if (live_fc) c.s[KF_SPHI_FC] += phi_fc;
   // beam_kernel.cu:1556 marks `phi > <phi>_good + 3 pi && lloss != 1` whatever the transverse loss flag says
   const bool cand = ll != 1u && (p.phi - f.pivot > f.cand_thr);
   double u = 0.0;
@@ -211,7 +236,7 @@ __device__ __forceinline__ void seg_accumulate_fused(const AccCol& acc, const Pt
     u = rel_phi(p.phi, f.pivot);
     amb = !(fabs(u) <= f.amb_thr);  // also catches NaN
     const double tx = p.x - f.xa, ty = p.y - f.ya;
-    acc.mx(KF_R2MAX, tx * tx + ty * ty);
+    c.s[KF_R2MAX] = fmax(c.s[KF_R2MAX], tx * tx + ty * ty);
   }
   if (cand || amb) {
     const u32 k = atomicAdd(&dl->count, 1u);
@@ -220,47 +245,116 @@ __device__ __forceinline__ void seg_accumulate_fused(const AccCol& acc, const Pt
       e.phi = p.phi; e.x = p.x; e.y = p.y; e.w = p.w;
       e.tag = (unsigned long long)local_idx | ((unsigned long long)((alive ? 1u : 0u) | (ll != 0 ? 2u : 0u) | (cand ? 4u : 0u)) << 32);
     }
-    acc.add(KF_NDEFER, 1.0);
+    c.ca += 1ull << 42;
   } else if (alive) {
-    acc.add(KF_NALIVE_M, 1.0);
-    acc.add(KF_SU_ALIVE, u);
+    c.cb += 1ull | ((good ? 1ull : 0ull) << 21);
+    c.s[KF_SU_ALIVE] += u;
     if (good) {
-      acc.add(KF_NGOOD_M, 1.0);
-      acc.add(KF_SPHI, p.phi);
-      acc.add(KF_SU, u); acc.fma2(KF_SU2, u);
-      acc.add(KF_SX, p.x); acc.fma2(KF_SX2, p.x);
-      acc.add(KF_SY, p.y); acc.fma2(KF_SY2, p.y);
-      acc.add(KF_SW, p.w);
+      c.s[KF_SPHI] += p.phi;
+      c.s[KF_SU] += u; c.s[KF_SU2] = fma(u, u, c.s[KF_SU2]);
+      c.s[KF_SX] += p.x; c.s[KF_SX2] = fma(p.x, p.x, c.s[KF_SX2]);
+      c.s[KF_SY] += p.y; c.s[KF_SY2] = fma(p.y, p.y, c.s[KF_SY2]);
+      c.s[KF_SW] += p.w;
     }
   }
 }
+// folds the iteration's sums into the thread's shared-memory column (fc: the FIN_FREQ slot is in use)
+__device__ __forceinline__ void fused_flush(double* col, const FusedAcc& c, bool fc) {
+  const int NF = KF_NACC - 1;
+  double t[NF];
+#pragma unroll
+  for (int s = 0; s < NF; ++s) t[s] = lds_f64(col + s * HPS_BLOCK);
+  t[KF_CNTA] = __longlong_as_double(__double_as_longlong(t[KF_CNTA]) + (long long)c.ca);
+  t[KF_CNTB] = __longlong_as_double(__double_as_longlong(t[KF_CNTB]) + (long long)c.cb);
+#pragma unroll
+  for (int s = KF_SPHI; s < NF; ++s) t[s] = s == KF_R2MAX ? fmax(t[s], c.s[s]) : t[s] + c.s[s];
+#pragma unroll
+  for (int s = 0; s < NF; ++s) sts_f64(col + s * HPS_BLOCK, t[s]);
+  if (fc) sts_f64(col + KF_SPHI_FC * HPS_BLOCK, lds_f64(col + KF_SPHI_FC * HPS_BLOCK) + c.s[KF_SPHI_FC]);
+}
+// the thread's column -> the 16 doubles that go through the block / grid fold
+__device__ __forceinline__ void fused_unpack(const double* col, double (&v)[16]) {
+  const unsigned long long ca = (unsigned long long)__double_as_longlong(col[KF_CNTA * HPS_BLOCK]);
+  const unsigned long long cb = (unsigned long long)__double_as_longlong(col[KF_CNTB * HPS_BLOCK]);
+  v[KT_NGOOD] = (double)(ca & 0x1fffffull); v[KT_NLLOSS] = (double)((ca >> 21) & 0x1fffffull); v[KT_NDEFER] = (double)(ca >> 42);
+  v[KT_NALIVE_M] = (double)(cb & 0x1fffffull); v[KT_NGOOD_M] = (double)((cb >> 21) & 0x1fffffull);
+  v[KT_SPHI] = col[KF_SPHI * HPS_BLOCK]; v[KT_SU_ALIVE] = col[KF_SU_ALIVE * HPS_BLOCK]; v[KT_SU] = col[KF_SU * HPS_BLOCK];
+  v[KT_SU2] = col[KF_SU2 * HPS_BLOCK]; v[KT_SX] = col[KF_SX * HPS_BLOCK]; v[KT_SX2] = col[KF_SX2 * HPS_BLOCK];
+  v[KT_SY] = col[KF_SY * HPS_BLOCK]; v[KT_SY2] = col[KF_SY2 * HPS_BLOCK]; v[KT_SW] = col[KF_SW * HPS_BLOCK];
+  v[KT_R2MAX] = col[KF_R2MAX * HPS_BLOCK]; v[KT_SPHI_FC] = col[KF_SPHI_FC * HPS_BLOCK];
+}
 
-// The pilot: one on-axis particle at (<phi>_good, <W>_good) of the previous kick through the segment's maps (the
-// reference-order maps with nvcc's operators; accuracy is irrelevant here, the result is only a pivot).  One copy in the
-// module (noinline), run by thread 0 of every block ahead of the sweep.
+// The pilot: one ON-AXIS particle at (<phi>_good, <W>_good) of the previous kick through the segment's maps, by thread 0
+// of every block ahead of the sweep.  Only a pivot comes out of it, so it runs the fast forms of the maps specialised
+// for x = x' = y = y' = 0 (I0 = 1, I1 = 0: no Bessel functions, no transverse update) -- about 1 us of one thread.
 __device__ __noinline__ double pilot_phase(const Op* ops, const OpC* opcs, int nops, double phi, double w, double mass, double charge) {
-  Pt p = {0.0, 0.0, 0.0, 0.0, phi, w, 0u};
   const double inv_mass = 1.0 / mass;
   for (int k = 0; k < nops; ++k) {
     const Op& op = ops[k];
     const double* q = op.p;
     const double* c = opcs[k].c;
     switch (op.type) {
-      case OP_DRIFT: p.phi += c[D_TWOPI_HL] / (q[2] * beta_of<MathLib>(p.w, mass, inv_mass)); break;
-      case OP_QUAD_HALF: p.phi += c[Q_TWOPI_LEN_HALF] / (q[3] * beta_of<MathLib>(p.w, mass, inv_mass)); break;
-      case OP_GAP_FIRST: op_gap_first<MathLib>(p, q, c, op.flag != 0, mass, inv_mass); break;
-      case OP_GAP_SECOND: op_gap_second<MathLib>(p, q, c, op.flag != 0, mass, inv_mass); break;
-      case OP_DIPOLE_FIRST: op_dipole(p, q, false, mass); break;
-      case OP_DIPOLE_SECOND: op_dipole(p, q, true, mass); break;
-      case OP_BUNCHER: op_buncher(p, q, op.elem, mass, charge); break;
-      case OP_FREQ_CHANGE: p.phi *= q[0]; break;
+      case OP_DRIFT: phi += c[D_PH_OVER_WL] * inv_beta_of(w, inv_mass); break;
+      case OP_QUAD_HALF: phi += c[Q_PH_OVER_WL] * inv_beta_of(w, inv_mass); break;
+      case OP_GAP_FIRST: {
+        const double ib = inv_beta_of(w, inv_mass);
+        if (q[G_AMP] == 0.0) phi += c[GF_DD_OVER_WL] * ib;
+        else if (op.flag == 0) phi += (c[GC_BETA_IN] * ib) * c[GC_PI_CLBL_DPS] + c[GF_DCLQ_OVER_WL] * ib;
+        else phi += (1.0 - c[GC_BETAG_CCL] * (c[GF_IBETA_IN] - ib)) * c[GC_PI_CLBL_DPS];
+        break;
+      }
+      case OP_GAP_SECOND: {  // op_gap_second_f on the axis
+        const bool ccl = op.flag != 0;
+        const double ib1 = inv_beta_of(w, inv_mass), beta = 1.0 / ib1;
+        double bb = beta;
+        if (beta > 1.1 * q[G_FBC]) bb = q[G_FBC];
+        else if (beta < q[G_FBMIN]) bb = q[G_FBMIN];
+        const double t_fac = q[G_T0] + bb * (q[G_T1] + bb * (q[G_T2] + bb * (q[G_T3] + bb * (q[G_T4] + bb * q[G_T5]))));
+        const double coef = bb * bb * c[GF_INV_TTF_DEN];
+        const double tp_fac = coef * (q[G_T1] + bb * (2 * q[G_T2] + bb * (3 * q[G_T3] + bb * (4 * q[G_T4] + 5 * bb * q[G_T5]))));
+        const double sp_fac = -coef * (q[G_S1] + bb * (2 * q[G_S2] + bb * (3 * q[G_S3] + bb * (4 * q[G_S4] + 5 * bb * q[G_S5]))));
+        if (q[G_AMP] == 0.0 || (ccl && beta < q[G_FBMIN])) { phi += c[GF_DD_OVER_WL] * ib1; break; }
+        double tw = t_fac;
+        if (ccl) tw = t_fac - K_TWOPI * tp_fac * (c[GC_BETA_IN] * ib1 - 1.0) * c[GF_BETAG_OVER_BIN];
+        double phi1 = phi + q[G_PHSHIFT];
+        if (ccl) phi1 += c[GC_PH_CONST] - c[GF_DG_OVER_WL] * ib1;
+        double sinp1, cosp1;
+        sincos(phi1, &sinp1, &cosp1);
+        const double prome1 = -c[GC_CON1] * (tp_fac * (sinp1 - c[GC_SINPS]) + sp_fac * (cosp1 - c[GC_COSPS]));
+        sincos(phi1 + prome1, &sinp1, &cosp1);
+        w += c[GC_AQ_EFL] * tw * cosp1;
+        const double ib = inv_beta_of(w, inv_mass);
+        const double prome = -2.0 * c[GC_CON1] * tp_fac * (sinp1 - c[GC_SINPS]);
+        if (ccl) phi += (1.0 - c[GC_BETAG_CCL] * (c[GF_IBETA_OUT] - ib)) * c[GC_PI_CLBL_DPS] + prome;
+        else phi += (c[GC_BETA_OUT] * ib) * c[GC_PI_CLBL_DPS] + prome + c[GF_DCLQ_OVER_WL] * ib;
+        break;
+      }
+      case OP_DIPOLE_FIRST: case OP_DIPOLE_SECOND: case OP_BUNCHER: {
+        Pt p = {0.0, 0.0, 0.0, 0.0, phi, w, 0u};
+        if (op.type == OP_BUNCHER) op_buncher(p, q, op.elem, mass, charge); else op_dipole(p, q, op.type == OP_DIPOLE_SECOND, mass);
+        phi = p.phi; w = p.w;
+        break;
+      }
+      case OP_FREQ_CHANGE: phi *= q[0]; break;
       default: break;  // kick (no field on the axis at the bunch centre), rotation, steerer, apertures
     }
   }
-  return p.phi;
+  return phi;
 }
 
-__device__ __forceinline__ long long to_fix(double v, double scale) { return __double2ll_rn(v * scale); }
+// Two-limb fixed point: a summand v, pre-scaled by a power of two into |v| < 8, becomes hi = rint(v 2^40) and
+// lo = rint((v - hi 2^-40) 2^80) -- the remainder is exact in fp64 -- and the limbs are summed as 64-bit integers:
+// 2^19 summands (8 ranks x 2^16 deferred particles) stay below 2^63, the resolution is 2^-80 of the pre-scaled value
+// (finer than one ulp of any summand that matters), and integer addition does not care about the order.
+struct Fix2 {
+  long long hi, lo;
+};
+__device__ __forceinline__ void fix_add(long long& hi, long long& lo, double v) {
+  const double h = rint(v * 0x1p40);
+  hi += (long long)h;
+  lo += __double2ll_rn(fma(-h, 0x1p-40, v) * 0x1p80);
+}
+__device__ __forceinline__ double fix_value(long long hi, long long lo) { return (double)hi * 0x1p-40 + (double)lo * 0x1p-80; }
 
 // sum of NV 64-bit integers per thread over the block -> s_out[0..NV) (shared); every thread of the block calls it
 template <int NV>
@@ -288,22 +382,19 @@ __device__ __forceinline__ void block_sum_i64(long long (&v)[NV], long long* s_w
 __device__ void scheff_policy(DevStats* st, ScDev* sc, const KickParams& kp, double r2max);
 __device__ void finalize_moments(const double* t, double ref, u32 n_global, DevStats* st, ScDev* sc, const KickParams& kp, int do_policy);
 
-// fixed-point scales of the deferred particles' contributions: 2^62 / (entries x bound of the summand)
-// (8 ranks x 2^16 entries: a summand may use 43 bits)
-#define FX_DPHI 4294967296.0           /* 2^32: |phi - P| < 2^11 */
-#define FX_PR 2199023255552.0          /* 2^41: |phi_r| <= pi */
-#define FX_PR2 549755813888.0          /* 2^39: phi_r^2 < 16 */
-#define FX_X 70368744177664.0          /* 2^46: |x|, |y| < 2^-3 m */
-#define FX_X2 562949953421312.0        /* 2^49: x^2 < 2^-6 */
-#define FX_W 8589934592.0              /* 2^33: w < 2^10 MeV */
+// pre-scales (exact powers of two) that bring a deferred particle's summands into |v| < 8
+#define PS_DPHI 0x1p-9   /* |phi - P| < 2^12 rad (checked) */
+#define PS_W 0x1p-7      /* w < 2^10 MeV (checked) */
+#define PS_PR2 0x1p-1    /* phi_r^2 <= pi^2 */
 
-// Last block of a FIN_KICK_FUSED sweep; every thread of the block calls it with this rank's totals in t[0..16) (shared).
-// Ends with DevStats / ScDev exactly as Beam::UpdateStatForSpaceCharge + Scheff::Start's policy leave them, or with
-// st->moments_fallback != 0 (1: redo the whole chain, 2: longitudinal losses are marked, redo the moment sums only).
+// Last block of a FIN_KICK_FUSED sweep; every thread of the block calls it with this rank's totals in t[0..16) (shared,
+// KT_* layout).  Ends with DevStats / ScDev exactly as Beam::UpdateStatForSpaceCharge + Scheff::Start's policy leave them,
+// or with st->moments_fallback != 0 (1: redo the whole chain, 2: longitudinal losses are marked, redo the moment sums only).
 __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
                                     const KickParams& kp, DeferList* dl, const XrView& xr, int fin_mode) {
-  __shared__ long long s_warp[8 * 12];
-  __shared__ long long s_i[12];
+  constexpr int NI = 20;
+  __shared__ long long s_warp[8 * NI];
+  __shared__ long long s_i[NI];
   __shared__ double s_g[HPS_XR_NS];   // round 1: totals over all ranks
   __shared__ double s_x[HPS_XR_NS];   // rounds 2 and 3
   __shared__ double s_R1, s_R2, s_SG0, s_nG1, s_nnew;
@@ -314,41 +405,43 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
   const u32 K = min(cnt, HPS_DEFER_CAP);
   // ---- pass 1: the deferred members of the good set, the candidates
   {
-    long long v[4] = {0, 0, 0, (threadIdx.x == 0 && cnt > HPS_DEFER_CAP) ? 1 : 0};  // n good, sum (phi - P), candidates, bad
+    long long v[5] = {0, 0, 0, 0, (threadIdx.x == 0 && cnt > HPS_DEFER_CAP) ? 1 : 0};  // n good, sum (phi - P) hi lo, candidates, bad
     for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
       const DeferEntry& e = dl->e[k];
       const u32 fl = (u32)(__ldcg(&e.tag) >> 32);
       const double d = __ldcg(&e.phi) - P;
       if ((fl & 3u) == 1u) {
         v[0] += 1;
-        if (!(fabs(d) < 2048.0)) v[3] += 1; else v[1] += to_fix(d, FX_DPHI);
+        if (!(fabs(d) < 4096.0)) v[4] += 1; else fix_add(v[1], v[2], d * PS_DPHI);
       }
-      if (fl & 4u) v[2] += 1;
+      if (fl & 4u) v[3] += 1;
     }
-    block_sum_i64<4>(v, s_warp, s_i);
-  }
-  if (threadIdx.x < SEG_NS) s_g[threadIdx.x] = t[threadIdx.x];
-  if (threadIdx.x == 0) {
-    s_g[16] = (double)s_i[0]; s_g[17] = __longlong_as_double(s_i[1]); s_g[18] = (double)s_i[2]; s_g[19] = (double)s_i[3];
-    s_g[20] = (double)K;
+    if (cnt != 0u) block_sum_i64<5>(v, s_warp, s_i);  // (block-uniform condition)
+    else if (threadIdx.x < 5) s_i[threadIdx.x] = 0;
   }
   __syncthreads();
-  if (p2p) xr_exchange_p2p(s_g, 21, 1u << KF_R2MAX, xr, 1u << 17);
+  if (threadIdx.x < 16) s_g[threadIdx.x] = t[threadIdx.x];
+  if (threadIdx.x == 0) {
+    s_g[16] = (double)s_i[0]; s_g[17] = __longlong_as_double(s_i[1]); s_g[18] = __longlong_as_double(s_i[2]);
+    s_g[19] = (double)s_i[3]; s_g[20] = (double)s_i[4]; s_g[21] = (double)K;
+  }
+  __syncthreads();
+  if (p2p) xr_exchange_p2p(s_g, 22, 1u << KT_R2MAX, xr, (1u << 17) | (1u << 18));
   if (threadIdx.x == 0) {
     // Beam::ChangeFrequency -> UpdateAvgPhi() (beam.cpp:1666; divides by N - num_loss, stale count)
-    if (fin_mode & FIN_FREQ) st->v[HPS_STAT_PHI_AVG] = s_g[KF_SPHI_FC] / (double)(u32)(b.n_global - st->num_loss);
-    const double n_g0 = s_g[KF_NGOOD], nl = s_g[16];
-    const double sg0 = s_g[KF_SPHI] + nl * P + (double)__double_as_longlong(s_g[17]) * (1.0 / FX_DPHI);
+    if (fin_mode & FIN_FREQ) st->v[HPS_STAT_PHI_AVG] = s_g[KT_SPHI_FC] / (double)(u32)(b.n_global - st->num_loss);
+    const double n_g0 = s_g[KT_NGOOD], nl = s_g[16];
+    const double sg0 = s_g[KT_SPHI] + nl * P + fix_value(__double_as_longlong(s_g[17]), __double_as_longlong(s_g[18])) * (1.0 / PS_DPHI);
     const double r1 = n_g0 > 0.0 ? sg0 / n_g0 : -99999.0;
     u32 code = 0u;
-    if (s_g[19] != 0.0 || !(n_g0 > 0.0) || !(fabs(r1 - P) <= f.m) || n_g0 != s_g[KF_NGOOD_M] + nl) code = 1u;
-    s_R1 = r1; s_R2 = r1; s_SG0 = sg0; s_nG1 = n_g0; s_nnew = 0.0; s_code = code; s_Kall = (u32)s_g[20]; s_ncand = (u32)s_g[18];
+    if (s_g[20] != 0.0 || !(n_g0 > 0.0) || !(fabs(r1 - P) <= f.m) || n_g0 != s_g[KT_NGOOD_M] + nl) code = 1u;
+    s_R1 = r1; s_R2 = r1; s_SG0 = sg0; s_nG1 = n_g0; s_nnew = 0.0; s_code = code; s_Kall = (u32)s_g[21]; s_ncand = (u32)s_g[19];
   }
   __syncthreads();
   if (s_code == 0u && s_ncand != 0u) {
     // ---- pass 2: Beam::UpdateLongitudinalLoss (beam_kernel.cu:1549-1559) on the candidates
     const double thr = s_R1 + K_TWOPI + K_PI;
-    long long v[3] = {0, 0, 0};  // newly non-zero lloss, marked members of the good set, their sum (phi - P)
+    long long v[4] = {0, 0, 0, 0};  // newly non-zero lloss, marked members of the good set, their sum (phi - P) hi lo
     for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
       DeferEntry& e = dl->e[k];
       const unsigned long long tag = __ldcg(&e.tag);
@@ -357,18 +450,20 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
       if ((fl & 4u) && phi > thr) {
         b.lloss[(u32)tag] = 1u;
         if (!(fl & 2u)) v[0] += 1;
-        if ((fl & 3u) == 1u) { v[1] += 1; v[2] += to_fix(phi - P, FX_DPHI); }
+        if ((fl & 3u) == 1u) { v[1] += 1; fix_add(v[2], v[3], (phi - P) * PS_DPHI); }
         e.tag = tag | (2ull << 32);
       }
     }
-    block_sum_i64<3>(v, s_warp, s_i);
-    if (threadIdx.x == 0) { s_x[0] = (double)s_i[0]; s_x[1] = (double)s_i[1]; s_x[2] = __longlong_as_double(s_i[2]); }
+    if (K != 0u) block_sum_i64<4>(v, s_warp, s_i);
+    else if (threadIdx.x < 4) s_i[threadIdx.x] = 0;
     __syncthreads();
-    if (p2p) xr_exchange_p2p(s_x, 3, 0u, xr, 1u << 2);
+    if (threadIdx.x == 0) { s_x[0] = (double)s_i[0]; s_x[1] = (double)s_i[1]; s_x[2] = __longlong_as_double(s_i[2]); s_x[3] = __longlong_as_double(s_i[3]); }
+    __syncthreads();
+    if (p2p) xr_exchange_p2p(s_x, 4, 0u, xr, (1u << 2) | (1u << 3));
     if (threadIdx.x == 0) {
       const double n_mark = s_x[1];
-      const double s_mark = n_mark * P + (double)__double_as_longlong(s_x[2]) * (1.0 / FX_DPHI);
-      const double n_g1 = s_g[KF_NGOOD] - n_mark;
+      const double s_mark = n_mark * P + fix_value(__double_as_longlong(s_x[2]), __double_as_longlong(s_x[3])) * (1.0 / PS_DPHI);
+      const double n_g1 = s_g[KT_NGOOD] - n_mark;
       s_nnew = s_x[0];
       s_nG1 = n_g1;
       s_R2 = n_g1 > 0.0 ? (s_SG0 - s_mark) / n_g1 : -99999.0;
@@ -381,53 +476,60 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
   if (threadIdx.x == 0 && s_code == 0u && !(fabs(delta) <= f.m)) s_code = 2u;  // (marks are written: only the sums are redone)
   __syncthreads();
   // ---- pass 3: the deferred particles' relative phases about the true <phi>_good, summed in fixed point
+  // v: 0 n alive, 1 n good, 2 bad, 3-4 sum pr alive, 5-6 sum pr, 7-8 pr^2, 9-10 x, 11-12 x^2, 13-14 y, 15-16 y^2, 17-18 w
   if (s_code == 0u && s_Kall != 0u) {
-    long long v[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // n alive, sum pr alive, n good, sum pr, pr^2, x, x^2, y, y^2, w, bad
+    long long v[NI];
+#pragma unroll
+    for (int k = 0; k < NI; ++k) v[k] = 0;
     for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
       const DeferEntry& e = dl->e[k];
       const u32 fl = (u32)(__ldcg(&e.tag) >> 32);
       if (!(fl & 1u)) continue;
       const double pr = rel_phi(__ldcg(&e.phi), R2);
-      v[0] += 1; v[1] += to_fix(pr, FX_PR);
+      v[0] += 1; fix_add(v[3], v[4], pr);
       if (fl & 2u) continue;
       const double x = __ldcg(&e.x), y = __ldcg(&e.y), w = __ldcg(&e.w);
-      if (!(fabs(x) < 0.125 && fabs(y) < 0.125 && fabs(w) < 1024.0)) { v[10] += 1; continue; }
-      v[2] += 1; v[3] += to_fix(pr, FX_PR); v[4] += to_fix(pr * pr, FX_PR2);
-      v[5] += to_fix(x, FX_X); v[6] += to_fix(x * x, FX_X2); v[7] += to_fix(y, FX_X); v[8] += to_fix(y * y, FX_X2);
-      v[9] += to_fix(w, FX_W);
+      if (!(fabs(x) < 2.0 && fabs(y) < 2.0 && fabs(w) < 1024.0)) { v[2] += 1; continue; }
+      v[1] += 1;
+      fix_add(v[5], v[6], pr); fix_add(v[7], v[8], pr * pr * PS_PR2);
+      fix_add(v[9], v[10], x); fix_add(v[11], v[12], x * x); fix_add(v[13], v[14], y); fix_add(v[15], v[16], y * y);
+      fix_add(v[17], v[18], w * PS_W);
     }
-    block_sum_i64<12>(v, s_warp, s_i);
-    if (threadIdx.x < 12) s_x[threadIdx.x] = __longlong_as_double(s_i[threadIdx.x]);
+    if (K != 0u) block_sum_i64<NI>(v, s_warp, s_i);
+    else if (threadIdx.x < NI) s_i[threadIdx.x] = 0;
     __syncthreads();
-    if (p2p) xr_exchange_p2p(s_x, 12, 0u, xr, 0xfffu);
+    if (threadIdx.x < NI) s_x[threadIdx.x] = __longlong_as_double(s_i[threadIdx.x]);
+    __syncthreads();
+    if (p2p) xr_exchange_p2p(s_x, NI, 0u, xr, (1u << NI) - 1u);
   } else {
-    if (threadIdx.x < 12) s_x[threadIdx.x] = 0.0;  // bit pattern of the integer 0
+    if (threadIdx.x < NI) s_x[threadIdx.x] = 0.0;  // bit pattern of the integer 0
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    auto I = [&](int k) { return (double)__double_as_longlong(s_x[k]); };
+    auto I = [&](int k) { return __double_as_longlong(s_x[k]); };
+    auto F = [&](int k) { return fix_value(I(k), I(k + 1)); };
     u32 code = s_code;
-    if (code == 0u && (I(10) != 0.0 || s_nG1 != s_g[KF_NGOOD_M] + I(2))) code = 2u;
+    if (code == 0u && (I(2) != 0 || s_nG1 != s_g[KT_NGOOD_M] + (double)I(1))) code = 2u;
     if (code != 1u) {  // what the first links of the chain leave behind (beam.cpp:776-782, 1007-1009)
       st->num_good = (u32)s_nG1;
       st->v[HPS_STAT_PHI_AVG_GOOD] = R2;
-      st->num_lloss = (u32)(s_g[KF_NLLOSS] + s_nnew);
+      st->num_lloss = (u32)(s_g[KT_NLLOSS] + s_nnew);
     }
     st->need_lloss_pass = 0u;
     st->moments_fallback = code;
     const double err = fmax(fabs(s_R1 - P), fabs(delta));
     if (code == 0u) {
-      const double nm = s_g[KF_NGOOD_M], na = s_g[KF_NALIVE_M];
+      const double nm = s_g[KT_NGOOD_M], na = s_g[KT_NALIVE_M];
       double m9[9];
-      m9[0] = s_g[KF_SU_ALIVE] - na * delta + I(1) * (1.0 / FX_PR);
-      m9[1] = s_g[KF_SU] - nm * delta + I(3) * (1.0 / FX_PR);
-      m9[2] = s_g[KF_SU2] - 2.0 * delta * s_g[KF_SU] + nm * delta * delta + I(4) * (1.0 / FX_PR2);
-      m9[3] = s_g[KF_SX] + I(5) * (1.0 / FX_X);
-      m9[4] = s_g[KF_SX2] + I(6) * (1.0 / FX_X2);
-      m9[5] = s_g[KF_SY] + I(7) * (1.0 / FX_X);
-      m9[6] = s_g[KF_SY2] + I(8) * (1.0 / FX_X2);
-      m9[7] = s_g[KF_SW] + I(9) * (1.0 / FX_W);
-      m9[8] = s_g[KF_R2MAX];
+      m9[0] = s_g[KT_SU_ALIVE] - na * delta + F(3);
+      m9[1] = s_g[KT_SU] - nm * delta + F(5);
+      m9[2] = s_g[KT_SU2] - 2.0 * delta * s_g[KT_SU] + nm * delta * delta + F(7) * (1.0 / PS_PR2);
+      m9[3] = s_g[KT_SX] + F(9);
+      m9[4] = s_g[KT_SX2] + F(11);
+      m9[5] = s_g[KT_SY] + F(13);
+      m9[6] = s_g[KT_SY2] + F(15);
+      m9[7] = s_g[KT_SW] + F(17) * (1.0 / PS_W);
+      m9[8] = s_g[KT_R2MAX];
       finalize_moments(m9, R2, b.n_global, st, sc, kp, 1);
       st->n_fused++;
       st->n_deferred += (unsigned long long)s_Kall;
@@ -448,6 +550,37 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
   }
 }
 
+// ---- per-thread asynchronous staging of the NEXT particle pair ------------------------------------------------------
+// At 16 Mi particles the beam (0.94 GB) streams from HBM: a thread loads its pair (~1-2 us under load), computes for
+// ~10 us, stores, loads the next pair -- with 4 warps per scheduler that load latency is exposed (ncu: long_scoreboard
+// 20-30 % of the stall samples, profiles/r2a_ncu_k_segment_16mi.txt), and a register prefetch of 28 words does not fit the
+// 128-register budget.  Each thread therefore copies its OWN next pair into its own shared-memory slots with cp.async
+// (LDGSTS: no registers, no block barrier -- a thread only ever reads what it copied itself) while it works on the
+// current pair, and picks it up with cp.async.wait_group at the top of the next iteration.
+struct PairStage {
+  double2 d[6][HPS_BLOCK];  // x xp y yp phi w
+  uint2 f[2][HPS_BLOCK];    // loss lloss
+};
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void stage_issue(PairStage* s, const BeamView& b, u32 i2) {
+  const int t = threadIdx.x;
+  cp_async16(&s->d[0][t], reinterpret_cast<const double2*>(b.x) + i2);
+  cp_async16(&s->d[1][t], reinterpret_cast<const double2*>(b.xp) + i2);
+  cp_async16(&s->d[2][t], reinterpret_cast<const double2*>(b.y) + i2);
+  cp_async16(&s->d[3][t], reinterpret_cast<const double2*>(b.yp) + i2);
+  cp_async16(&s->d[4][t], reinterpret_cast<const double2*>(b.phi) + i2);
+  cp_async16(&s->d[5][t], reinterpret_cast<const double2*>(b.w) + i2);
+  cp_async8(&s->f[0][t], reinterpret_cast<const uint2*>(b.loss) + i2);
+  cp_async8(&s->f[1][t], reinterpret_cast<const uint2*>(b.lloss) + i2);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // PPT = particles per thread.  PPT == 2 moves two adjacent particles with one 128-bit access per
 // array; PPT == 1 halves the register footprint and doubles the resident warps (the maps are chains of
 // dependent fp64 operations, so the sweep is latency-bound before it is bandwidth-bound).
@@ -457,15 +590,17 @@ template <int PPT, int MINB, bool FULL, int MATH>
 __global__ void __launch_bounds__(HPS_BLOCK, MINB)
 k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
           DevStats* st, ScDev* sc, const double2* __restrict__ field, KickParams kp, double* partials,
-          u32* ticket, double* bins, DeferList* dl, const __grid_constant__ XrView xr) {
-  __shared__ Op s_ops[HPS_MAX_SEG_OPS];
-  __shared__ OpC s_opc[HPS_MAX_SEG_OPS];
+          u32* ticket, double* bins, DeferList* dl, int stage, const __grid_constant__ XrView xr) {
   __shared__ KickCtx s_k;
   __shared__ FusedCtx s_f;
   __shared__ double s_cxy[2];
   __shared__ double s_total[SEG_NS];
   __shared__ double s_scratch[HPS_BLOCK];
-  extern __shared__ double s_acc[];  // [SEG_NS][HPS_BLOCK] partial sums of the epilogue, one column per thread
+  // dynamic shared memory, sized per launch (segment_smem): [SEG_ACC][HPS_BLOCK] partial sums of the epilogue, one column
+  // per thread | the cp.async stage of the next particle pair (stage != 0 only) | the segment's op records and constants
+  extern __shared__ double s_acc[];
+  Op* const s_ops = reinterpret_cast<Op*>(s_acc + SEG_ACC * HPS_BLOCK + (stage ? sizeof(PairStage) / sizeof(double) : 0));
+  OpC* const s_opc = reinterpret_cast<OpC*>(s_ops + nops);
 
   pdl_launch_dependents();
   pdl_wait();  // the op constants (k_prepare_ops) and everything below come from preceding kernels
@@ -480,11 +615,11 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
     double* cdst = reinterpret_cast<double*>(s_opc);
     for (int i = threadIdx.x; i < nc; i += blockDim.x) cdst[i] = csrc[i];
   }
-  const AccCol acc = {s_acc + threadIdx.x};
+  double* const col = s_acc + threadIdx.x;  // this thread's column of partial sums
   if (fin_mode != FIN_NONE) {
 #pragma unroll
-    for (int s = 0; s < SEG_NS; ++s) acc.a[s * HPS_BLOCK] = 0.0;
-    if (!fused) acc.a[2 * HPS_BLOCK] = -DBL_MAX;
+    for (int s = 0; s < SEG_ACC; ++s) col[s * HPS_BLOCK] = 0.0;
+    if (!fused) col[2 * HPS_BLOCK] = -DBL_MAX;
   }
   if (threadIdx.x == 0) {
     s_cxy[0] = st->v[HPS_STAT_X_AVG];
@@ -525,15 +660,33 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
 
   if (PPT == 2) {
     const u32 npairs = (b.n + 1) >> 1;
-    for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
-      const double2 X = reinterpret_cast<const double2*>(b.x)[i2];
-      const double2 XP = reinterpret_cast<const double2*>(b.xp)[i2];
-      const double2 Y = reinterpret_cast<const double2*>(b.y)[i2];
-      const double2 YP = reinterpret_cast<const double2*>(b.yp)[i2];
-      const double2 PH = reinterpret_cast<const double2*>(b.phi)[i2];
-      const double2 W = reinterpret_cast<const double2*>(b.w)[i2];
-      const uint2 L = reinterpret_cast<const uint2*>(b.loss)[i2];
-      const uint2 LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
+    PairStage* stg = reinterpret_cast<PairStage*>(s_acc + SEG_ACC * HPS_BLOCK);
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 first = blockIdx.x * blockDim.x + threadIdx.x;
+    if (stage && first < npairs) stage_issue(stg, b, first);
+    for (u32 i2 = first; i2 < npairs; i2 += stride) {
+      double2 X, XP, Y, YP, PH, W;
+      uint2 L, LL;
+      if (stage) {
+        const int t = threadIdx.x;
+        stage_wait();
+        X = stg->d[0][t]; XP = stg->d[1][t]; Y = stg->d[2][t]; YP = stg->d[3][t]; PH = stg->d[4][t]; W = stg->d[5][t];
+        L = stg->f[0][t]; LL = stg->f[1][t];
+        // the next copy may overwrite the slots only after these reads have returned: its index depends on the last of them
+        u32 zero;
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(LL.y ^ __double2hiint(W.y)));
+        const u32 nx = i2 + stride + zero;
+        if (nx < npairs) stage_issue(stg, b, nx);
+      } else {
+        X = reinterpret_cast<const double2*>(b.x)[i2];
+        XP = reinterpret_cast<const double2*>(b.xp)[i2];
+        Y = reinterpret_cast<const double2*>(b.y)[i2];
+        YP = reinterpret_cast<const double2*>(b.yp)[i2];
+        PH = reinterpret_cast<const double2*>(b.phi)[i2];
+        W = reinterpret_cast<const double2*>(b.w)[i2];
+        L = reinterpret_cast<const uint2*>(b.loss)[i2];
+        LL = reinterpret_cast<const uint2*>(b.lloss)[i2];
+      }
       Pt p[2] = {{X.x, XP.x, Y.x, YP.x, PH.x, W.x, L.x}, {X.y, XP.y, Y.y, YP.y, PH.y, W.y, L.y}};
       const u32 ll[2] = {LL.x, LL.y};
       const bool valid[2] = {true, 2 * i2 + 1 < b.n};
@@ -553,11 +706,18 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
           reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p[0].loss, p[1].loss);
       }
       if (fused) {
-        seg_accumulate_fused(acc, p[0], ll[0], fc[0], lf[0], s_f, dl, 2 * i2);
-        if (valid[1]) seg_accumulate_fused(acc, p[1], ll[1], fc[1], lf[1], s_f, dl, 2 * i2 + 1);
+        FusedAcc c;
+        c.ca = 0ull; c.cb = 0ull;
+#pragma unroll
+        for (int s = 0; s < KF_NACC; ++s) c.s[s] = 0.0;
+        seg_accumulate_fused(c, p[0], ll[0], fc[0], lf[0], s_f, dl, 2 * i2);
+        if (valid[1]) seg_accumulate_fused(c, p[1], ll[1], fc[1], lf[1], s_f, dl, 2 * i2 + 1);
+        fused_flush(col, c, (fin_mode & FIN_FREQ) != 0);
       } else if (fin_mode != FIN_NONE) {
-        seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
-        if (valid[1]) seg_accumulate(acc, p[1], ll[1], fc[1], lf[1]);
+        double c[SEGL_NS] = {0.0, 0.0, -DBL_MAX, 0.0, 0.0, 0.0, 0.0, 0.0};
+        seg_accumulate(c, p[0], ll[0], fc[0], lf[0]);
+        if (valid[1]) seg_accumulate(c, p[1], ll[1], fc[1], lf[1]);
+        acc_flush<SEGL_NS>(col, c, 1u << 2);
       }
     }
   } else {
@@ -579,25 +739,36 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
         if (dirty & 32) b.w[i] = p[0].w;
         if ((dirty & 64) && p[0].loss != l0) b.loss[i] = p[0].loss;
       }
-      if (fused) seg_accumulate_fused(acc, p[0], ll[0], fc[0], lf[0], s_f, dl, i);
-      else if (fin_mode != FIN_NONE) seg_accumulate(acc, p[0], ll[0], fc[0], lf[0]);
+      if (fused) {
+        FusedAcc c;
+        c.ca = 0ull; c.cb = 0ull;
+#pragma unroll
+        for (int s = 0; s < KF_NACC; ++s) c.s[s] = 0.0;
+        seg_accumulate_fused(c, p[0], ll[0], fc[0], lf[0], s_f, dl, i);
+        fused_flush(col, c, (fin_mode & FIN_FREQ) != 0);
+      } else if (fin_mode != FIN_NONE) {
+        double c[SEGL_NS] = {0.0, 0.0, -DBL_MAX, 0.0, 0.0, 0.0, 0.0, 0.0};
+        seg_accumulate(c, p[0], ll[0], fc[0], lf[0]);
+        acc_flush<SEGL_NS>(col, c, 1u << 2);
+      }
     }
   }
   if (fin_mode == FIN_NONE) return;
   double v[SEG_NS];
-#pragma unroll
-  for (int s = 0; s < SEG_NS; ++s) v[s] = acc.a[s * HPS_BLOCK];
   if (fused) {
-    if (grid_reduce<SEG_NS>(v, 1u << KF_R2MAX, partials, ticket, s_total, s_scratch, xr, false)) {
+    fused_unpack(col, v);
+    if (grid_reduce<SEG_NS>(v, 1u << KT_R2MAX, partials, ticket, s_total, s_scratch, xr, false)) {
       fused_kick_finalize(s_total, s_f, b, st, sc, bins, kp, dl, xr, fin_mode);
     }
     return;
   }
+#pragma unroll
+  for (int s = 0; s < SEG_NS; ++s) v[s] = s < SEGL_NS ? col[s * HPS_BLOCK] : 0.0;
   if (grid_reduce<SEG_NS>(v, 1u << 2, partials, ticket, s_total, s_scratch, xr)) {
     if (threadIdx.x == 0) finalize_segment(fin_mode, s_total, st, b.n_global);
   }
 }
-#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, ScDev*, const double2*, KickParams, double*, u32*, double*, DeferList*, const __grid_constant__ XrView
+#define SEG_ARGS BeamView, const Op*, const OpC*, int, int, int, int, DevStats*, ScDev*, const double2*, KickParams, double*, u32*, double*, DeferList*, int, const __grid_constant__ XrView
 typedef void (*SegKernel)(SEG_ARGS);
 // variant -> kernel.  20 (default): 2 particles/thread, reference-order maps with exact branch-free arithmetic;
 // 0: 2 particles/thread, fast maps; 1 / 2: fast maps, 1 particle/thread at 3 / 4 blocks per SM;
@@ -1665,16 +1836,19 @@ static cudaError_t launch_chain(const LaunchCfg& c, void (*kernel)(KArgs...), di
 void launch_prepare_ops(const LaunchCfg& c, const Op* ops, OpC* opcs, int nops, double mass, double charge) {
   if (nops > 0) k_prepare_ops<<<(nops + 63) / 64, 64, 0, c.stream>>>(ops, opcs, nops, mass, charge);
 }
-size_t segment_smem() { return (size_t)SEG_NS * HPS_BLOCK * sizeof(double); }
+size_t segment_smem(int nops, int stage) {
+  return (size_t)SEG_ACC * HPS_BLOCK * sizeof(double) + (stage ? sizeof(PairStage) : 0) + (size_t)nops * (sizeof(Op) + sizeof(OpC));
+}
 void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, const Op* ops, const OpC* opcs, int nops,
                     int fin_mode, int dirty, int compat, DevStats* st, ScDev* sc, const double2* field,
                     const KickParams& kp, double* bins, DeferList* dl) {
   bool full = false;
   for (int k = 0; k < nops; ++k) full |= host_ops[k].type == OP_DIPOLE_FIRST || host_ops[k].type == OP_DIPOLE_SECOND || host_ops[k].type == OP_BUNCHER;
   const unsigned grid1 = c.grid_seg1, grid2 = c.grid_seg;
-#define SEG_CALL b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, bins, dl, c.xr
-  if (full) launch_chain(c, seg_kernel(seg_full_variant(c.seg_variant)), dim3(grid1), dim3(HPS_BLOCK), segment_smem(), SEG_CALL);
-  else launch_chain(c, seg_kernel(c.seg_variant), dim3(grid2), dim3(HPS_BLOCK), segment_smem(), SEG_CALL);
+#define SEG_CALL b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, bins, dl, c.stage, c.xr
+  const size_t smem = segment_smem(nops, c.stage);
+  if (full) launch_chain(c, seg_kernel(seg_full_variant(c.seg_variant)), dim3(grid1), dim3(HPS_BLOCK), smem, SEG_CALL);
+  else launch_chain(c, seg_kernel(c.seg_variant), dim3(grid2), dim3(HPS_BLOCK), smem, SEG_CALL);
 #undef SEG_CALL
 }
 void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
@@ -1826,9 +2000,10 @@ void launch_rel_phi_out(const LaunchCfg& c, const BeamView& b, const DevStats* s
 }
 int segment_occupancy(int variant) {
   // static + dynamic shared memory of the sweep exceed the 48 KB default: opt in once per variant and device
-  cudaFuncSetAttribute(seg_kernel(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segment_smem());
+  const size_t smem = segment_smem(HPS_MAX_SEG_OPS, 1);  // the largest launch
+  cudaFuncSetAttribute(seg_kernel(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg_kernel(variant), HPS_BLOCK, segment_smem());
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg_kernel(variant), HPS_BLOCK, smem);
   return nb;
 }
 int segment_full_variant(int variant) { return seg_full_variant(variant); }

@@ -18,6 +18,7 @@ struct LaunchCfg {
   double* partials;       // [max grid][HPS_NSLOT]
   u32* ticket;            // [0] reductions, [1] deposit hand-off (sharded beams)
   int pdl;                // launch the kick-chain kernels with programmatic stream serialization
+  int stage;              // the sweep stages each thread's next particle pair in shared memory with cp.async
   XrView xr;              // cross-rank exchange of a particle-sharded beam (mode XR_NONE otherwise)
 };
 
