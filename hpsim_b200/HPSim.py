@@ -503,6 +503,37 @@ class SpaceCharge:
     def get_remesh_threshold(self): return self._get(K.SC_REMESH_THRESHOLD)
 
 
+# ------------------------------------------------------------------------------------ PlotData
+class PlotData:
+    """reference PlotData (src/util/inc/plot_data.h:43-66): one row of beam moments per monitor element, filled by
+    Update2DPlotData (src/simulation/src/simulation_engine.cu:34-82) in the online mode.  The reference's Python module
+    does not export it (only the C++ `InitEngine(beam, bl, spch, graph_on, plot_data)` takes one); here
+    `Simulator.set_plot_data(PlotData(n))` is that call."""
+
+    def __init__(self, size: int):
+        self._c = _ctx()
+        self.size = int(size)
+        self.h = self._c.lib.hps_monitor_create(self._c.h, self.size)
+        if not self.h:
+            raise K.HpsError(K.ERR_CUDA, (self._c.lib.hps_last_error(self._c.h) or b"").decode())
+
+    def __del__(self):
+        try:
+            self._c.lib.hps_monitor_destroy(self.h)
+        except Exception:
+            pass
+
+    def values(self):
+        """{member: numpy array of the rows written so far} (PlotDataMember::GetValue), plus "count"."""
+        buf = np.zeros((len(K.MON_FIELDS), self.size))
+        n = C.c_uint32()
+        self._c.check(self._c.lib.hps_monitor_download(self.h, K.ptr(buf), C.byref(n)))
+        k = min(int(n.value), self.size)
+        out = {f: buf[i, :k].copy() for i, f in enumerate(K.MON_FIELDS)}
+        out["count"] = int(n.value)
+        return out
+
+
 # ----------------------------------------------------------------------------------- Simulator
 class Simulator:
     """reference SimulationEngine (src/simulation/src/simulation_engine.cpp:34-95) + wrap_simulator.cpp"""
@@ -518,6 +549,11 @@ class Simulator:
 
     def reset(self):
         self._c.check(self._c.lib.hps_engine_reset(self._c.h, self.beam.h))
+
+    def set_plot_data(self, plot_data: "PlotData | None"):
+        """InitEngine's (graph_on, plot_data) pair: monitor elements append their rows to `plot_data` from now on."""
+        self.plot_data = plot_data
+        self._c.check(self._c.lib.hps_ctx_set_monitor(self._c.h, plot_data.h if plot_data is not None else None))
 
     def set_space_charge(self, on_off: str):
         self.space_charge_on = on_off.lower() == "on"

@@ -15,7 +15,7 @@ import numpy as np
 from .lattice import ELEM_DTYPE, NPARAM, NAME_LEN
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libhpsim_b200.so")
+LIB_PATH = os.environ.get("HPSIM_B200_LIB") or os.path.join(HERE, "csrc", "libhpsim_b200.so")  # (the override is for build experiments)
 
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_LATTICE, ERR_NOTFOUND, ERR_COMM = range(7)
 
@@ -38,6 +38,8 @@ UPD_NAMES = [
 UPD = {n: i for i, n in enumerate(UPD_NAMES)}
 
 PROF_CLASSES = ["segment", "lloss", "moments", "deposit", "field"]
+MON_FIELDS = ["xavg", "xsig", "xpavg", "xpsig", "xemit", "yavg", "ysig", "ypavg", "ypsig", "yemit", "phiavg", "phisig", "wavg", "wsig",
+              "zemit", "loss_ratio", "loss_local"]  # members of the reference's PlotData, hps_monitor_field order
 SC_INTERVAL, SC_ADJ_BUNCH, SC_ADJ_BUNCH_CUTOFF_W, SC_MESH_CUTOFF_W, SC_REMESH_THRESHOLD, SC_FRACTION, SC_NR, SC_NZ = range(8)
 
 
@@ -109,6 +111,10 @@ PROTOTYPES = {
     "hps_beam_update": (C.c_int, [_vp, C.c_int]),
     "hps_beam_get": (C.c_int, [_vp, C.c_int, _dp]),
     "hps_beam_moment_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), _dp, _dp]),
+    "hps_monitor_create": (_vp, [_vp, C.c_uint32]),
+    "hps_monitor_destroy": (None, [_vp]),
+    "hps_ctx_set_monitor": (C.c_int, [_vp, _vp]),
+    "hps_monitor_download": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
     "hps_lattice_create": (_vp, [_vp, _vp, C.c_uint32]),
     "hps_lattice_destroy": (None, [_vp]),
     "hps_lattice_size": (C.c_uint32, [_vp]),

@@ -79,6 +79,7 @@ struct DevStats {
   double pivot_m;            // margin in force [rad]; adapted from the prediction errors seen
   double pivot_err_max;      // largest |<phi>_good - pivot| of the fused kicks so far (diagnostics)
   unsigned long long n_fused, n_fallback, n_deferred;  // kicks finished in the epilogue / by k_moments; deferred particles
+  double mon_ref_w;          // k_monitor: energy of the reference particle, handed from its owner to the other blocks / ranks
 };
 
 // side list of the fused-moment epilogue: particles whose classification needs the true <phi>_good
@@ -166,7 +167,9 @@ struct XrView {
   u32* err;                      // set non-zero when a peer did not answer in time
 };
 
-#define HPS_BLOCK 256
+#ifndef HPS_BLOCK
+#define HPS_BLOCK 256      // threads per block of the sweeps (a build-time experiment knob: -DHPS_BLOCK=320)
+#endif
 #define HPS_NSLOT 16          // partial-sum slots per block
 #define HPS_FIELD_RS 4         // source rings per block of the field solve
 #define HPS_MAX_SEG_OPS 24    // ops staged in shared memory per segment

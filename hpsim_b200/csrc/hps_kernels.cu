@@ -393,7 +393,7 @@ __device__ void finalize_moments(const double* t, double ref, u32 n_global, DevS
 __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
                                     const KickParams& kp, DeferList* dl, const XrView& xr, int fin_mode) {
   constexpr int NI = 20;
-  __shared__ long long s_warp[8 * NI];
+  __shared__ long long s_warp[(HPS_BLOCK / 32) * NI];
   __shared__ long long s_i[NI];
   __shared__ double s_g[HPS_XR_NS];   // round 1: totals over all ranks
   __shared__ double s_x[HPS_XR_NS];   // rounds 2 and 3
@@ -1044,10 +1044,47 @@ __device__ __forceinline__ void moments_phase(const BeamView& b, DevStats* st, S
   }
 }
 
+// Fallback of the fused-moment epilogue of K1 (DevStats::moments_fallback): code 1 -> the whole chain again (good count
+// and <phi>_good, longitudinal-loss pass, moments); code 2 -> losses are marked, moments only.  The flag is written by
+// K1's finaliser only, so every block reads the same value for the whole launch.  Every thread of the grid calls it;
+// s_scratch: blockDim.x doubles.
+__device__ __forceinline__ void moments_fallback_phase(u32 code, const BeamView& b, DevStats* st, ScDev* sc, double* bins, const KickParams& kp,
+                                                       double* partials, u32* ticket, double* s_total, double* s_scratch, const XrView& xr) {
+  int with_lloss = 0;
+  if (code == 1u) {
+    // first link again: Beam::UpdateLongitudinalLoss steps 1-2 (what K1's FIN_KICK epilogue computes)
+    double acc[LL_NS] = {0.0, 0.0, -DBL_MAX, 0.0};  // n_good, sum phi good, MAX phi over lloss == 0, n_lloss
+    const u32 npairs = (b.n + 1) >> 1;
+    for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
+      const double2 PH = ld_f64x2(b.phi, i2);
+      const uint2 L = ld_u32x2(b.loss, i2);
+      const uint2 LL = ld_u32x2(b.lloss, i2);
+      const double ph[2] = {PH.x, PH.y};
+      const u32 l[2] = {L.x, L.y}, ll[2] = {LL.x, LL.y};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j == 1 && !(2 * i2 + 1 < b.n)) continue;
+        if (l[j] == 0 && ll[j] == 0) { acc[0] += 1.0; acc[1] += ph[j]; }
+        if (ll[j] == 0) acc[2] = fmax(acc[2], ph[j]); else acc[3] += 1.0;
+      }
+    }
+    if (grid_reduce<LL_NS>(acc, 1u << 2, partials, ticket, s_total, s_scratch, xr)) {
+      if (threadIdx.x == 0) {
+        const double t8[8] = {s_total[0], s_total[1], s_total[2], 0.0, 0.0, 0.0, s_total[3], 0.0};
+        finalize_segment(FIN_KICK, t8, st, b.n_global);
+        __threadfence();
+      }
+    }
+    grid_barrier(ticket + 2);
+    with_lloss = 1;
+  }
+  moments_phase(b, st, sc, bins, kp, 1, with_lloss, partials, ticket, s_total, s_scratch, xr);
+}
+
 // mode 0: the stand-alone link of the chain (Beam::Update* API path, XR_NCCL, HPSIM_FUSED_MOMENTS=0).
-// mode 1: fallback of the fused-moment epilogue of K1 (DevStats::moments_fallback): 0 -> nothing to do; 1 -> the whole
-//   chain again (good count and <phi>_good, longitudinal-loss pass, moments); 2 -> losses are marked, moments only.
-//   The flag is written by K1's finaliser only, so every block reads the same value for the whole launch.
+// mode 1: only when the fused-moment epilogue of the sweep before asked for it (DevStats::moments_fallback).
+// (Folding the fallback into k_deposit instead -- one launch less per kick -- was measured: the extra code path costs the
+//  deposit loop registers at its 64-register budget, 586 -> 751 ms per C4 pass, more than the empty launch.)
 __global__ void __launch_bounds__(HPS_BLOCK)
 k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int do_policy, int with_lloss, int mode, double* partials,
           u32* ticket, const __grid_constant__ XrView xr) {
@@ -1057,35 +1094,8 @@ k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int 
   pdl_wait();
   if (mode == 1) {
     const u32 code = *(volatile u32*)&st->moments_fallback;
-    if (code == 0u) return;
-    with_lloss = 0;
-    if (code == 1u) {
-      // first link again: Beam::UpdateLongitudinalLoss steps 1-2 (what K1's FIN_KICK epilogue computes)
-      double acc[LL_NS] = {0.0, 0.0, -DBL_MAX, 0.0};  // n_good, sum phi good, MAX phi over lloss == 0, n_lloss
-      const u32 npairs = (b.n + 1) >> 1;
-      for (u32 i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < npairs; i2 += gridDim.x * blockDim.x) {
-        const double2 PH = ld_f64x2(b.phi, i2);
-        const uint2 L = ld_u32x2(b.loss, i2);
-        const uint2 LL = ld_u32x2(b.lloss, i2);
-        const double ph[2] = {PH.x, PH.y};
-        const u32 l[2] = {L.x, L.y}, ll[2] = {LL.x, LL.y};
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (j == 1 && !(2 * i2 + 1 < b.n)) continue;
-          if (l[j] == 0 && ll[j] == 0) { acc[0] += 1.0; acc[1] += ph[j]; }
-          if (ll[j] == 0) acc[2] = fmax(acc[2], ph[j]); else acc[3] += 1.0;
-        }
-      }
-      if (grid_reduce<LL_NS>(acc, 1u << 2, partials, ticket, s_total, s_scratch, xr)) {
-        if (threadIdx.x == 0) {
-          const double t8[8] = {s_total[0], s_total[1], s_total[2], 0.0, 0.0, 0.0, s_total[3], 0.0};
-          finalize_segment(FIN_KICK, t8, st, b.n_global);
-          __threadfence();
-        }
-      }
-      grid_barrier(ticket + 2);
-      with_lloss = 1;
-    }
+    if (code != 0u) moments_fallback_phase(code, b, st, sc, bins, kp, partials, ticket, s_total, s_scratch, xr);
+    return;
   }
   moments_phase(b, st, sc, bins, kp, do_policy, with_lloss, partials, ticket, s_total, s_scratch, xr);
 }
@@ -1755,6 +1765,79 @@ k_stat(BeamView b, DevStats* st, StatReq rq, double* partials, u32* ticket, cons
 }
 
 // ================================================================================================
+// Update2DPlotData (simulation_engine.cu:34-82) in one sweep: Beam::UpdateLoss + Beam::UpdateEmittance (beam.cpp:981-990:
+// horizontal, vertical, relative phase about the reference particle, longitudinal) + one row of the monitor table
+// ================================================================================================
+// slots: 0 n_loss | x: 1 sum 2 sum^2 3 sum x' 4 sum x'^2 5 sum x x' | y: 6..10 | 11 sum phi_r 12 phi_r^2 13 sum w 14 w^2 15 phi_r w
+enum { MON_NS = 16 };
+__global__ void __launch_bounds__(HPS_BLOCK)
+k_monitor(BeamView b, DevStats* st, MonView mon, double* partials, u32* ticket, const __grid_constant__ XrView xr) {
+  __shared__ double s_total[MON_NS];
+  __shared__ double s_scratch[HPS_BLOCK];
+  __shared__ double s_ref[2];
+  // the reference particle (global particle 0): phase for UpdateRelativePhi (beam.cu:1122-1130), energy for the
+  // emittance normalisation (beam_kernel.cu:1345) and <W> - W_ref.  Sharded beam: its owner tells the others.
+  if (xr.nranks > 1) {
+    if (blockIdx.x == 0) {
+      if (threadIdx.x < 2) s_ref[threadIdx.x] = (b.offset == 0 && b.n > 0) ? (threadIdx.x == 0 ? b.phi[0] : b.w[0]) : 0.0;
+      __syncthreads();
+      if (xr.mode == XR_P2P) xr_exchange_p2p(s_ref, 2, 0u, xr);
+      if (threadIdx.x == 0) { st->phi_r_ref = s_ref[0]; st->mon_ref_w = s_ref[1]; __threadfence(); }
+    }
+    grid_barrier(ticket + 2);
+    if (threadIdx.x == 0) { s_ref[0] = ldv(&st->phi_r_ref); s_ref[1] = ldv(&st->mon_ref_w); }
+  } else if (threadIdx.x == 0) {
+    s_ref[0] = b.phi[0]; s_ref[1] = b.w[0];
+  }
+  __syncthreads();
+  const double phi0 = s_ref[0], w0 = s_ref[1];
+  double acc[MON_NS];
+#pragma unroll
+  for (int s = 0; s < MON_NS; ++s) acc[s] = 0.0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x) {
+    if (b.loss[i] != 0) { acc[0] += 1.0; continue; }
+    const double x = b.x[i], xp = b.xp[i], y = b.y[i], yp = b.yp[i], w = b.w[i];
+    const double pr = rel_phi(b.phi[i], phi0);
+    acc[1] += x; acc[2] += x * x; acc[3] += xp; acc[4] += xp * xp; acc[5] += x * xp;
+    acc[6] += y; acc[7] += y * y; acc[8] += yp; acc[9] += yp * yp; acc[10] += y * yp;
+    acc[11] += pr; acc[12] += pr * pr; acc[13] += w; acc[14] += w * w; acc[15] += pr * w;
+  }
+  if (!grid_reduce<MON_NS>(acc, 0u, partials, ticket, s_total, s_scratch, xr)) return;
+  if (threadIdx.x != 0) return;
+  const double* t = s_total;
+  st->num_loss = (u32)t[0];
+  st->phi_r_ref = phi0;
+  StatReq rq;
+  rq.kind = KS_EMIT_T; rq.w_ref = w0; rq.good_only = 0; rq.var_a = 0; rq.var_b = 1;
+  rq.out[0] = HPS_STAT_X_AVG; rq.out[1] = HPS_STAT_X_SIG; rq.out[2] = HPS_STAT_XP_AVG; rq.out[3] = HPS_STAT_XP_SIG; rq.out[4] = HPS_STAT_X_EMIT;
+  finalize_stat(t, b, st, rq);
+  rq.out[0] = HPS_STAT_Y_AVG; rq.out[1] = HPS_STAT_Y_SIG; rq.out[2] = HPS_STAT_YP_AVG; rq.out[3] = HPS_STAT_YP_SIG; rq.out[4] = HPS_STAT_Y_EMIT;
+  finalize_stat(t + 5, b, st, rq);
+  rq.kind = KS_EMIT_Z;
+  finalize_stat(t + 10, b, st, rq);
+  // the row (simulation_engine.cu:36-81)
+  const u32 row = mon.counters[0], loss_num = mon.counters[1];
+  const u32 nl = st->num_loss;
+  const double loss_local = (double)(u32)(nl - loss_num);  // `GetLossNum() - loss_num`: unsigned arithmetic
+  const u32 loss_new = (u32)((double)loss_num + loss_local);
+  mon.counters[1] = loss_new;
+  mon.counters[0] = row + 1u;
+  if (row < mon.cap) {
+    auto put = [&](int f, double v) { mon.data[(size_t)f * mon.cap + row] = v; };
+    put(HPS_MON_LOSS_LOCAL, log10(loss_local / (double)b.n_global + 1e-6));
+    put(HPS_MON_LOSS_RATIO, (double)loss_new / (double)b.n_global);
+    put(HPS_MON_XAVG, st->v[HPS_STAT_X_AVG]); put(HPS_MON_XSIG, st->v[HPS_STAT_X_SIG]);
+    put(HPS_MON_XPAVG, st->v[HPS_STAT_XP_AVG]); put(HPS_MON_XPSIG, st->v[HPS_STAT_XP_SIG]);
+    put(HPS_MON_YAVG, st->v[HPS_STAT_Y_AVG]); put(HPS_MON_YSIG, st->v[HPS_STAT_Y_SIG]);
+    put(HPS_MON_YPAVG, st->v[HPS_STAT_YP_AVG]); put(HPS_MON_YPSIG, st->v[HPS_STAT_YP_SIG]);
+    put(HPS_MON_PHIAVG, st->v[HPS_STAT_PHI_AVG_R]); put(HPS_MON_PHISIG, st->v[HPS_STAT_PHI_SIG_R]);
+    put(HPS_MON_WSIG, st->v[HPS_STAT_W_SIG]);
+    put(HPS_MON_XEMIT, st->v[HPS_STAT_X_EMIT]); put(HPS_MON_YEMIT, st->v[HPS_STAT_Y_EMIT]); put(HPS_MON_ZEMIT, st->v[HPS_STAT_Z_EMIT]);
+    put(HPS_MON_WAVG, st->v[HPS_STAT_W_AVG] - w0);
+  }
+}
+
+// ================================================================================================
 // XR_NCCL only: fold the all-gathered rank partials in rank order and run the finaliser that the
 // XR_P2P / single-GPU path runs inside the reducing kernel's last block
 // ================================================================================================
@@ -1965,6 +2048,9 @@ cudaError_t launch_scheff(const LaunchCfg& c, unsigned grid, const BeamView& b, 
 }
 void launch_stat(const LaunchCfg& c, const BeamView& b, DevStats* st, const StatReq& rq) {
   k_stat<<<c.grid_single, HPS_BLOCK, 0, c.stream>>>(b, st, rq, c.partials, c.ticket, c.xr);
+}
+void launch_monitor(const LaunchCfg& c, const BeamView& b, DevStats* st, const MonView& mon) {
+  k_monitor<<<c.grid_single, HPS_BLOCK, 0, c.stream>>>(b, st, mon, c.partials, c.ticket, c.xr);
 }
 void launch_xr_finalize(const LaunchCfg& c, const FinReq& f, const BeamView& b, DevStats* st, ScDev* sc, double* bins) {
   k_xr_finalize<<<1, HPS_BLOCK, 0, c.stream>>>(c.xr, f, b, st, sc, bins);

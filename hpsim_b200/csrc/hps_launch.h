@@ -68,6 +68,13 @@ size_t scheff_smem(const KickParams&);
 cudaError_t launch_scheff(const LaunchCfg&, unsigned grid, const BeamView&, DevStats*, ScDev*, double* bins, double2* field,
                           double2* part, u32* tickets, const KickParams&, u32 mesh_seq);
 void launch_stat(const LaunchCfg&, const BeamView&, DevStats*, const StatReq&);
+// Update2DPlotData on the device: loss count + the three emittance passes in one sweep, one row of the monitor table
+struct MonView {
+  double* data;    // [HPS_MON_NFIELD][cap]
+  u32* counters;   // [0] monitor_num, [1] loss_num (simulation_engine.cu:32-33)
+  u32 cap;
+};
+void launch_monitor(const LaunchCfg&, const BeamView&, DevStats*, const MonView&);
 void launch_set_phi_ref(const LaunchCfg&, const BeamView&, DevStats*, int use_good, double phi0);
 void launch_copy_stat(const LaunchCfg&, DevStats*, int dst, int src);
 void launch_shift(const LaunchCfg&, double* a, double v, u32 n, u32 offset);

@@ -50,6 +50,16 @@ struct Builder {
     plan.ops.push_back(op);
     return plan.ops.back();
   }
+  // Update2DPlotData(): everything before it must have been applied, and the kick statistics that follow must see the
+  // loss count and centroid it refreshes -- so the sweep in front of it ends without a reduction of its own
+  void monitor() {
+    close(FIN_NONE, false);
+    Segment m;
+    m.op_begin = (u32)plan.ops.size();
+    m.monitor = true;
+    plan.segs.push_back(m);
+    begin();
+  }
   // Scheff::Start(beam, length) in the middle of an element: the sweep so far ends with the first
   // reduction of the moment chain, the next sweep starts with the kick itself.
   void kick(double length, u32 elem) {
@@ -77,6 +87,7 @@ Plan build_plan(const std::vector<hps_elem>& lat, u32 first, u32 last, EngineSta
 
   // simulation_engine.cpp:81-83 + Reset() (simulation_engine.cu:101-111)
   if (first < eng.prev_end) {
+    b.plan.engine_reset = true;
     eng.ccl_cell_num = 0;
     eng.design_w = beam.design_w;
     eng.wavelen = CLIGHT / beam.freq;
@@ -105,6 +116,7 @@ Plan build_plan(const std::vector<hps_elem>& lat, u32 first, u32 last, EngineSta
       }
       case HPS_ELEM_QUAD: {  // SimulateQuad :147-161
         for (int half = 0; half < 2; ++half) {
+          if (half == 1 && eng.monitor_on && (e.flags & HPS_FLAG_MONITOR)) b.monitor();  // :153-154
           if (half == 1 && sc.on) b.kick(p[0], id);
           Op& op = b.emit(OP_QUAD_HALF, id);
           op.p[0] = p[0]; op.p[1] = p[1]; op.p[2] = p[2]; op.p[3] = eng.wavelen;
@@ -204,7 +216,9 @@ Plan build_plan(const std::vector<hps_elem>& lat, u32 first, u32 last, EngineSta
           op.p[0] = p[0]; op.p[1] = p[1]; op.p[2] = p[2]; op.p[3] = p[3];
         }
         break;
-      case HPS_ELEM_DIAGNOSTICS: break;  // :331-335, offline mode
+      case HPS_ELEM_DIAGNOSTICS:  // :331-335
+        if (eng.monitor_on && (e.flags & HPS_FLAG_MONITOR)) b.monitor();
+        break;
       case HPS_ELEM_STEERER:  // :337-344 (H10: sign-sensitive test)
         if (p[0] > 1e-10 || p[1] > 1e-10) {
           Op& op = b.emit(OP_STEERER, id);

@@ -19,6 +19,7 @@ struct EngineState {  // the file statics of simulation_engine.cu:19-33 that out
   double design_w = 0.0;
   double wavelen = 0.0;   // d_wavelen (simulation_kernel.cu:13)
   u32 ccl_cell_num = 0;
+  bool monitor_on = false;  // param->graphics_on: monitor elements call Update2DPlotData
 };
 
 struct BeamHost {  // host-side members of Beam that the engine reads / writes
@@ -36,6 +37,7 @@ struct Segment {
   u32 op_begin = 0, op_count = 0;
   int fin_mode = FIN_NONE;   // FinMode | FIN_FREQ
   bool kick_follows = false; // the stat / deposit / field kernels of one kick run after this sweep
+  bool monitor = false;      // no sweep: Update2DPlotData (simulation_engine.cu:34-82) at this point of the program
   KickParams kp;             // valid when kick_follows, and for a leading OP_SC_KICK
 };
 
@@ -43,6 +45,7 @@ struct Plan {
   std::vector<Op> ops;
   std::vector<Segment> segs;
   u32 n_kicks = 0;
+  bool engine_reset = false;  // this call restarted upstream of the previous end: Reset() (monitor_num = loss_num = 0)
   std::string error;  // non-empty => lattice not simulable (the reference would exit(-1) / crash)
 };
 

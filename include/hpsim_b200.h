@@ -278,6 +278,28 @@ int hps_scheff_download_tables(hps_scheff*, double* bins, double* field, double*
  * slice, 4 grid barrier (+ mesh push of a sharded beam), 5 field solve; 6-7 unused. */
 int hps_scheff_phase_cycles(hps_scheff*, uint64_t out[8]);
 
+/* ---- online monitor outputs ------------------------------------------------
+ * Replaces PlotData (reference src/util/inc/plot_data.h:43-66) and Update2DPlotData (src/simulation/src/
+ * simulation_engine.cu:34-82), i.e. SimulationEngine::InitEngine(beam, bl, spch, graph_on = true, plot_data): with a
+ * monitor attached, every quadrupole (between its halves, ahead of the kick; simulation_engine.cu:153-154) and every
+ * diagnostics element (:331-335) whose HPS_FLAG_MONITOR is set refreshes the loss count and the emittances
+ * (Beam::UpdateLoss, Beam::UpdateEmittance -- with their side effects on the stale counters the kick chain reads) and
+ * appends one row of 17 values.  Rows restart at 0 whenever the engine is reset (monitor_num, simulation_engine.cu:105).
+ * Everything happens on the device inside hps_simulate; hps_monitor_download is the only synchronising call. */
+typedef struct hps_monitor hps_monitor;
+enum hps_monitor_field {           /* members of PlotData, in this order */
+  HPS_MON_XAVG = 0, HPS_MON_XSIG, HPS_MON_XPAVG, HPS_MON_XPSIG, HPS_MON_XEMIT,
+  HPS_MON_YAVG, HPS_MON_YSIG, HPS_MON_YPAVG, HPS_MON_YPSIG, HPS_MON_YEMIT,
+  HPS_MON_PHIAVG, HPS_MON_PHISIG, HPS_MON_WAVG /* <W> - W_ref */, HPS_MON_WSIG, HPS_MON_ZEMIT,
+  HPS_MON_LOSS_RATIO, HPS_MON_LOSS_LOCAL /* log10(local loss fraction + 1e-6) */,
+  HPS_MON_NFIELD
+};
+hps_monitor* hps_monitor_create(hps_ctx*, uint32_t capacity);      /* PlotData(int)                          */
+void hps_monitor_destroy(hps_monitor*);
+int hps_ctx_set_monitor(hps_ctx*, hps_monitor*);                    /* NULL: graphics_on = false              */
+/* out: [HPS_MON_NFIELD][capacity] doubles (PlotDataMember::GetValue of every member); *count: rows written */
+int hps_monitor_download(hps_monitor*, double* out, uint32_t* count);
+
 /* Diagnostics of the fused moment chain (no reference counterpart): the reference's Beam::UpdateStatForSpaceCharge
  * (src/beam/src/beam.cpp:1003-1016) re-reads the particles for every link of its chain; here the sweep in front of a
  * kick sums the moments about a predicted <phi>_good and re-centres exactly.  out[0] kicks finished that way, out[1]

@@ -78,7 +78,15 @@ struct Saved {
 // beam has to exchange and where: every sum / count / max below goes through xr().
 typedef void (*hps_oracle_allreduce_fn)(double* buf, int count, int op /* 0 sum, 1 max */, void* user);
 
+struct hps_monitor {  // util/inc/plot_data.h:43-66 + monitor_num / loss_num (simulation_engine.cu:32-33)
+  hps_ctx* ctx;
+  uint cap = 0;
+  std::vector<double> data;  // [HPS_MON_NFIELD][cap]
+  uint monitor_num = 0, loss_num = 0;
+};
+
 struct hps_ctx {
+  hps_monitor* monitor = nullptr;  // param->graphics_on / plot_data
   std::string err;
   int compat = 1;
   int nthreads = 0;
@@ -1043,6 +1051,7 @@ void ScheffStart(hps_scheff* s, hps_beam* b, double length) {
 
 // ---------------------------------------------------------------------- engine
 void Reset(hps_ctx* c, hps_beam* b) {  // simulation_engine.cu:101-111
+  if (c->monitor) { c->monitor->monitor_num = 0; c->monitor->loss_num = 0; }
   c->ccl_cell_num = 0;
   c->design_w = b->design_w;
   c->wavelen = CLIGHT / b->freq;
@@ -1056,6 +1065,31 @@ void PrepGap(hps_ctx* c, hps_beam* b, const Gap& g) {
     c->wavelen = CLIGHT / g.frequency;
     ChangeFrequency(b, g.frequency);
   }
+}
+
+// simulation_engine.cu:34-82
+void Update2DPlotData(hps_ctx* c, hps_beam* b) {
+  hps_monitor* m = c->monitor;
+  UpdateLoss(b);
+  double loss_local = (double)(uint)(b->s.num_loss - m->loss_num);
+  m->loss_num = (uint)((double)m->loss_num + loss_local);
+  loss_local /= b->ng;
+  loss_local = std::log10(loss_local + 1e-6);
+  const double loss_ratio = (double)m->loss_num / b->ng;
+  UpdateEmittance(b);
+  const double w_avg = b->s.v[HPS_STAT_W_AVG] - from_ref_particle(b, b->w);
+  const uint row = m->monitor_num++;
+  if (row >= m->cap) return;  // (the reference writes past its arrays)
+  auto put = [&](int f, double v) { m->data[(size_t)f * m->cap + row] = v; };
+  put(HPS_MON_LOSS_LOCAL, loss_local); put(HPS_MON_LOSS_RATIO, loss_ratio);
+  put(HPS_MON_XAVG, b->s.v[HPS_STAT_X_AVG]); put(HPS_MON_XSIG, b->s.v[HPS_STAT_X_SIG]);
+  put(HPS_MON_XPAVG, b->s.v[HPS_STAT_XP_AVG]); put(HPS_MON_XPSIG, b->s.v[HPS_STAT_XP_SIG]);
+  put(HPS_MON_YAVG, b->s.v[HPS_STAT_Y_AVG]); put(HPS_MON_YSIG, b->s.v[HPS_STAT_Y_SIG]);
+  put(HPS_MON_YPAVG, b->s.v[HPS_STAT_YP_AVG]); put(HPS_MON_YPSIG, b->s.v[HPS_STAT_YP_SIG]);
+  put(HPS_MON_PHIAVG, b->s.v[HPS_STAT_PHI_AVG_R]); put(HPS_MON_PHISIG, b->s.v[HPS_STAT_PHI_SIG_R]);
+  put(HPS_MON_WSIG, b->s.v[HPS_STAT_W_SIG]);
+  put(HPS_MON_XEMIT, b->s.v[HPS_STAT_X_EMIT]); put(HPS_MON_YEMIT, b->s.v[HPS_STAT_Y_EMIT]); put(HPS_MON_ZEMIT, b->s.v[HPS_STAT_Z_EMIT]);
+  put(HPS_MON_WAVG, w_avg);
 }
 
 int VisitElement(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint id) {
@@ -1076,6 +1110,7 @@ int VisitElement(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     }
     case HPS_ELEM_QUAD:  // :147-161
       HalfQuad(b, c->wavelen, p[0], p[1], p[2], id);
+      if (c->monitor && (e.flags & HPS_FLAG_MONITOR)) Update2DPlotData(c, b);
       if (sc) ScheffStart(sc, b, p[0]);
       HalfQuad(b, c->wavelen, p[0], p[1], p[2], id);
       break;
@@ -1142,7 +1177,9 @@ int VisitElement(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
       UpdateLoss(b); UpdateAvgXY(b);
       RectangularAperture(b, p[0], p[1], p[2], p[3], id);
       break;
-    case HPS_ELEM_DIAGNOSTICS: break;  // :331-335 (offline: no-op)
+    case HPS_ELEM_DIAGNOSTICS:  // :331-335
+      if (c->monitor && (e.flags & HPS_FLAG_MONITOR)) Update2DPlotData(c, b);
+      break;
     case HPS_ELEM_STEERER:  // :337-344
       if (p[0] > 1e-10 || p[1] > 1e-10) SteererMap(b, p[0], p[1]);
       break;
@@ -1494,6 +1531,24 @@ int hps_scheff_get(hps_scheff* s, int p, double* v) {
 int hps_scheff_set_mesh_size(hps_scheff* s, uint32_t nr, uint32_t nz) {
   // wrap_spacecharge.cpp set_mesh_size -> Scheff::SetMeshSize (nx_init_/nz_init_ keep the constructor values)
   SetMeshSize(s, nr, nz);
+  return HPS_OK;
+}
+hps_monitor* hps_monitor_create(hps_ctx* c, uint32_t capacity) {
+  if (!c || capacity == 0) return nullptr;
+  hps_monitor* m = new hps_monitor();
+  m->ctx = c; m->cap = capacity;
+  m->data.assign((size_t)HPS_MON_NFIELD * capacity, 0.0);
+  return m;
+}
+void hps_monitor_destroy(hps_monitor* m) {
+  if (!m) return;
+  if (m->ctx->monitor == m) m->ctx->monitor = nullptr;
+  delete m;
+}
+int hps_ctx_set_monitor(hps_ctx* c, hps_monitor* m) { c->monitor = m; return HPS_OK; }
+int hps_monitor_download(hps_monitor* m, double* out, uint32_t* count) {
+  if (out) std::memcpy(out, m->data.data(), m->data.size() * sizeof(double));
+  if (count) *count = m->monitor_num;
   return HPS_OK;
 }
 int hps_beam_moment_stats(hps_beam*, uint64_t out[3], double* e, double* m) {  // the oracle runs the reference's chain as it is

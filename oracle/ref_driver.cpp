@@ -29,6 +29,7 @@
 #include "beamline_element.h"
 #include "space_charge.h"
 #include "simulation_engine.h"
+#include "plot_data.h"
 
 namespace {
 
@@ -200,7 +201,12 @@ int main(int argc, char** argv) {
     if (cfg.count("mesh_cutoff_w")) spch->SetMeshSizeCutoffW(D(cfg, "mesh_cutoff_w", 0.0));
   }
   SimulationEngine engine;
-  engine.InitEngine(&beam, &bl, spch);
+  // online mode (graph_on + PlotData): monitor elements call Update2DPlotData (simulation_engine.cu:34-82)
+  const int mon_cap = (int)D(cfg, "monitor", 0);
+  // (PlotData(int) leaves xpavg / xpsig / ypavg / ypsig unallocated, plot_data.cpp:7-14; Resize allocates all 17 members)
+  PlotData* plot = mon_cap > 0 ? new PlotData() : NULL;
+  if (plot) plot->Resize(mon_cap);
+  engine.InitEngine(&beam, &bl, spch, plot != NULL, plot);
 
   std::string first = S(cfg, "first", ""), last = S(cfg, "last", "");
   int repeats = (int)D(cfg, "repeats", 1);
@@ -238,6 +244,15 @@ int main(int argc, char** argv) {
       beam.GetAvgRelativePhi(), beam.GetSigRelativePhi(), beam.GetRefEnergy(), beam.GetRefPhase(),
       beam.freq, beam.current, beam.design_w};
   WriteBeamFile(S(cfg, "beam_out", "beam_out.bin"), beam, stats);
+  if (plot) {  // 17 x mon_cap doubles in the order of hps_monitor_field (include/hpsim_b200.h)
+    PlotDataMember<double>* mem[17] = {&plot->xavg, &plot->xsig, &plot->xpavg, &plot->xpsig, &plot->xemit, &plot->yavg, &plot->ysig,
+                                       &plot->ypavg, &plot->ypsig, &plot->yemit, &plot->phiavg, &plot->phisig, &plot->wavg, &plot->wsig,
+                                       &plot->zemit, &plot->loss_ratio, &plot->loss_local};
+    FILE* f = fopen(S(cfg, "monitor_out", "monitor.bin").c_str(), "wb");
+    if (!f) { std::cerr << "ref_driver: cannot write monitor_out" << std::endl; return 2; }
+    for (int k = 0; k < 17; ++k) { std::vector<double> v = mem[k]->GetValue(); fwrite(v.data(), 8, v.size(), f); }
+    fclose(f);
+  }
   // optional: the reference's own text dump (Beam::PrintToFile, beam.cpp:670-707)
   if (cfg.count("print_to")) beam.PrintToFile(S(cfg, "print_to", "beam.txt"), S(cfg, "print_msg", "ref_driver"));
   std::cout << "ref_driver: loss=" << stats[0] << " lloss=" << stats[1] << " good=" << stats[2] << std::endl;

@@ -218,7 +218,7 @@ REF_STATS = ["loss", "lloss", "good", "x_avg", "x_sig", "y_avg", "y_sig", "phi_a
 
 def run_reference(workdir, n, first, last, sc=True, double=True, nr=32, nz=128, interval=0.025, adj_bunch=3,
                   cutoff_w=0.8, remesh=0.02, seed=SEED, beam_in=None, design_w=None, freq=FREQ, repeats=1, timeout=900,
-                  mesh_cutoff_w=None):
+                  mesh_cutoff_w=None, extra=()):
     """Runs oracle/_ref/ref_driver{,_dp} (the reference's own CUDA code) and returns (state, log)."""
     exe = REF_DP if double else REF_SP
     os.makedirs(workdir, exist_ok=True)
@@ -237,6 +237,7 @@ def run_reference(workdir, n, first, last, sc=True, double=True, nr=32, nz=128, 
         cfg += [f"beam_in {beam_in}", f"freq {float(freq)!r}"]
         if design_w is not None:
             cfg.append(f"design_w {float(design_w)!r}")  # float(): repr(np.float64) is not a C number
+    cfg += list(extra)
     path = os.path.join(workdir, "ref.cfg")
     with open(path, "w") as f:
         f.write("\n".join(cfg) + "\n")
@@ -244,6 +245,12 @@ def run_reference(workdir, n, first, last, sc=True, double=True, nr=32, nz=128, 
     if p.returncode != 0:
         raise RuntimeError(f"ref_driver failed ({p.returncode}): {p.stdout[-2000:]} {p.stderr[-2000:]}")
     return read_beam_file(out), p.stdout
+
+
+def read_monitor_file(path, cap):
+    """17 x cap doubles written by ref_driver's `monitor_out` (order of hps_monitor_field)."""
+    a = np.fromfile(path, dtype=np.float64).reshape(len(K.MON_FIELDS), cap)
+    return {f: a[i].copy() for i, f in enumerate(K.MON_FIELDS)}
 
 
 def run_reference_cfg(workdir, n, beam_lines, first, last, sc=True, double=True, extra=(), timeout=900):

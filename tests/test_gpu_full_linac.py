@@ -123,8 +123,9 @@ def test_full_linac_space_charge_vs_live_reference(tmp_path):
     """BASELINE C1 / C4 range, SC on: loss and longitudinal-loss COUNTS and the beam moments against the reference's own
     two-run spread."""
     # moments: the reference's only noise source is the order of its deposit atomics; this code sums its moments in another
-    # order than the reference (1e-16 relative), and 7 900 CCL kicks amplify either seed to 1e-4 .. 1e-3 of an rms
-    rep = _sc_on_against_reference_spread(tmp_path, 32768, "48DT", mom_tol=5e-3)
+    # order than the reference (1e-16 relative), and 7 900 CCL kicks amplify either seed: 1e-4 .. 1e-2 of an rms seen on
+    # B200, depending on the summation scheme (for scale: the sampling error of an rms of 26 Ki particles is 4e-3)
+    rep = _sc_on_against_reference_spread(tmp_path, 32768, "48DT", mom_tol=2e-2)
     assert rep["kicks"] == 8894
 
 
@@ -352,3 +353,49 @@ def test_fused_moment_epilogue_matches_standalone_chain(last, n, tol):
     else:  # into the CCL with space charge: counts, and the typical particle
         assert abs(rep["n_loss"][0] - rep["n_loss"][1]) <= 3 and abs(rep["n_lloss"][0] - rep["n_lloss"][1]) <= 3, rep
         assert rep["median_rel"] < 1e-6, rep
+
+
+# --------------------------------------------------------------------------------------------- online monitors
+def _monitor_run(lib, n, last, sc, cap=64):
+    c = H.Case(lib, n=n, sc=sc)
+    HPSim._use_library(lib)
+    try:
+        pd = HPSim.PlotData(cap)
+    finally:
+        HPSim._use_library(None)
+    c.sim.set_plot_data(pd)
+    r = c.run("TBDB02", last)
+    c.beam.get_loss_num("l")
+    vals = pd.values()
+    st = c.state()
+    c.sim.set_plot_data(None)
+    return vals, st, r
+
+
+@pytest.mark.parametrize("sc", [False, True])
+def test_monitor_rows_vs_oracle_and_reference(tmp_path, sc):
+    """PlotData / Update2DPlotData (simulation_engine.cu:34-82): the 17 values per monitor quadrupole of DTL tank 1, and the
+    beam itself (the monitor's UpdateLoss / UpdateEmittance refresh counters the kick chain reads, H4 / H5)."""
+    n, last = 32768, "01QM30"
+    vg, sg, rg = _monitor_run(H.cuda_lib(), n, last, sc)
+    vo, so, ro = _monitor_run(H.oracle_lib(), n, last, sc)
+    nmon = sum(1 for i in range(62, H.lattice()["name"].tolist().index(last.encode()) + 1) if int(H.lattice()["flags"][i]) & 2)
+    assert vg["count"] == vo["count"] == nmon == 31, (vg["count"], vo["count"], nmon)
+    rep = H.compare(sg, so, 1e-9)
+    assert rep["loss_equal"] and rep["lloss_equal"], rep
+    tol = 1e-9 if not sc else 1e-6
+    for f in K.MON_FIELDS:
+        a, b = vg[f], vo[f]
+        scale = np.maximum(np.abs(b), np.abs(b).max() * 1e-3 + 1e-300)
+        assert np.all(np.abs(a - b) <= tol * scale), (f, a, b)
+    assert np.all(np.diff(vg["loss_ratio"]) >= 0) and vg["loss_ratio"][-1] > 0.05
+    if HAVE_REF:
+        mon_out = os.path.join(str(tmp_path), "mon.bin")
+        ref, _ = H.run_reference(str(tmp_path), n, "TBDB02", last, sc=sc, double=True, extra=["monitor 64", f"monitor_out {mon_out}"])
+        vr = H.read_monitor_file(mon_out, 64)
+        rep = H.compare(sg, ref, 1e-9)
+        assert rep["loss_equal"] and rep["lloss_equal"], rep
+        for f in K.MON_FIELDS:
+            a, b = vg[f], vr[f][:nmon]
+            scale = np.maximum(np.abs(b), np.abs(b).max() * 1e-3 + 1e-300)
+            assert np.all(np.abs(a - b) <= tol * scale), (f, a, b)

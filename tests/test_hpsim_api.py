@@ -173,3 +173,25 @@ def test_set_db_epics_and_set_db_model_reach_the_lattice():
             HPSim.set_db_model("TDDB01", "phase_offset_cal", f0, conn, bl)
     finally:
         HPSim._use_library(None)
+
+
+def test_monitor_rows_on_the_oracle():
+    """PlotData / Update2DPlotData through the mirror (HPSim.PlotData, Simulator.set_plot_data) on the CPU oracle: one row per
+    monitor quadrupole, restarted by an engine reset; the GPU counterpart is tests/test_gpu_full_linac.py."""
+    lib = H.oracle_lib()
+    c = H.Case(lib, n=2048, sc=True)
+    HPSim._use_library(lib)
+    try:
+        pd = HPSim.PlotData(16)
+    finally:
+        HPSim._use_library(None)
+    c.sim.set_plot_data(pd)
+    c.run("TBDB02", "01QM10")
+    v = pd.values()
+    assert v["count"] == 11 and len(v["xsig"]) == 11
+    assert np.all(v["xsig"] > 0) and np.all(v["zemit"] > 0) and np.all(np.diff(v["loss_ratio"]) >= 0)
+    assert np.all(v["loss_local"] >= -6.0)
+    c.beam.restore_initial_beam()
+    c.run("TBDB02", "01QM03")            # restart upstream: Reset() zeroes monitor_num
+    assert pd.values()["count"] == 4
+    c.sim.set_plot_data(None)
