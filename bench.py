@@ -366,29 +366,52 @@ def main():
             t = torch.tensor(chk_local, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             chk = t.numpy()
-    # ---- sharded result against a single-GPU run of the same beam (rank 0, its own context without a communicator)
+    # ---- sharded result against a single-GPU run of the same beam (rank 0, its own context without a communicator).
+    # (1) EXACT on a short range (LEBT + the first DTL cells, 258 kicks: every exchange of the kick chain is exercised
+    #     hundreds of times and the dynamics have not yet amplified the summation-order difference): loss counts equal,
+    #     sums of w / phi / x^2 over the survivors to 1e-9.  (2) REPORTED on the timed range: through the whole linac the
+    #     space-charge dynamics are chaotic (two code versions differ by 2 % in the longitudinal-loss count), so the
+    #     counts of the timed step are compared loosely only.
     check = None
-    if sharded and not args.no_check and rank == 0:
-        HPSim._ctx_cache.clear()
-        one = H.Case(lib, n=n_beam, sc=True, remesh=cfg["remesh"])
-        if cfg["pre"]:
-            one.run(*cfg["pre"])
-            one.beam.save_intermediate_beam()
-        # two passes: like the timed steps, the checked pass starts from a restored beam with the SCHEFF remesh memory
-        # and the stale loss count of the pass before it
-        for _ in range(2):
-            (one.beam.restore_intermediate_beam if cfg["pre"] else one.beam.restore_initial_beam)()
-            one.run(*cfg["rng"])
-        r1 = one.state()
-        c1 = [float((r1["loss"] != 0).sum()), float((r1["lloss"] != 0).sum()), float(r1["w"][r1["loss"] == 0].sum()), float(len(r1["w"]))]
-        check = {"n_loss": [int(chk[0]), int(c1[0])], "n_lloss": [int(chk[1]), int(c1[1])], "sum_w_alive": [chk[2], c1[2]],
-                 "order": "[sharded, single GPU]",
-                 "note": "with space charge on, the split changes the summation order of the moment reductions (1e-16) and the DTL "
-                         "amplifies it; counts are asserted to 1e-3 relative, the energy sum to 1e-6"}
-        n_alive = max(1.0, c1[3] - c1[0])
-        check["ok"] = bool(abs(chk[0] - c1[0]) <= max(2.0, 1e-3 * max(c1[0], 1.0)) and abs(chk[1] - c1[1]) <= max(2.0, 1e-3 * max(c1[1], 1.0))
-                           and abs(chk[2] - c1[2]) <= 1e-6 * abs(c1[2]) + 1e-3 * abs(c1[2]) / n_alive * abs(chk[0] - c1[0]))
-        del one, r1
+    if sharded and not args.no_check:
+        def sums(st):
+            a = st["loss"] == 0
+            return np.array([float((st["loss"] != 0).sum()), float((st["lloss"] != 0).sum()), float(st["w"][a].sum()),
+                             float(st["phi"][a].sum()), float((st["x"][a] ** 2).sum()), float(a.sum())])
+        short = ("TBDB02", "01QM10")
+        case.beam.restore_initial_beam()
+        case.run(*short)
+        ss = sums(case.state())
+        import torch
+        t = torch.tensor(ss, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ss = t.numpy()
+        if rank == 0:
+            HPSim._ctx_cache.clear()
+            one = H.Case(lib, n=n_beam, sc=True, remesh=cfg["remesh"])
+            one.run(*short)
+            s1 = sums(one.state())
+            exact_ok = bool(ss[0] == s1[0] and ss[1] == s1[1] and ss[5] == s1[5] and
+                            all(abs(ss[k] - s1[k]) <= 1e-9 * abs(s1[k]) for k in (2, 3, 4)))
+            # the timed range: two passes, like the timed steps the checked pass starts from a restored beam with the SCHEFF
+            # remesh memory and the stale loss count of the pass before it
+            if cfg["pre"]:
+                one.beam.restore_initial_beam()
+                one.run(*cfg["pre"])
+                one.beam.save_intermediate_beam()
+            for _ in range(2):
+                (one.beam.restore_intermediate_beam if cfg["pre"] else one.beam.restore_initial_beam)()
+                one.run(*cfg["rng"])
+            r1 = one.state()
+            c1 = [float((r1["loss"] != 0).sum()), float((r1["lloss"] != 0).sum()), float(r1["w"][r1["loss"] == 0].sum())]
+            loose_ok = bool(abs(chk[0] - c1[0]) <= 0.01 * n_beam and abs(chk[1] - c1[1]) <= 0.03 * n_beam and abs(chk[2] - c1[2]) <= 0.01 * abs(c1[2]))
+            check = {"short_range": {"range": list(short), "n_loss": [int(ss[0]), int(s1[0])], "n_lloss": [int(ss[1]), int(s1[1])],
+                                     "sum_w": [ss[2], s1[2]], "sum_phi": [ss[3], s1[3]], "sum_x2": [ss[4], s1[4]], "ok": exact_ok,
+                                     "gate": "counts equal, sums within 1e-9"},
+                     "timed_range": {"n_loss": [int(chk[0]), int(c1[0])], "n_lloss": [int(chk[1]), int(c1[1])], "sum_w_alive": [chk[2], c1[2]],
+                                     "ok": loose_ok, "gate": "chaotic range: counts within 1 % / 3 % of N, energy sum within 1 %"},
+                     "order": "[sharded, single GPU]", "ok": bool(exact_ok and loose_ok)}
+            del one, r1
     if dist is not None:
         dist.barrier()
     if rank != 0:
@@ -435,6 +458,13 @@ def main():
                      "by_kernel_us_per_launch": {k: 1e3 * v["ms"] / v["launches"] for k, v in prof.items() if v["launches"]},
                      "profiled_step_ms": run["device_ms"]},
     }
+    if sharded:
+        cs = (C.c_uint64 * 4)()
+        lib.hps_ctx_comm_stats(ctx.h, cs)
+        line["exchange"] = {"small_exchanges": int(cs[1]), "small_wait_us_avg": cs[0] / max(1, cs[1]) / 1e3,
+                            "mesh_exchanges": int(cs[3]), "mesh_wait_us_avg": cs[2] / max(1, cs[3]) / 1e3,
+                            "note": "rank 0, whole process: time from a reduction's own stores being issued to every peer's words "
+                                    "having arrived (NVLink latency + rank skew); mesh: block 0 of the field solve after its Green slice"}
     if check is not None:
         line["sharded_check"] = check
     if tf:

@@ -76,6 +76,7 @@ PROTOTYPES = {
     "hps_comm_unique_id": (C.c_int, [_vp]),
     "hps_ctx_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "hps_ctx_comm_mode": (C.c_int, [_vp]),
+    "hps_ctx_comm_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "hps_ctx_synchronize": (C.c_int, [_vp]),
     "hps_host_alloc": (_vp, [C.c_size_t]),
     "hps_host_free": (None, [_vp]),

@@ -54,6 +54,7 @@ struct hps_ctx {
   // cp.async staging of the next particle pair in the sweep: -1 = automatic (on when the rank's particle state does not
   // fit the L2 anyway), 0 / 1 = forced (HPSIM_STAGE)
   int stage = -1;
+  int patterns = 1;  // HPSIM_PATTERNS=0: always the generic sweep
   // program upload buffers
   Op* d_ops = nullptr;
   OpC* d_opc = nullptr;  // device-prepared constants, parallel to d_ops
@@ -70,6 +71,10 @@ struct hps_ctx {
   // the same program on the same objects (scans, benchmarks, optimisation loops re-run one range thousands of times).
   struct GraphEntry {
     uint64_t key = 0, stamp = 0, sweeps = 0, extra = 0, launches = 0;
+    std::vector<unsigned char> material;  // everything the captured launches depend on; compared in full on a hash hit
+    const void* beam = nullptr;           // the objects whose device pointers the graph captured: destroying or
+    const void* scheff = nullptr;         // re-allocating one of them drops the entry (drop_graphs_of)
+    const void* monitor = nullptr;
     cudaGraphExec_t exec = nullptr;
     Op* d_ops = nullptr;
     OpC* d_opc = nullptr;
@@ -100,6 +105,7 @@ struct hps_ctx {
 
 struct hps_beam {
   hps_ctx* ctx;
+  uint64_t gen = 0;  // unique per object (graph-cache key: a recycled address is not the same beam)
   BeamHost h;           // mass charge current freq design_w n_global
   u32 n = 0, offset = 0, gstride = 1, n_alloc = 0;
   char* slab = nullptr;  // one allocation: 6 fp64 arrays + 2 u32 arrays
@@ -126,6 +132,7 @@ struct hps_lattice {
 
 struct hps_scheff {
   hps_ctx* ctx;
+  uint64_t gen = 0;  // bumped by every (re-)allocation of the tables
   ScHost h;
   u32 nr_init, nz_init;
   double interval_init = 0.01, mesh_w = 0.0;
@@ -142,6 +149,21 @@ struct hps_scheff {
 };
 
 namespace {
+uint64_t g_next_gen = 1;
+
+// CUDA graphs that captured device pointers of `obj` (a beam, a SCHEFF or a monitor) must not outlive them
+void drop_graphs_of(hps_ctx* c, const void* obj) {
+  bool synced = false;
+  for (size_t i = 0; i < c->graphs.size();) {
+    auto& g = c->graphs[i];
+    if (g.beam == obj || g.scheff == obj || g.monitor == obj) {
+      if (!synced) { cudaStreamSynchronize(c->stream); synced = true; }
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      cudaFree(g.d_ops); cudaFree(g.d_opc);
+      c->graphs.erase(c->graphs.begin() + (long)i);
+    } else ++i;
+  }
+}
 
 int fail(hps_ctx* c, int code, const std::string& m) {
   if (c) c->err = m; else g_err = m;
@@ -183,6 +205,8 @@ LaunchCfg cfg(hps_ctx* c, const hps_beam* b) {
   l.xr = c->xr;
   l.pdl = c->pdl && !c->profile;  // the per-launch events of profile mode sit between the kernels anyway
   l.stage = c->stage >= 0 ? c->stage : (b->slab_bytes > ((size_t)96 << 20) ? 1 : 0);
+  l.patterns = c->patterns;
+  l.num_sms = c->num_sms;
   return l;
 }
 
@@ -395,6 +419,7 @@ hps_ctx* hps_ctx_create(int device) {
   if (const char* v = getenv("HPSIM_FUSED")) c->fused = atoi(v);
   if (const char* v = getenv("HPSIM_FUSED_MOMENTS")) c->fused_moments = atoi(v);
   if (const char* v = getenv("HPSIM_STAGE")) c->stage = atoi(v);
+  if (const char* v = getenv("HPSIM_PATTERNS")) c->patterns = atoi(v);
   if (const char* v = getenv("HPSIM_GRAPH")) c->use_graphs = atoi(v);
   if (const char* v = getenv("HPSIM_L2_PERSIST")) c->l2_persist = atoi(v);
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
@@ -500,8 +525,8 @@ int hps_ctx_comm_init(hps_ctx* c, int rank, int nranks, const void* id) {
   XrView& x = c->xr;
   std::memset(&x, 0, sizeof(x));
   x.rank = rank; x.nranks = nranks;
-  char* misc = nullptr;  // [seq 2 x u64][err u32 + pad][send NS][recv R*NS]
-  const size_t misc_bytes = 32 + (size_t)(1 + nranks) * HPS_XR_NS * sizeof(double);
+  char* misc = nullptr;  // [seq 2 x u64][err u32 + pad][send NS][recv R*NS][stats 4 x u64]
+  const size_t misc_bytes = 32 + (size_t)(1 + nranks) * HPS_XR_NS * sizeof(double) + 4 * sizeof(unsigned long long);
   CK(c, cudaMalloc(&c->xr_box, sizeof(XrBox)));
   CK(c, cudaMemset(c->xr_box, 0, sizeof(XrBox)));
   CK(c, cudaMalloc(&misc, misc_bytes));
@@ -511,6 +536,7 @@ int hps_ctx_comm_init(hps_ctx* c, int rank, int nranks, const void* id) {
   x.err = reinterpret_cast<u32*>(misc + 16);
   x.send = reinterpret_cast<double*>(misc + 32);
   x.recv = x.send + HPS_XR_NS;
+  x.stats = reinterpret_cast<unsigned long long*>(x.recv + (size_t)nranks * HPS_XR_NS);
   CK(c, cudaDeviceSynchronize());
   // map every peer's box (CUDA IPC; NVLink / NVSwitch peer access).  HPSIM_XR=nccl keeps to NCCL.
   const char* want = getenv("HPSIM_XR");
@@ -550,6 +576,16 @@ int hps_ctx_comm_init(hps_ctx* c, int rank, int nranks, const void* id) {
   return HPS_OK;
 }
 int hps_ctx_comm_mode(hps_ctx* c) { return c->xr.mode; }
+int hps_ctx_comm_stats(hps_ctx* c, uint64_t out[4]) {
+  for (int k = 0; k < 4; ++k) out[k] = 0;
+  if (c->xr.nranks <= 1 || !c->xr.stats) return HPS_OK;
+  cudaSetDevice(c->device);
+  unsigned long long h[4];
+  CK(c, cudaMemcpyAsync(h, c->xr.stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 4; ++k) out[k] = h[k];
+  return HPS_OK;
+}
 
 void* hps_host_alloc(size_t bytes) {
   void* p = nullptr;
@@ -564,6 +600,7 @@ hps_beam* hps_beam_create(hps_ctx* c, uint64_t n_global, double mass, double cha
   cudaSetDevice(c->device);
   hps_beam* b = new hps_beam();
   b->ctx = c;
+  b->gen = g_next_gen++;
   b->h.mass = mass; b->h.charge = charge; b->h.current = current; b->h.freq = 0.0; b->h.design_w = 0.0;
   b->h.n_global = (u32)n_global;
   // Interleaved ownership: rank r holds the global particles r, r + R, r + 2R, ...  The C1 beam recipe
@@ -593,6 +630,7 @@ void hps_beam_destroy(hps_beam* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
+  drop_graphs_of(b->ctx, b);
   if (b->ctx->l2_window_base == b->slab && b->slab) {  // the stream's L2 window must not outlive the slab
     cudaStreamAttrValue av;
     std::memset(&av, 0, sizeof(av));
@@ -853,6 +891,7 @@ void hps_monitor_destroy(hps_monitor* m) {
   if (!m) return;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  drop_graphs_of(m->ctx, m);
   if (m->ctx->monitor == m) m->ctx->monitor = nullptr;
   cudaFree(m->data); cudaFree(m->counters);
   delete m;
@@ -927,6 +966,8 @@ int hps_lattice_update_elem(hps_lattice* l, uint32_t i, const hps_elem* in) {
 // ---- SCHEFF -----------------------------------------------------------------------------------------
 static int scheff_alloc(hps_scheff* s) {
   hps_ctx* c = s->ctx;
+  drop_graphs_of(c, s);
+  s->gen = g_next_gen++;
   cudaFree(s->bins); cudaFree(s->field); cudaFree(s->field_part); cudaFree(s->field_tickets);
   s->bins = nullptr; s->field = nullptr; s->field_part = nullptr; s->field_tickets = nullptr;
   const size_t nb = (size_t)s->h.nr * s->h.nz, nf = (size_t)(s->h.nr + 1) * (s->h.nz + 1);
@@ -976,6 +1017,7 @@ void hps_scheff_destroy(hps_scheff* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
+  drop_graphs_of(s->ctx, s);
   cudaFree(s->dev); cudaFree(s->bins); cudaFree(s->field); cudaFree(s->field_part); cudaFree(s->field_tickets);
   delete s;
 }
@@ -1165,29 +1207,32 @@ static int run_range(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, 
 
   // ---- CUDA graph path: single GPU, no per-launch profiling, no drift-wise re-planning
   if (c->use_graphs && c->xr.nranks <= 1 && !c->profile && (!sc || sc->mesh_w == 0.0) && nops > 0) {
-    uint64_t key = 1469598103934665603ull;
-    key = fnv(key, plan.ops.data(), nops * sizeof(Op));
+    // key material: everything the captured launches depend on -- the op records, the segment descriptors, the kick
+    // parameters, the objects (generation ids, not just addresses) and the launch switches
+    std::vector<unsigned char> mat;
+    auto put = [&](const void* p, size_t n) { const unsigned char* q = static_cast<const unsigned char*>(p); mat.insert(mat.end(), q, q + n); };
+    put(plan.ops.data(), nops * sizeof(Op));
     for (const Segment& s : plan.segs) {
-      const uint64_t d[4] = {s.op_begin, s.op_count, (uint64_t)s.fin_mode, (uint64_t)s.kick_follows};
-      key = fnv(key, d, sizeof(d));
+      const uint64_t d[5] = {s.op_begin, s.op_count, (uint64_t)s.fin_mode, (uint64_t)s.kick_follows, (uint64_t)s.monitor};
+      put(d, sizeof(d));
       if (s.kick_follows || (s.op_count && plan.ops[s.op_begin].type == OP_SC_KICK)) {
         const double kd[6] = {s.kp.freq, s.kp.mass, s.kp.current_frac, s.kp.remesh_val, s.kp.adj_bunch_w, s.kp.mesh_w};
         const uint64_t ku[4] = {s.kp.adj_bunch_cfg, s.kp.nr, s.kp.nz, s.kp.n_global};
-        key = fnv(fnv(key, kd, sizeof(kd)), ku, sizeof(ku));
+        put(kd, sizeof(kd)); put(ku, sizeof(ku));
       }
     }
-    const uint64_t env[12] = {(uint64_t)(uintptr_t)b->slab, (uint64_t)(uintptr_t)b->st, b->n, b->offset, (uint64_t)(uintptr_t)(sc ? sc->dev : nullptr),
-                              (uint64_t)(uintptr_t)(sc ? sc->bins : nullptr), (uint64_t)(uintptr_t)(sc ? sc->field : nullptr),
-                              (uint64_t)c->seg_variant, (uint64_t)(c->fused | (c->fused_moments << 4) | ((c->stage & 3) << 8)), (uint64_t)c->compat, (uint64_t)c->pdl,
-                              (uint64_t)(uintptr_t)(sc ? sc->field_part : nullptr)};
-    key = fnv(key, env, sizeof(env));
+    const uint64_t env[16] = {b->gen, (uint64_t)(uintptr_t)b->slab, (uint64_t)(uintptr_t)b->st, b->n, b->offset, sc ? sc->gen : 0ull,
+                              (uint64_t)(uintptr_t)(sc ? sc->dev : nullptr), (uint64_t)(uintptr_t)(sc ? sc->bins : nullptr),
+                              (uint64_t)(uintptr_t)(sc ? sc->field : nullptr), (uint64_t)(uintptr_t)(sc ? sc->field_tickets : nullptr),
+                              (uint64_t)c->seg_variant, (uint64_t)(c->fused | (c->fused_moments << 4) | ((c->stage & 3) << 8) | (c->patterns << 12)),
+                              (uint64_t)c->compat, (uint64_t)c->pdl, (uint64_t)(uintptr_t)(c->monitor ? c->monitor->data : nullptr),
+                              (uint64_t)plan.engine_reset};
+    put(env, sizeof(env));
     const double bm[2] = {b->h.mass, b->h.charge};
-    key = fnv(key, bm, sizeof(bm));
-    const uint64_t mk[3] = {(uint64_t)(uintptr_t)(c->monitor ? c->monitor->data : nullptr), (uint64_t)plan.engine_reset, (uint64_t)(uintptr_t)b->defer};
-    key = fnv(key, mk, sizeof(mk));
-    for (const Segment& sg : plan.segs) if (sg.monitor) { const uint64_t one = 0x6d6f6eull; key = fnv(key, &one, sizeof(one)); }
+    put(bm, sizeof(bm));
+    const uint64_t key = fnv(1469598103934665603ull, mat.data(), mat.size());
     for (auto& g : c->graphs)
-      if (g.key == key && g.exec) {
+      if (g.key == key && g.exec && g.material == mat) {
         g.stamp = ++c->graph_stamp;
         CK(c, cudaGraphLaunch(g.exec, c->stream));
         c->launches += g.launches;
@@ -1206,6 +1251,8 @@ static int run_range(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, 
     }
     hps_ctx::GraphEntry g;
     g.key = key;
+    g.material = std::move(mat);
+    g.beam = b; g.scheff = sc; g.monitor = c->monitor;
     CK(c, cudaMalloc(&g.d_ops, nops * sizeof(Op)));
     CK(c, cudaMalloc(&g.d_opc, nops * sizeof(OpC)));
     CK(c, cudaMemcpy(g.d_ops, plan.ops.data(), nops * sizeof(Op), cudaMemcpyHostToDevice));

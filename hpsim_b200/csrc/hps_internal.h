@@ -165,6 +165,8 @@ struct XrView {
   double* recv;                  //          [nranks][HPS_XR_NS] gathered vectors
   double* bins_gather;           // XR_NCCL: [nranks][nb+2] gathered charge meshes
   u32* err;                      // set non-zero when a peer did not answer in time
+  unsigned long long* stats;     // [0] ns spent waiting in the small exchanges, [1] their count, [2] ns between a rank's own
+                                 // mesh being pushed and the last peer's mesh having arrived (block 0 of k_field), [3] count
 };
 
 #ifndef HPS_BLOCK

@@ -49,7 +49,9 @@ __device__ void finalize_segment(int fin, const double* t, DevStats* st, u32 n_g
 // back to back so that their independent fp64 chains can overlap.
 // MATH: 0 = the reference's expression order with nvcc's `/` and sqrt, 1 = the fast maps, 2 = the reference's
 // expression order with the branch-free exact arithmetic of hps_math.cuh (same bits as 0)
-template <bool FULL, int N, int MATH>
+// TYPE / CCL: the op type and the RF-gap flavour when the launch's op sequence is known at compile time (the pattern
+// sweeps below: the type switch and the DTL / CCL branches inside the gap maps fold away); -1 = read them from the record.
+template <bool FULL, int N, int MATH, int TYPE = -1, int CCL = -1>
 __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const u32 (&gidx)[N], const bool (&valid)[N],
                                          const Op& op, const OpC& opc, const KickCtx& kc, const double* cxy,
                                          const double2* __restrict__ field, const BeamView& b, int compat,
@@ -57,9 +59,10 @@ __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const 
   const double* q = op.p;
   const double* c = opc.c;
   const double mass = b.mass, charge = b.charge;
+  const bool ccl = CCL >= 0 ? (CCL != 0) : (op.flag != 0);
 #define EACH for (int j = 0; j < N; ++j) if (valid[j])
 #define EACH_ALIVE for (int j = 0; j < N; ++j) if (valid[j] && pt[j].loss == 0)
-  switch (op.type) {
+  switch (TYPE >= 0 ? TYPE : op.type) {
     case OP_DRIFT:
 #pragma unroll
       EACH_ALIVE { if (MATH == 1) op_drift_f(pt[j], q, c, op.elem, inv_mass); else if (MATH == 2) op_drift<MathNR>(pt[j], q, c, op.elem, mass, inv_mass); else op_drift<MathLib>(pt[j], q, c, op.elem, mass, inv_mass); }
@@ -70,11 +73,11 @@ __device__ __forceinline__ void apply_op(Pt (&pt)[N], const u32 (&ll)[N], const 
       break;
     case OP_GAP_FIRST:
 #pragma unroll
-      EACH_ALIVE { if (MATH == 1) op_gap_first_f(pt[j], q, c, op.flag != 0, inv_mass); else if (MATH == 2) op_gap_first<MathNR>(pt[j], q, c, op.flag != 0, mass, inv_mass); else op_gap_first<MathLib>(pt[j], q, c, op.flag != 0, mass, inv_mass); }
+      EACH_ALIVE { if (MATH == 1) op_gap_first_f(pt[j], q, c, ccl, inv_mass); else if (MATH == 2) op_gap_first<MathNR>(pt[j], q, c, ccl, mass, inv_mass); else op_gap_first<MathLib>(pt[j], q, c, ccl, mass, inv_mass); }
       break;
     case OP_GAP_SECOND:
 #pragma unroll
-      EACH_ALIVE { if (MATH == 1) op_gap_second_f(pt[j], q, c, op.flag != 0, inv_mass); else if (MATH == 2) op_gap_second<MathNR>(pt[j], q, c, op.flag != 0, mass, inv_mass); else op_gap_second<MathLib>(pt[j], q, c, op.flag != 0, mass, inv_mass); }
+      EACH_ALIVE { if (MATH == 1) op_gap_second_f(pt[j], q, c, ccl, inv_mass); else if (MATH == 2) op_gap_second<MathNR>(pt[j], q, c, ccl, mass, inv_mass); else op_gap_second<MathLib>(pt[j], q, c, ccl, mass, inv_mass); }
       break;
     // the rare, code-heavy maps (7 dipoles and 2 bunchers in the whole linac) live in the FULL variant only,
     // which keeps the hot variant's SASS inside the instruction cache
@@ -586,7 +589,29 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 // dependent fp64 operations, so the sweep is latency-bound before it is bandwidth-bound).
 // (A TMA-staged, double-buffered variant of the PPT == 2 loop was measured slower -- 35.0 vs 32.0 ms of sweep time
 // per C2 pass: the sweep is not load-bound and the per-tile block barrier re-aligns the warps -- and was removed.)
-template <int PPT, int MINB, bool FULL, int MATH>
+// SEQ: the launch's op sequence when it is one of the ten that make up 99.8 % of the sweeps of a full-linac run
+// (tests/host_maps.cu `plan` with HPS_PLAN_PATTERNS=1: 4 855 x [kick, CCL gap second half, next CCL gap first half],
+// 3 030 x [kick, drift, drift], ... of 9 108), packed 8 bits per op: type | (gap flavour + 1) << 5.  The sweep is then
+// compiled for exactly that sequence -- no loop, no type switch, the DTL / CCL branches of the gap maps folded, the
+// scheduler free to overlap the tail of one map with the head of the next.  0 = any sequence (loop + switch).
+// Measured on C4 (16 Mi particles): 754 -> 687 us per sweep with the first two patterns alone.
+#define SQ(type, flavour) ((type) | (((flavour) + 1) << 5))
+#define SEQ2(a, b) ((a) | ((b) << 8))
+#define SEQ3(a, b, c) ((a) | ((b) << 8) | ((c) << 16))
+enum {
+  SEQ_ANY = 0,
+  SEQ_CCL_CELL = SEQ3(SQ(OP_SC_KICK, -1), SQ(OP_GAP_SECOND, 1), SQ(OP_GAP_FIRST, 1)),
+  SEQ_DRIFT_STEP = SEQ3(SQ(OP_SC_KICK, -1), SQ(OP_DRIFT, -1), SQ(OP_DRIFT, -1)),
+  SEQ_DRIFT_QUAD = SEQ3(SQ(OP_SC_KICK, -1), SQ(OP_DRIFT, -1), SQ(OP_QUAD_HALF, -1)),
+  SEQ_QUAD_DRIFT = SEQ3(SQ(OP_SC_KICK, -1), SQ(OP_QUAD_HALF, -1), SQ(OP_DRIFT, -1)),
+  SEQ_QUAD_GAP1D = SEQ3(SQ(OP_SC_KICK, -1), SQ(OP_QUAD_HALF, -1), SQ(OP_GAP_FIRST, 0)),
+  SEQ_GAP2D_QUAD = SEQ3(SQ(OP_SC_KICK, -1), SQ(OP_GAP_SECOND, 0), SQ(OP_QUAD_HALF, -1)),
+  SEQ_APER_DRIFT = SEQ2(SQ(OP_CAPERTURE, -1), SQ(OP_DRIFT, -1)),
+  SEQ_KICK_DRIFT = SEQ2(SQ(OP_SC_KICK, -1), SQ(OP_DRIFT, -1)),
+  SEQ_KICK_GAP2C = SEQ2(SQ(OP_SC_KICK, -1), SQ(OP_GAP_SECOND, 1)),
+  SEQ_APER_GAP1C = SEQ2(SQ(OP_CAPERTURE, -1), SQ(OP_GAP_FIRST, 1)),
+};
+template <int PPT, int MINB, bool FULL, int MATH, int SEQ = SEQ_ANY>
 __global__ void __launch_bounds__(HPS_BLOCK, MINB)
 k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, int nops, int fin_mode, int dirty, int compat,
           DevStats* st, ScDev* sc, const double2* __restrict__ field, KickParams kp, double* partials,
@@ -694,7 +719,13 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       const u32 g[2] = {g0, g0 + b.gstride};
       double fc[2] = {0.0, 0.0};
       bool lf[2] = {false, false};
-      for (int k = 0; k < nops; ++k) apply_op<FULL, 2, MATH>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf, inv_mass);
+#define AP(TYPE, CCLF, K) apply_op<FULL, 2, MATH, TYPE, CCLF>(p, ll, g, valid, s_ops[K], s_opc[K], s_k, s_cxy, field, b, compat, fc, lf, inv_mass)
+      if (SEQ != SEQ_ANY) {
+        AP((SEQ & 31), ((SEQ >> 5) & 3) - 1, 0);
+        if ((SEQ >> 8) & 31) AP(((SEQ >> 8) & 31), ((SEQ >> 13) & 3) - 1, 1);
+        if ((SEQ >> 16) & 31) AP(((SEQ >> 16) & 31), ((SEQ >> 21) & 3) - 1, 2);
+      } else for (int k = 0; k < nops; ++k) AP(-1, -1, k);
+#undef AP
       if (nops > 0) {
         if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p[0].x, p[1].x);
         if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p[0].xp, p[1].xp);
@@ -781,6 +812,7 @@ static SegKernel seg_kernel(int variant) {
     case 10: return k_segment<2, 2, false, 0>;
     case 11: return k_segment<1, 3, false, 0>;
     case 20: return k_segment<2, 2, false, 2>;
+
     case 21: return k_segment<1, 3, false, 2>;
     case -1: return k_segment<1, 3, true, 1>;
     case -2: return k_segment<1, 3, true, 0>;
@@ -788,6 +820,29 @@ static SegKernel seg_kernel(int variant) {
     case 0: return k_segment<2, 2, false, 1>;
     default: return k_segment<2, 2, false, 2>;
   }
+}
+// the pattern sweeps of the default variant (2 particles / thread, reference-order maps, exact arithmetic)
+// (the drift sequences need few registers: 3 resident blocks per SM instead of 2 hide more of their memory latency)
+struct SeqKernel { int seq; int minb; SegKernel fn; };
+static const SeqKernel g_seq_kernels[] = {
+#define SK(S, B) {S, B, k_segment<2, B, false, 2, S>}
+    SK(SEQ_CCL_CELL, 2), SK(SEQ_DRIFT_STEP, 2), SK(SEQ_DRIFT_QUAD, 2), SK(SEQ_QUAD_DRIFT, 2), SK(SEQ_QUAD_GAP1D, 2), SK(SEQ_GAP2D_QUAD, 2),
+    SK(SEQ_APER_DRIFT, 2), SK(SEQ_KICK_DRIFT, 2), SK(SEQ_KICK_GAP2C, 2), SK(SEQ_APER_GAP1C, 2),
+    SK(SEQ_DRIFT_STEP, 3), SK(SEQ_APER_DRIFT, 3), SK(SEQ_KICK_DRIFT, 3),  // HPSIM_PATTERNS=2
+#undef SK
+};
+static const SeqKernel* seq_kernel(const Op* host_ops, int nops, int want_minb) {
+  if (nops < 2 || nops > 3 || !host_ops) return nullptr;
+  int code = 0;
+  for (int k = 0; k < nops; ++k) {
+    const int t = host_ops[k].type;
+    const bool gap = t == OP_GAP_FIRST || t == OP_GAP_SECOND;
+    code |= SQ(t, gap ? (host_ops[k].flag != 0 ? 1 : 0) : -1) << (8 * k);
+  }
+  const SeqKernel* hit = nullptr;
+  for (const SeqKernel& e : g_seq_kernels)
+    if (e.seq == code && (!hit || e.minb == want_minb)) hit = &e;
+  return hit;
 }
 static int seg_full_variant(int variant) { return variant >= 20 ? -3 : (variant >= 10 ? -2 : -1); }
 static bool seg_pairs(int variant) { return !(variant == 1 || variant == 2 || variant == 11 || variant == 21 || variant < 0); }
@@ -1449,11 +1504,14 @@ __device__ __forceinline__ void field_solve(DevStats* st, ScDev* sc, const doubl
     auto value = [&](int r, u32 k) -> unsigned long long {
       return ll ? ll_recv64(slot[r] + 2 * (size_t)k, seq32, xr.err) : slot[r][k];
     };
+    const bool stamp = ll && irp == 0 && ch == 0 && threadIdx.x == 0;
+    const unsigned long long t_wait = stamp ? global_ns() : 0ull;
     if (live) {
       unsigned long long a = 0ull;
       for (int r = 0; r < xr.nranks; ++r) a += value(r, t * nr + rs0 + kk);
       s_b[kk * nz + t] = (double)(long long)a * inv_scale;
     }
+    if (stamp) { xr.stats[2] += global_ns() - t_wait; xr.stats[3] += 1ull; }
     if (irp == 0 && ch == 0 && threadIdx.x == 0) {
       u32 cnt = 0;
       double pm = 0.0;
@@ -1901,7 +1959,6 @@ __global__ void k_rel_phi_out(BeamView b, const DevStats* st, double* out) {
 // ================================================================================================
 // launch wrappers
 // ================================================================================================
-static int g_field_smem_set = 0, g_deposit_smem_set = 0, g_scheff_smem_set = 0;
 
 // Launch with programmatic stream serialization (see pdl_wait in hps_kernels.cuh) when c.pdl is set.
 template <typename... KArgs, typename... Args>
@@ -1930,8 +1987,14 @@ void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, c
   const unsigned grid1 = c.grid_seg1, grid2 = c.grid_seg;
 #define SEG_CALL b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, bins, dl, c.stage, c.xr
   const size_t smem = segment_smem(nops, c.stage);
+  // pattern sweeps (default variant only): the op sequence is compiled in
+  const SeqKernel* pat = (c.seg_variant == 20 && c.patterns && !full) ? seq_kernel(host_ops, nops, c.patterns >= 2 ? 3 : 2) : nullptr;
   if (full) launch_chain(c, seg_kernel(seg_full_variant(c.seg_variant)), dim3(grid1), dim3(HPS_BLOCK), smem, SEG_CALL);
-  else launch_chain(c, seg_kernel(c.seg_variant), dim3(grid2), dim3(HPS_BLOCK), smem, SEG_CALL);
+  else if (pat) {
+    const unsigned pairs = (b.n + 1) / 2;
+    const unsigned grid = std::max(1u, std::min((pairs + HPS_BLOCK - 1) / HPS_BLOCK, (unsigned)(c.num_sms * pat->minb)));
+    launch_chain(c, pat->fn, dim3(grid), dim3(HPS_BLOCK), smem, SEG_CALL);
+  } else launch_chain(c, seg_kernel(c.seg_variant), dim3(grid2), dim3(HPS_BLOCK), smem, SEG_CALL);
 #undef SEG_CALL
 }
 void launch_lloss_pass(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc) {
@@ -1964,27 +2027,22 @@ size_t field_smem(const KickParams& kp, int /*threads*/) {
 unsigned field_chunks(const KickParams& kp) { return (kp.nr + field_rs(kp) - 1) / field_rs(kp); }
 // sets the dynamic-shared-memory opt-in of the chain kernels for a mesh (done at SCHEFF allocation, so that no
 // function attribute has to change while a stream capture is in progress)
+// (the attribute is per device: it is set for the CURRENT device every time a SCHEFF is allocated there, never cached
+//  process-wide -- a second device would otherwise run meshes above 48 KB without the opt-in)
 cudaError_t prepare_chain_attributes(const KickParams& kp) {
-  if (deposit_smem(kp) > 48 * 1024 && !g_deposit_smem_set) {
+  if (deposit_smem(kp) > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    g_deposit_smem_set = 1;
   }
-  if (field_smem(kp, field_threads(kp)) > 48 * 1024 && !g_field_smem_set) {
+  if (field_smem(kp, field_threads(kp)) > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    g_field_smem_set = 1;
   }
   return cudaSuccess;
 }
 cudaError_t launch_deposit(const LaunchCfg& c, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
                            const KickParams& kp) {
-  const size_t smem = deposit_smem(kp);
-  if (smem > 48 * 1024 && !g_deposit_smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    g_deposit_smem_set = 1;
-  }
+  const size_t smem = deposit_smem(kp);  // (> 48 KB: opted in by prepare_chain_attributes when the SCHEFF was allocated)
   launch_chain(c, k_deposit, dim3(c.grid_deposit), dim3(512), smem, b, st, sc, bins, kp, c.ticket + 1, c.xr);
   return cudaSuccess;
 }
@@ -1992,11 +2050,6 @@ cudaError_t launch_field(const LaunchCfg& c, DevStats* st, ScDev* sc, const doub
                          u32* tickets, const KickParams& kp, u32 mesh_seq) {
   const int T = field_threads(kp);
   const size_t smem = field_smem(kp, T);
-  if (smem > 48 * 1024 && !g_field_smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    g_field_smem_set = 1;
-  }
   launch_chain(c, k_field, dim3(kp.nr + 1, field_chunks(kp)), dim3(T * field_rs(kp)), smem, st, sc, bins, field, part, tickets, kp, T, mesh_seq, c.xr);
   return cudaSuccess;
 }
@@ -2027,11 +2080,10 @@ unsigned scheff_items(const KickParams& kp) { const unsigned rs = scheff_rs(kp);
 int scheff_occupancy(const KickParams& kp) {
   const size_t smem = scheff_smem(kp);
   const bool big = scheff_block() == 1024;
-  if (smem > 48 * 1024 && !g_scheff_smem_set) {
+  if (smem > 48 * 1024) {
     cudaError_t e = big ? cudaFuncSetAttribute(k_scheff<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
                         : cudaFuncSetAttribute(k_scheff<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return 0;
-    g_scheff_smem_set = 1;
   }
   int nb = 0;
   if (big) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scheff<1024>, 1024, smem);
@@ -2088,6 +2140,8 @@ int segment_occupancy(int variant) {
   // static + dynamic shared memory of the sweep exceed the 48 KB default: opt in once per variant and device
   const size_t smem = segment_smem(HPS_MAX_SEG_OPS, 1);  // the largest launch
   cudaFuncSetAttribute(seg_kernel(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (variant == 20)
+    for (const SeqKernel& e : g_seq_kernels) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg_kernel(variant), HPS_BLOCK, smem);
   return nb;

@@ -127,11 +127,13 @@ __device__ __forceinline__ void xr_exchange_p2p(double* total, int ns, unsigned 
     ll_send(&xr.peer[p]->data[par][xr.rank][w], (w & 1) ? (u32)(bits >> 32) : (u32)bits, seq32);
   }
   const XrBox* own = xr.peer[xr.rank];
+  const unsigned long long t_sent = threadIdx.x == 0 ? global_ns() : 0ull;
   for (int t = threadIdx.x; t < xr.nranks * nw; t += blockDim.x) {
     const int r = t / nw, w = t - r * nw;
     s_recv[r * (2 * HPS_XR_NS) + w] = ll_recv(&own->data[par][r][w], seq32, xr.err);
   }
   __syncthreads();
+  if (threadIdx.x == 0) { xr.stats[0] += global_ns() - t_sent; xr.stats[1] += 1ull; }  // own stores issued -> all peers' words here
   if ((int)threadIdx.x < ns) {
     const int s = threadIdx.x;
     const bool mx = (max_mask >> s) & 1u, as_int = (int_mask >> s) & 1u;

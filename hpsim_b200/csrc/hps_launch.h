@@ -19,6 +19,8 @@ struct LaunchCfg {
   u32* ticket;            // [0] reductions, [1] deposit hand-off (sharded beams)
   int pdl;                // launch the kick-chain kernels with programmatic stream serialization
   int stage;              // the sweep stages each thread's next particle pair in shared memory with cp.async
+  int patterns;           // use the pattern sweeps (op sequence compiled in) where the launch matches one
+  int num_sms;
   XrView xr;              // cross-rank exchange of a particle-sharded beam (mode XR_NONE otherwise)
 };
 

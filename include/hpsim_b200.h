@@ -123,6 +123,10 @@ int hps_ctx_comm_init(hps_ctx*, int rank, int nranks, const void* nccl_unique_id
 /* 0 = single rank, 1 = in-kernel exchange over peer memory (CUDA IPC, NVLink), 2 = NCCL all-gather
  * between kernels (fallback when the peer mapping is unavailable, or HPSIM_XR=nccl). */
 int hps_ctx_comm_mode(hps_ctx*);
+/* Wait-time accounting of the in-kernel exchanges of a sharded beam (no reference counterpart): out[0] ns the reducing
+ * kernels' last blocks spent between issuing their own stores and holding every peer's words, out[1] number of such
+ * exchanges, out[2] ns block 0 of the field solve waited for the peers' charge meshes after its Green slice, out[3] count. */
+int hps_ctx_comm_stats(hps_ctx*, uint64_t out[4]);
 
 /* Pinned host staging buffers for hps_beam_upload / hps_beam_download (optional: any host pointer
  * works, pinned ones copy at full PCIe rate), and the number of kernels this context has launched

@@ -1234,6 +1234,7 @@ int hps_oracle_set_comm(hps_ctx* c, int rank, int nranks, hps_oracle_allreduce_f
   return HPS_OK;
 }
 int hps_ctx_comm_mode(hps_ctx*) { return 0; }
+int hps_ctx_comm_stats(hps_ctx*, uint64_t out[4]) { for (int k = 0; k < 4; ++k) out[k] = 0; return HPS_OK; }
 int hps_ctx_synchronize(hps_ctx*) { return HPS_OK; }
 void* hps_host_alloc(size_t bytes) { return std::malloc(bytes); }
 void hps_host_free(void* p) { std::free(p); }

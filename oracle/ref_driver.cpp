@@ -233,6 +233,9 @@ int main(int argc, char** argv) {
   // moments exactly as the Python getters would refresh them
   beam.UpdateLoss();
   beam.UpdateLongitudinalLoss();
+  std::cout.precision(17);
+  std::cout << "ref_driver: after UpdateLongitudinalLoss num_good=" << beam.GetGoodParticleNum() << " phi_avg_good=" << beam.GetAvgPhi(true)
+            << " num_loss=" << beam.GetLossNum() << " num_lloss=" << beam.GetLongitudinalLossNum() << std::endl;
   beam.UpdateEmittance();
   beam.UpdateAvgW(); beam.UpdateSigW();
   beam.UpdateAvgPhi(); beam.UpdateSigPhi();

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <string>
 #include <vector>
 
 #include "../hpsim_b200/csrc/hps_kernels.cuh"
@@ -171,6 +172,25 @@ static int plan_main(int argc, char** argv) {
   }
   size_t nkick_ops = 0, ngap = 0;
   for (const Op& op : plan.ops) { nkick_ops += op.type == OP_SC_KICK; ngap += op.type == OP_GAP_FIRST; }
+  if (getenv("HPS_PLAN_PATTERNS")) {  // histogram of the op-type sequences of the segments (which fused sweeps dominate)
+    std::vector<std::pair<std::string, size_t>> hist;
+    for (const Segment& s : plan.segs) {
+      std::string key;
+      for (u32 k = 0; k < s.op_count; ++k) {
+        const Op& op = plan.ops[s.op_begin + k];
+        static const char* nm[] = {"none", "drift", "quad", "gap1", "gap2", "dip1", "dip2", "bunch", "rot", "steer", "capert", "rapert", "KICK", "freq"};
+        key += nm[op.type];
+        if (op.type == OP_GAP_FIRST || op.type == OP_GAP_SECOND) key += op.flag ? "c" : "d";
+        key += " ";
+      }
+      key += s.kick_follows ? "| kick" : ((s.fin_mode & 3) == FIN_APERTURE ? "| aperture" : "| -");
+      bool found = false;
+      for (auto& h : hist) if (h.first == key) { h.second++; found = true; break; }
+      if (!found) hist.push_back({key, 1});
+    }
+    std::sort(hist.begin(), hist.end(), [](const std::pair<std::string, size_t>& a, const std::pair<std::string, size_t>& b) { return a.second > b.second; });
+    for (auto& h : hist) printf("PATTERN %6zu  %s\n", h.second, h.first.c_str());
+  }
   printf("PLAN ops %zu segments %zu kicks %u kick_segments %zu kick_ops %zu gaps %zu aperture_syncs %zu max_ops_per_segment %zu "
          "freq %.4f design_w %.6f\n", plan.ops.size(), plan.segs.size(), plan.n_kicks, kick_segs, nkick_ops, ngap, fin_aper, max_ops, bh.freq, bh.design_w);
   return 0;

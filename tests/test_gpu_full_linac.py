@@ -366,6 +366,8 @@ def _monitor_run(lib, n, last, sc, cap=64):
     c.sim.set_plot_data(pd)
     r = c.run("TBDB02", last)
     c.beam.get_loss_num("l")
+    print("MONITOR_RUN after get_loss_num('l'): num_good", c.beam._stat("num_good"), "phi_avg_good", repr(c.beam._stat("phi_avg_good")),
+          "num_loss", c.beam._stat("num_loss"), "num_lloss", c.beam._stat("num_lloss"))
     vals = pd.values()
     st = c.state()
     c.sim.set_plot_data(None)
@@ -391,9 +393,16 @@ def test_monitor_rows_vs_oracle_and_reference(tmp_path, sc):
     assert np.all(np.diff(vg["loss_ratio"]) >= 0) and vg["loss_ratio"][-1] > 0.05
     if HAVE_REF:
         mon_out = os.path.join(str(tmp_path), "mon.bin")
-        ref, _ = H.run_reference(str(tmp_path), n, "TBDB02", last, sc=sc, double=True, extra=["monitor 64", f"monitor_out {mon_out}"])
+        ref, log = H.run_reference(str(tmp_path), n, "TBDB02", last, sc=sc, double=True, extra=["monitor 64", f"monitor_out {mon_out}"])
+        print("MONITOR_REF", [l for l in log.splitlines() if "after UpdateLongitudinalLoss" in l])
+        _, log0 = H.run_reference(str(tmp_path), n, "TBDB02", last, sc=sc, double=True)
+        print("MONITOR_REF_NOMON", [l for l in log0.splitlines() if "after UpdateLongitudinalLoss" in l])
         vr = H.read_monitor_file(mon_out, 64)
         rep = H.compare(sg, ref, 1e-9)
+        if not rep["lloss_equal"]:
+            bad = np.nonzero(sg["lloss"] != ref["lloss"])[0]
+            print("MONITOR_LLOSS_DIFF", bad[:20], sg["lloss"][bad[:20]], ref["lloss"][bad[:20]], sg["phi"][bad[:20]], ref["phi"][bad[:20]],
+                  "good-mean phi", sg["phi"][(sg["loss"] == 0) & (sg["lloss"] == 0)].mean(), ref["phi"][(ref["loss"] == 0) & (ref["lloss"] == 0)].mean())
         assert rep["loss_equal"] and rep["lloss_equal"], rep
         for f in K.MON_FIELDS:
             a, b = vg[f], vr[f][:nmon]
