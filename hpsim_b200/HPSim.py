@@ -594,8 +594,13 @@ def get_db_model(record: str, field: str, dbconn: DBConnection) -> str:
     return ""
 
 
-def _reload(dbconn: DBConnection, beamline: BeamLine) -> int:
-    return beamline._refresh(L.load_from_conn(dbconn.conn, dbconn.dbs, write_model_index=False))
+def _reload(dbconn: DBConnection, beamline: BeamLine, names=None) -> int:
+    """Push what a database write changed down to the engine.  `names`: only these elements are re-read (the reference's
+    PVObserver re-reads the elements attached to the PV, pv_observer.cpp:18-23); None re-reads the whole line (~1 s for
+    the 6 540-element LANSCE lattice -- tens of thousands of single-column SELECTs)."""
+    if names is None:
+        return beamline._refresh(L.load_from_conn(dbconn.conn, dbconn.dbs, write_model_index=False))
+    return beamline._refresh(L.reload_elements(dbconn.conn, dbconn.dbs, beamline.table, names))
 
 
 def set_db_epics(pv: str, value: str, dbconn: DBConnection, beamline: BeamLine) -> None:
@@ -606,7 +611,8 @@ def set_db_epics(pv: str, value: str, dbconn: DBConnection, beamline: BeamLine) 
         cur = dbconn.conn.execute(f"update {db}.epics_channel set value = ? where lcs_name = ?", (str(value), pv))
         if cur.rowcount:
             break
-    _reload(dbconn, beamline)
+    names = L.pv_elements(dbconn.conn, dbconn.dbs, pv)
+    _reload(dbconn, beamline, names if names else None)  # a PV nobody listens to in channel_list: re-read everything
 
 
 def set_db_model(record: str, field: str, value: str, dbconn: DBConnection, beamline: BeamLine) -> None:
@@ -622,5 +628,10 @@ def set_db_model(record: str, field: str, value: str, dbconn: DBConnection, beam
             if dbconn.conn.execute(f"select id from {db}.{tbl} where name = ?", (record,)).fetchone() is None:
                 continue
             dbconn.conn.execute(f"update {db}.{tbl} set {field} = {value} where name = ?", (record,))
-            _reload(dbconn, beamline)
+            if tbl == "rf_module":  # a module stands for all of its gaps
+                names = [r[0] for r in dbconn.conn.execute(
+                    f"select g.name from {db}.rf_gap g join {db}.rf_module m on m.id = g.module_id where m.name = ?", (record,))]
+            else:
+                names = [record]
+            _reload(dbconn, beamline, names)
             return

@@ -54,7 +54,7 @@ struct hps_ctx {
   // cp.async staging of the next particle pair in the sweep: -1 = automatic (on when the rank's particle state does not
   // fit the L2 anyway), 0 / 1 = forced (HPSIM_STAGE)
   int stage = -1;
-  int patterns = 1;  // HPSIM_PATTERNS=0: always the generic sweep
+  int patterns = 2;  // HPSIM_PATTERNS=0: always the generic sweep; 1: pattern sweeps at 2 blocks per SM; 2: 3 blocks per SM for the drift patterns
   // program upload buffers
   Op* d_ops = nullptr;
   OpC* d_opc = nullptr;  // device-prepared constants, parallel to d_ops
@@ -101,6 +101,7 @@ struct hps_ctx {
   char* flush_buf = nullptr;
   size_t flush_bytes = 0;
   hps_monitor* monitor = nullptr;  // param->graphics_on / plot_data of InitEngine (not owned)
+  int comm_failed = 0;             // an NCCL collective of a Beam::Update* call failed (reported by the next getter)
 };
 
 struct hps_beam {
@@ -227,6 +228,18 @@ int xr_after_reduce(hps_ctx* c, const LaunchCfg& l, int kind, int fin_mode, int 
   return HPS_OK;
 }
 
+// Sharded beam, P2P exchange: a peer that did not answer within HPS_XR_TIMEOUT_NS left the error word set (the kernels
+// carry on with stale data rather than hang the GPU).  Called at every synchronising entry point, with the stream idle:
+// reports the failure once and clears the word.
+int xr_check(hps_ctx* c) {
+  if (c->xr.mode != XR_P2P || !c->xr.err) return HPS_OK;
+  u32 xerr = 0;
+  CK(c, cudaMemcpy(&xerr, c->xr.err, sizeof(u32), cudaMemcpyDeviceToHost));
+  if (!xerr) return HPS_OK;
+  CK(c, cudaMemset(c->xr.err, 0, sizeof(u32)));
+  return fail(c, HPS_ERR_COMM, "a peer rank did not answer a cross-rank exchange within 2 s: the results since the last synchronisation are invalid");
+}
+
 void carve(hps_beam* b, char* slab, double* c[6], u32** loss, u32** lloss) {
   const size_t da = align_up((size_t)b->n_alloc * sizeof(double), 256), ua = align_up((size_t)b->n_alloc * sizeof(u32), 256);
   for (int i = 0; i < 6; ++i) c[i] = reinterpret_cast<double*>(slab + i * da);
@@ -246,7 +259,8 @@ void stat(hps_beam* b, const StatReq& r) {
   const BeamView v = view(b);
   launch_stat(l, v, b->st, r);
   b->ctx->launches++;
-  xr_after_reduce(b->ctx, l, FK_STAT, 0, 0, &r, nullptr, v, b->st, nullptr, nullptr);
+  // (XR_NCCL: a failed all-gather leaves its message in the context; hps_beam_update / hps_beam_get report it)
+  if (xr_after_reduce(b->ctx, l, FK_STAT, 0, 0, &r, nullptr, v, b->st, nullptr, nullptr) != HPS_OK) b->ctx->comm_failed = 1;
 }
 void UpdateLoss(hps_beam* b) { stat(b, req(KS_COUNT_LOSS)); }
 void UpdateGoodParticleCount(hps_beam* b) { stat(b, req(KS_COUNT_GOOD, 0, -1, 1)); }
@@ -472,7 +486,10 @@ int hps_ctx_set_math(hps_ctx* c, int mode) {
   c->seg_grid_cap_full = (unsigned)c->num_sms * (unsigned)std::max(1, segment_occupancy(segment_full_variant(c->seg_variant)));
   return HPS_OK;
 }
-int hps_ctx_synchronize(hps_ctx* c) { CK(c, cudaStreamSynchronize(c->stream)); return HPS_OK; }
+int hps_ctx_synchronize(hps_ctx* c) {
+  CK(c, cudaStreamSynchronize(c->stream));
+  return xr_check(c);
+}
 uint64_t hps_ctx_launch_count(hps_ctx* c) { return c->launches; }
 int hps_ctx_set_profile(hps_ctx* c, int on) {
   c->profile = on;
@@ -684,7 +701,7 @@ int hps_beam_download(hps_beam* b, double* x, double* xp, double* y, double* yp,
   if (loss) CK(c, cudaMemcpyAsync(loss, b->loss, (size_t)b->n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (lloss) CK(c, cudaMemcpyAsync(lloss, b->lloss, (size_t)b->n * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  return HPS_OK;
+  return xr_check(c);
 }
 int hps_beam_download_phi_relative(hps_beam* b, int use_good, double* out) {
   hps_ctx* c = b->ctx;
@@ -926,6 +943,7 @@ int hps_beam_moment_stats(hps_beam* b, uint64_t out[3], double* pivot_err_max, d
 int hps_beam_get(hps_beam* b, int id, double* out) {
   hps_ctx* c = b->ctx;
   if (id < 0 || id >= HPS_STAT_COUNT) return fail(c, HPS_ERR_ARG, "unknown stat id");
+  if (c->comm_failed) { c->comm_failed = 0; return HPS_ERR_COMM; }
   cudaSetDevice(c->device);
   DevStats h;
   CK(c, cudaMemcpyAsync(&h, b->st, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
@@ -1351,6 +1369,15 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
       e0 = e1 + 1;
     }
   }
+  if (c->monitor) {
+    // online mode: Simulate() ends with Beam::UpdateStatForPlotting (simulation_engine.cpp:93-94, beam.cpp:1024-1029) --
+    // the whole kick-statistics chain once more (it MARKS longitudinal losses, also with space charge off), sigma_W and
+    // <phi_r> of the good particles
+    if (c->xr.mode == XR_NCCL) return fail(c, HPS_ERR_ARG, "monitors are not supported with the NCCL all-gather exchange (HPSIM_XR=nccl)");
+    UpdateStatForSpaceCharge(b);
+    UpdateSig(b, HPS_W, HPS_STAT_W_SIG_GOOD, true);
+    UpdateAvg(b, 6, HPS_STAT_PHI_AVG_R, true);
+  }
   CK(c, cudaEventRecord(c->ev1, c->stream));
   CK(c, cudaGetLastError());
   prof_finish(c);
@@ -1378,11 +1405,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
     out->extra_sweeps = extra;
     out->launches = c->launches - launches0;
     out->device_ms = ms;
-    if (c->xr.mode == XR_P2P) {
-      u32 xerr = 0;
-      CK(c, cudaMemcpy(&xerr, c->xr.err, sizeof(u32), cudaMemcpyDeviceToHost));
-      if (xerr) return fail(c, HPS_ERR_COMM, "a peer rank did not answer a cross-rank exchange within 20 s");
-    }
+    return xr_check(c);
   }
   return HPS_OK;
 }

@@ -85,7 +85,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define HPS_XR_TIMEOUT_NS 20000000000ull  // a peer that stays silent this long is reported, not waited for
+#define HPS_XR_TIMEOUT_NS 2000000000ull  // a peer that stays silent this long (2 s) is reported, not waited for
 
 // LL word = 32-bit payload | (32-bit sequence number << 32); 8-byte stores are single transactions.
 __device__ __forceinline__ void ll_send(unsigned long long* word, u32 payload, u32 seq32) {

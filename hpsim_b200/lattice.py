@@ -105,108 +105,163 @@ _TABLE_OF = {"quad": "quad", "drift": "drift", "dtl_gap": "rf_gap", "ccl_gap": "
              "buncher": "buncher", "dipole": "dipole", "spch_comp": "spch_comp", "steerer": "steerer"}
 
 
+def _new_elem(etype, name):
+    e = np.zeros((), dtype=ELEM_DTYPE)
+    e["type"] = etype
+    e["name"] = str(name).encode()[: NAME_LEN - 1]
+    return e
+
+
+def _read_element(conn: sqlite3.Connection, q: _Db, db: str, name, view_index, mtype):
+    """One row of `linac` -> element record (GenerateBeamLine's per-type blocks, reference src/beamline/src/init.cpp:75-429;
+    the same columns PVObserver::UpdateModel re-reads, src/server/src/pv_observer.cpp:92-364).  None for unknown types."""
+    new = _new_elem
+
+    def col(table, column, _vi=view_index, _db=db):
+        return q.one(f"select {_txt(column)} from {_db}.{table} where view_index = {_vi}")
+
+    if mtype == "quad":
+        e = new(QUAD, name)
+        e["p"][2] = _atof(col("quad", "gradient_model"))
+        e["p"][0] = _atof(col("quad", "length_model"))
+        e["p"][1] = _atof(col("quad", "aperture_model"))
+        if _atoi(col("quad", "monitor")) > 0:
+            e["flags"] |= FLAG_MONITOR
+    elif mtype == "drift":
+        e = new(DRIFT, name)
+        e["p"][0] = _atof(col("drift", "length_model"))
+        e["p"][1] = _atof(col("drift", "aperture_model"))
+    elif mtype in ("dtl_gap", "ccl_gap"):
+        e = new(RFGAP_DTL if mtype == "dtl_gap" else RFGAP_CCL, name)
+        key = "cell_id" if mtype == "dtl_gap" else "tank_id"
+        ttf = conn.execute(
+            "select " + ", ".join(_txt("t1." + c) for c in (
+                "beta_g", "beta_min", "ta0", "ta1", "ta2", "ta3", "ta4", "ta5",
+                "sa1", "sa2", "sa3", "sa4", "sa5"))
+            + f" from {db}.transit_time_factor t1 join {db}.rf_gap t2 on "
+            f"t1.module_id = t2.module_id and t1.tank_id = t2.{key} "
+            f"where t2.view_index = {view_index}").fetchone()
+        p = e["p"]
+        p[12:25] = [_atof(v) for v in ttf]
+        p[0] = _atof(col("rf_gap", "length_model"))
+        p[1] = _atof(col("rf_gap", "frequency_model"))
+        p[2] = _atof(q.one(
+            f"select {_txt('cell_length_betalambda_design')} from {db}.rf_module where id = "
+            f"(select module_id from {db}.rf_gap where view_index = {view_index})"))
+        p[3] = _atof(col("rf_gap", "amplitude_model"))
+        p[4] = _atof(col("rf_gap", "ref_phase_model"))
+        p[5] = _atof(col("rf_gap", "beam_phase_shift_model"))
+        p[6] = _atof(col("rf_gap", "energy_out_model"))
+        p[7] = _atof(col("rf_gap", "beta_center_model"))
+        p[8] = _atof(col("rf_gap", "dg_model"))
+        p[9] = _atof(col("rf_gap", "t_model"))
+        p[10] = _atof(col("rf_gap", "tp_model"))
+        p[11] = _atof(col("rf_gap", "sp_model"))
+    elif mtype == "rotation":
+        e = new(ROTATION, name)
+        e["p"][0] = _atof(col("rotation", "angle_model"))
+    elif mtype == "caperture":
+        e = new(CAPERTURE, name)
+        e["p"][0] = _atof(col("caperture", "aperture_model"))
+        if _atoi(col("caperture", "in_out_model")) > 0:
+            e["flags"] |= FLAG_ON
+    elif mtype == "raperture":
+        e = new(RAPERTURE, name)
+        e["p"][0] = _atof(col("raperture", "aperture_xl_model"))
+        e["p"][1] = _atof(col("raperture", "aperture_xr_model"))
+        e["p"][2] = _atof(col("raperture", "aperture_yt_model"))
+        e["p"][3] = _atof(col("raperture", "aperture_yb_model"))
+        if _atoi(col("raperture", "in_out_model")) > 0:
+            e["flags"] |= FLAG_ON
+    elif mtype == "diagnostics":
+        e = new(DIAGNOSTICS, name)
+        if _atoi(col("diagnostics", "monitor")) > 0:
+            e["flags"] |= FLAG_MONITOR
+    elif mtype == "buncher":
+        e = new(BUNCHER, name)
+        e["p"][0] = _atof(col("buncher", "voltage_model"))
+        e["p"][1] = _atof(col("buncher", "frequency_model"))
+        e["p"][2] = _atof(col("buncher", "phase_model"))
+        e["p"][3] = _atof(col("buncher", "aperture_model"))
+        if _atoi(col("buncher", "on_off")) > 0:
+            e["flags"] |= FLAG_ON
+    elif mtype == "dipole":
+        e = new(DIPOLE, name)
+        for k, c in enumerate(("rho_model", "angle_model", "edge_angle1_model",
+                               "edge_angle2_model", "half_gap_model", "k1_model",
+                               "k2_model", "field_index_model", "kenergy_model")):
+            e["p"][k] = _atof(col("dipole", c))
+    elif mtype == "spch_comp":
+        e = new(SPCH_COMP, name)
+        e["p"][0] = _atof(col("spch_comp", "fraction_model"))
+    elif mtype == "steerer":
+        e = new(STEERER, name)
+        e["p"][0] = _atof(col("steerer", "bl_h_model"))
+        e["p"][1] = _atof(col("steerer", "bl_v_model"))
+    else:
+        return None  # GenerateBeamLine ignores unknown model types
+    return e
+
+
 def load_from_conn(conn: sqlite3.Connection, dbs: Iterable[str], write_model_index: bool = False) -> np.ndarray:
     """`write_model_index=True` also records each element's model index in its table row, as
     GenerateBeamLine does (init.cpp:68-73) -- only ever used on a private in-memory copy."""
     q = _Db(conn)
     out = []
-
-    def new(etype, name):
-        e = np.zeros((), dtype=ELEM_DTYPE)
-        e["type"] = etype
-        e["name"] = str(name).encode()[: NAME_LEN - 1]
-        return e
-
     for db in dbs:
         rows = conn.execute(f"select name, {_txt('view_index')}, model_type from {db}.linac").fetchall()
         for name, view_index, mtype in rows:
-            def col(table, column, _vi=view_index, _db=db):
-                return q.one(f"select {_txt(column)} from {_db}.{table} where view_index = {_vi}")
-
-            if mtype == "quad":
-                e = new(QUAD, name)
-                e["p"][2] = _atof(col("quad", "gradient_model"))
-                e["p"][0] = _atof(col("quad", "length_model"))
-                e["p"][1] = _atof(col("quad", "aperture_model"))
-                if _atoi(col("quad", "monitor")) > 0:
-                    e["flags"] |= FLAG_MONITOR
-            elif mtype == "drift":
-                e = new(DRIFT, name)
-                e["p"][0] = _atof(col("drift", "length_model"))
-                e["p"][1] = _atof(col("drift", "aperture_model"))
-            elif mtype in ("dtl_gap", "ccl_gap"):
-                e = new(RFGAP_DTL if mtype == "dtl_gap" else RFGAP_CCL, name)
-                key = "cell_id" if mtype == "dtl_gap" else "tank_id"
-                ttf = conn.execute(
-                    "select " + ", ".join(_txt("t1." + c) for c in (
-                        "beta_g", "beta_min", "ta0", "ta1", "ta2", "ta3", "ta4", "ta5",
-                        "sa1", "sa2", "sa3", "sa4", "sa5"))
-                    + f" from {db}.transit_time_factor t1 join {db}.rf_gap t2 on "
-                    f"t1.module_id = t2.module_id and t1.tank_id = t2.{key} "
-                    f"where t2.view_index = {view_index}").fetchone()
-                p = e["p"]
-                p[12:25] = [_atof(v) for v in ttf]
-                p[0] = _atof(col("rf_gap", "length_model"))
-                p[1] = _atof(col("rf_gap", "frequency_model"))
-                p[2] = _atof(q.one(
-                    f"select {_txt('cell_length_betalambda_design')} from {db}.rf_module where id = "
-                    f"(select module_id from {db}.rf_gap where view_index = {view_index})"))
-                p[3] = _atof(col("rf_gap", "amplitude_model"))
-                p[4] = _atof(col("rf_gap", "ref_phase_model"))
-                p[5] = _atof(col("rf_gap", "beam_phase_shift_model"))
-                p[6] = _atof(col("rf_gap", "energy_out_model"))
-                p[7] = _atof(col("rf_gap", "beta_center_model"))
-                p[8] = _atof(col("rf_gap", "dg_model"))
-                p[9] = _atof(col("rf_gap", "t_model"))
-                p[10] = _atof(col("rf_gap", "tp_model"))
-                p[11] = _atof(col("rf_gap", "sp_model"))
-            elif mtype == "rotation":
-                e = new(ROTATION, name)
-                e["p"][0] = _atof(col("rotation", "angle_model"))
-            elif mtype == "caperture":
-                e = new(CAPERTURE, name)
-                e["p"][0] = _atof(col("caperture", "aperture_model"))
-                if _atoi(col("caperture", "in_out_model")) > 0:
-                    e["flags"] |= FLAG_ON
-            elif mtype == "raperture":
-                e = new(RAPERTURE, name)
-                e["p"][0] = _atof(col("raperture", "aperture_xl_model"))
-                e["p"][1] = _atof(col("raperture", "aperture_xr_model"))
-                e["p"][2] = _atof(col("raperture", "aperture_yt_model"))
-                e["p"][3] = _atof(col("raperture", "aperture_yb_model"))
-                if _atoi(col("raperture", "in_out_model")) > 0:
-                    e["flags"] |= FLAG_ON
-            elif mtype == "diagnostics":
-                e = new(DIAGNOSTICS, name)
-                if _atoi(col("diagnostics", "monitor")) > 0:
-                    e["flags"] |= FLAG_MONITOR
-            elif mtype == "buncher":
-                e = new(BUNCHER, name)
-                e["p"][0] = _atof(col("buncher", "voltage_model"))
-                e["p"][1] = _atof(col("buncher", "frequency_model"))
-                e["p"][2] = _atof(col("buncher", "phase_model"))
-                e["p"][3] = _atof(col("buncher", "aperture_model"))
-                if _atoi(col("buncher", "on_off")) > 0:
-                    e["flags"] |= FLAG_ON
-            elif mtype == "dipole":
-                e = new(DIPOLE, name)
-                for k, c in enumerate(("rho_model", "angle_model", "edge_angle1_model",
-                                       "edge_angle2_model", "half_gap_model", "k1_model",
-                                       "k2_model", "field_index_model", "kenergy_model")):
-                    e["p"][k] = _atof(col("dipole", c))
-            elif mtype == "spch_comp":
-                e = new(SPCH_COMP, name)
-                e["p"][0] = _atof(col("spch_comp", "fraction_model"))
-            elif mtype == "steerer":
-                e = new(STEERER, name)
-                e["p"][0] = _atof(col("steerer", "bl_h_model"))
-                e["p"][1] = _atof(col("steerer", "bl_v_model"))
-            else:
-                continue  # GenerateBeamLine ignores unknown model types
+            e = _read_element(conn, q, db, name, view_index, mtype)
+            if e is None:
+                continue
             if write_model_index:
                 conn.execute(f"update {db}.{_TABLE_OF[mtype]} set model_index = {len(out)} where view_index = {view_index}")
             out.append(e)
     return np.array(out, dtype=ELEM_DTYPE)
+
+
+def reload_elements(conn: sqlite3.Connection, dbs: Iterable[str], table: np.ndarray, elem_names: Iterable[str]) -> np.ndarray:
+    """Re-reads only the named elements (what PVObserver::UpdateModel does for the elements attached to a PV,
+    reference src/server/src/pv_observer.cpp:18-23) and returns an updated copy of `table`."""
+    q = _Db(conn)
+    out = table.copy()
+    index = {n.decode(): i for i, n in enumerate(table["name"])}
+    for nm in elem_names:
+        i = index.get(nm)
+        if i is None:
+            continue
+        for db in dbs:
+            row = conn.execute(f"select {_txt('view_index')}, model_type from {db}.linac where name = ?", (nm,)).fetchone()
+            if row is None:
+                continue
+            e = _read_element(conn, q, db, nm, row[0], row[1])
+            if e is not None:
+                out[i] = e
+            break
+    return out
+
+
+def pv_elements(conn: sqlite3.Connection, dbs: Iterable[str], pv: str) -> list[str]:
+    """Names of the beamline elements a PV drives: InitPVObserverList (reference src/server/src/init_pv_observer_list.cpp:8-121)
+    -- the elements of `channel_list` that name the PV in channel1..4; an rf_module stands for all of its gaps; a master
+    phase PV (value_type rf_ph_master) stands for the gaps of every module whose phase channel it steers."""
+    names: list[str] = []
+    for db in dbs:
+        try:
+            vt = conn.execute(f"select value_type from {db}.epics_channel where lcs_name = ?", (pv,)).fetchone()
+            elems = conn.execute(f"select model_type, name from {db}.channel_list where channel1 = ? or channel2 = ? or channel3 = ? "
+                                 f"or channel4 = ?", (pv, pv, pv, pv)).fetchall()
+        except sqlite3.Error:
+            continue
+        if vt is None:
+            continue
+        for mtype, name in elems:
+            if mtype == "rf_module":
+                names += [r[0] for r in conn.execute(
+                    f"select g.name from {db}.rf_gap g join {db}.rf_module m on m.id = g.module_id where m.name = ?", (name,))]
+            else:
+                names.append(name)
+    return names
 
 
 def load_from_dbs(db_paths: Sequence[str], names: Sequence[str] | None = None) -> np.ndarray:

@@ -289,6 +289,8 @@ int hps_scheff_phase_cycles(hps_scheff*, uint64_t out[8]);
  * diagnostics element (:331-335) whose HPS_FLAG_MONITOR is set refreshes the loss count and the emittances
  * (Beam::UpdateLoss, Beam::UpdateEmittance -- with their side effects on the stale counters the kick chain reads) and
  * appends one row of 17 values.  Rows restart at 0 whenever the engine is reset (monitor_num, simulation_engine.cu:105).
+ * Like the reference's online mode, hps_simulate then also ends with Beam::UpdateStatForPlotting
+ * (simulation_engine.cpp:93-94, beam.cpp:1024-1029), which marks longitudinal losses even with space charge off.
  * Everything happens on the device inside hps_simulate; hps_monitor_download is the only synchronising call. */
 typedef struct hps_monitor hps_monitor;
 enum hps_monitor_field {           /* members of PlotData, in this order */

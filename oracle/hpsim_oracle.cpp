@@ -1582,6 +1582,11 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
       int rc = VisitElement(c, b, lat, sc, i);
       if (rc != HPS_OK) return rc;
     }
+  if (c->monitor) {  // simulation_engine.cpp:93-94 -> Beam::UpdateStatForPlotting (beam.cpp:1024-1029)
+    UpdateStatForSpaceCharge(b);
+    UpdateSig(b, b->w, HPS_STAT_W_SIG_GOOD, true);
+    UpdateAvg(b, b->phi_r, HPS_STAT_PHI_AVG_R, true);
+  }
   auto t1 = std::chrono::steady_clock::now();
   if (out) {
     std::memset(out, 0, sizeof(*out));

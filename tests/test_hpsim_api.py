@@ -195,3 +195,34 @@ def test_monitor_rows_on_the_oracle():
     c.run("TBDB02", "01QM03")            # restart upstream: Reset() zeroes monitor_num
     assert pd.values()["count"] == 4
     c.sim.set_plot_data(None)
+
+
+def test_set_db_epics_rereads_only_the_elements_of_the_pv():
+    """set_db_epics re-reads the elements attached to the PV (InitPVObserverList's channel_list relations, reference
+    src/server/src/init_pv_observer_list.cpp:8-121) instead of the whole line; the result must equal a full reload."""
+    import random
+    HPSim._use_library(H.oracle_lib())
+    try:
+        conn = HPSim.DBConnection(H.DB_FILES[0])
+        conn.load_lib(H.SQLITE_EXT)
+        for f, nm in zip(H.DB_FILES[1:], ("dtl", "trst", "ccl")):
+            conn.attach_db(f, nm)
+        conn.clear_model_index()
+        bl = HPSim.BeamLine(conn)
+        assert L.pv_elements(conn.conn, conn.dbs, "TDDB001E04") == ["TDDB01"]
+        random.seed(7)
+        for pv in random.sample(conn.get_epics_channels(), 12):
+            v = HPSim.get_db_epics(pv, conn)
+            try:
+                nv = repr(float(v) * 1.013 + 0.01)
+            except ValueError:
+                continue
+            before = bl.table.copy()
+            HPSim.set_db_epics(pv, nv, conn, bl)
+            full = L.load_from_conn(conn.conn, conn.dbs)
+            assert np.array_equal(full, bl.table), pv
+            names = L.pv_elements(conn.conn, conn.dbs, pv)
+            changed = {bl.table["name"][i].decode() for i in np.nonzero(before != bl.table)[0]}
+            assert changed <= set(names), (pv, changed, names[:4])
+    finally:
+        HPSim._use_library(None)

@@ -10,7 +10,7 @@ for l in open(sys.argv[1]):
               'step frac', round(r['whole_step']['frac'], 3), {k: round(v, 1) for k, v in r.get('by_kernel_ms', {}).items()}, d['config']['run'], d.get('result'))
 PY
 }
-for V in ${VARIANTS:-pat1:HPSIM_PATTERNS=1 pat0:HPSIM_PATTERNS=0}; do
+for V in ${VARIANTS:-pat1:HPSIM_PATTERNS=1 pat2:HPSIM_PATTERNS=2}; do
   NAME=${V%%:*}; ENVS=${V#*:}
   echo "== c4 $NAME ($ENVS)"
   env $(echo $ENVS | tr ',' ' ') timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/bench_c4_$NAME.log 2>&1; echo "  rc=$?"; summ gpurun_out/bench_c4_$NAME.log
