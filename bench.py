@@ -259,6 +259,42 @@ def main():
         tab["p"][i][0] *= 1.0 + 0.05 * (2.0 * (rank + 0.5) / world - 1.0)
         case.beamline._refresh(tab)
 
+    # ---- sharded result against a single-GPU run of the same beam (rank 0, its own context without a communicator).
+    # (1) EXACT on a short range, both beams fresh (LEBT + the first DTL cells, 258 kicks: every exchange of the kick chain
+    #     is exercised hundreds of times and the dynamics have not yet amplified the summation-order difference): loss
+    #     counts equal, sums of w / phi / x^2 over the survivors to 1e-9.  It has to come first: the reference's stale
+    #     counters make a pass depend on the passes before it.
+    # (2) REPORTED on the timed range after the timing: through the whole linac the space-charge dynamics are chaotic (two
+    #     code versions differ by 2 % in the longitudinal-loss count), so the counts of the timed step are compared loosely.
+    check = None
+    if sharded and not args.no_check:
+        def sums(st):
+            a = st["loss"] == 0
+            return np.array([float((st["loss"] != 0).sum()), float((st["lloss"] != 0).sum()), float(st["w"][a].sum()),
+                             float(st["phi"][a].sum()), float((st["x"][a] ** 2).sum()), float(a.sum())])
+        short = ("TBDB02", "01QM10")
+        case.run(*short)
+        import torch
+        t = torch.tensor(sums(case.state()), dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ss = t.numpy()
+        case.beam.restore_initial_beam()
+        if rank == 0:
+            keep = dict(HPSim._ctx_cache)
+            HPSim._ctx_cache.clear()
+            one = H.Case(lib, n=n_beam, sc=True, remesh=cfg["remesh"])
+            one.run(*short)
+            s1 = sums(one.state())
+            del one
+            HPSim._ctx_cache.clear()
+            HPSim._ctx_cache.update(keep)
+            exact_ok = bool(ss[0] == s1[0] and ss[1] == s1[1] and ss[5] == s1[5] and
+                            all(abs(ss[k] - s1[k]) <= 1e-9 * abs(s1[k]) for k in (2, 3, 4)))
+            check = {"short_range": {"range": list(short), "n_loss": [int(ss[0]), int(s1[0])], "n_lloss": [int(ss[1]), int(s1[1])],
+                                     "sum_w": [ss[2], s1[2]], "sum_phi": [ss[3], s1[3]], "sum_x2": [ss[4], s1[4]], "ok": exact_ok,
+                                     "gate": "counts equal, sums within 1e-9"}, "order": "[sharded, single GPU]", "ok": exact_ok}
+        dist.barrier()
+
     if cfg["pre"]:  # untimed lead-in; the timed range starts from the kept "intermediate" beam
         case.run(*cfg["pre"])
         case.beam.save_intermediate_beam()
@@ -366,52 +402,23 @@ def main():
             t = torch.tensor(chk_local, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             chk = t.numpy()
-    # ---- sharded result against a single-GPU run of the same beam (rank 0, its own context without a communicator).
-    # (1) EXACT on a short range (LEBT + the first DTL cells, 258 kicks: every exchange of the kick chain is exercised
-    #     hundreds of times and the dynamics have not yet amplified the summation-order difference): loss counts equal,
-    #     sums of w / phi / x^2 over the survivors to 1e-9.  (2) REPORTED on the timed range: through the whole linac the
-    #     space-charge dynamics are chaotic (two code versions differ by 2 % in the longitudinal-loss count), so the
-    #     counts of the timed step are compared loosely only.
-    check = None
-    if sharded and not args.no_check:
-        def sums(st):
-            a = st["loss"] == 0
-            return np.array([float((st["loss"] != 0).sum()), float((st["lloss"] != 0).sum()), float(st["w"][a].sum()),
-                             float(st["phi"][a].sum()), float((st["x"][a] ** 2).sum()), float(a.sum())])
-        short = ("TBDB02", "01QM10")
-        case.beam.restore_initial_beam()
-        case.run(*short)
-        ss = sums(case.state())
-        import torch
-        t = torch.tensor(ss, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ss = t.numpy()
-        if rank == 0:
-            HPSim._ctx_cache.clear()
-            one = H.Case(lib, n=n_beam, sc=True, remesh=cfg["remesh"])
-            one.run(*short)
-            s1 = sums(one.state())
-            exact_ok = bool(ss[0] == s1[0] and ss[1] == s1[1] and ss[5] == s1[5] and
-                            all(abs(ss[k] - s1[k]) <= 1e-9 * abs(s1[k]) for k in (2, 3, 4)))
-            # the timed range: two passes, like the timed steps the checked pass starts from a restored beam with the SCHEFF
-            # remesh memory and the stale loss count of the pass before it
-            if cfg["pre"]:
-                one.beam.restore_initial_beam()
-                one.run(*cfg["pre"])
-                one.beam.save_intermediate_beam()
-            for _ in range(2):
-                (one.beam.restore_intermediate_beam if cfg["pre"] else one.beam.restore_initial_beam)()
-                one.run(*cfg["rng"])
-            r1 = one.state()
-            c1 = [float((r1["loss"] != 0).sum()), float((r1["lloss"] != 0).sum()), float(r1["w"][r1["loss"] == 0].sum())]
-            loose_ok = bool(abs(chk[0] - c1[0]) <= 0.01 * n_beam and abs(chk[1] - c1[1]) <= 0.03 * n_beam and abs(chk[2] - c1[2]) <= 0.01 * abs(c1[2]))
-            check = {"short_range": {"range": list(short), "n_loss": [int(ss[0]), int(s1[0])], "n_lloss": [int(ss[1]), int(s1[1])],
-                                     "sum_w": [ss[2], s1[2]], "sum_phi": [ss[3], s1[3]], "sum_x2": [ss[4], s1[4]], "ok": exact_ok,
-                                     "gate": "counts equal, sums within 1e-9"},
-                     "timed_range": {"n_loss": [int(chk[0]), int(c1[0])], "n_lloss": [int(chk[1]), int(c1[1])], "sum_w_alive": [chk[2], c1[2]],
-                                     "ok": loose_ok, "gate": "chaotic range: counts within 1 % / 3 % of N, energy sum within 1 %"},
-                     "order": "[sharded, single GPU]", "ok": bool(exact_ok and loose_ok)}
-            del one, r1
+    # ---- the timed range, sharded vs single GPU (see the short-range check above for why this one is loose)
+    if check is not None and rank == 0:
+        HPSim._ctx_cache.clear()
+        one = H.Case(lib, n=n_beam, sc=True, remesh=cfg["remesh"])
+        if cfg["pre"]:
+            one.run(*cfg["pre"])
+            one.beam.save_intermediate_beam()
+        for _ in range(2):  # like a timed step, the checked pass starts from a restored beam after a pass (H4 / H21)
+            (one.beam.restore_intermediate_beam if cfg["pre"] else one.beam.restore_initial_beam)()
+            one.run(*cfg["rng"])
+        r1 = one.state()
+        c1 = [float((r1["loss"] != 0).sum()), float((r1["lloss"] != 0).sum()), float(r1["w"][r1["loss"] == 0].sum())]
+        loose_ok = bool(abs(chk[0] - c1[0]) <= 0.01 * n_beam and abs(chk[1] - c1[1]) <= 0.03 * n_beam and abs(chk[2] - c1[2]) <= 0.01 * abs(c1[2]))
+        check["timed_range"] = {"n_loss": [int(chk[0]), int(c1[0])], "n_lloss": [int(chk[1]), int(c1[1])], "sum_w_alive": [chk[2], c1[2]],
+                                "ok": loose_ok, "gate": "chaotic range: counts within 1 % / 3 % of N, energy sum within 1 %"}
+        check["ok"] = bool(check["short_range"]["ok"] and loose_ok)
+        del one, r1
     if dist is not None:
         dist.barrier()
     if rank != 0:
@@ -445,6 +452,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "result": {"n_loss": int(chk[0]), "n_lloss": int(chk[1]), "sum_w_alive": float(chk[2])},
+        "moment_chain": case.beam.moment_stats(),
         "roofline": {"bound": "hbm", "kernel": "k_segment", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic[0] if traffic else None,
                      "traffic_source": ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, cold L2 (%s)" % traffic[1]) if traffic else None,

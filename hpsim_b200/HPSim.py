@@ -408,10 +408,15 @@ class Beam:
 
     def moment_stats(self):
         """Diagnostics of the fused moment chain (hps_beam_moment_stats; no reference counterpart)."""
-        out = (C.c_uint64 * 3)()
+        out = (C.c_uint64 * 18)()
         err, m = C.c_double(), C.c_double()
         self._c.check(self._c.lib.hps_beam_moment_stats(self.h, out, C.byref(err), C.byref(m)))
-        return {"fused": int(out[0]), "fallback": int(out[1]), "deferred": int(out[2]), "pivot_err_max": err.value, "pivot_margin": m.value}
+        n = max(1, int(out[8]))
+        return {"fused": int(out[0]), "fallback": int(out[1]), "deferred": int(out[2]), "pivot_err_max": err.value, "pivot_margin": m.value,
+                "fallback_cause": {"list_overflow": int(out[9]), "marking_band": int(out[10]), "wrap_margin": int(out[11])},
+                "sweep_timeline_us": {"launches": int(out[8]), "sweep": out[3] / n / 1e3, "fold": out[4] / n / 1e3, "finalise": out[5] / n / 1e3,
+                                      "start_skew": out[6] / n / 1e3, "pilot": out[7] / n / 1e3,
+                                      "finalise_phases": [out[12 + k] / n / 1e3 for k in range(6)]}}
 
     def apply_cut(self, coord, lo, hi):
         m = {"x": K.X, "y": K.Y, "w": K.W, "p": K.PHI}

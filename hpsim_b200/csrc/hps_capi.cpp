@@ -64,6 +64,7 @@ struct hps_ctx {
   // cross-rank exchange state of a particle-sharded beam (hps_ctx_comm_init)
   XrView xr;
   XrBox* xr_box = nullptr;
+  double* xr_sync = nullptr;  // one device double: operand of the host-skew rendezvous (xr_rendezvous)
   void* xr_mapped[HPS_XR_MAXR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   int pdl = 1;       // HPSIM_PDL=0 turns programmatic dependent launch off
@@ -240,6 +241,17 @@ int xr_check(hps_ctx* c) {
   return fail(c, HPS_ERR_COMM, "a peer rank did not answer a cross-rank exchange within 2 s: the results since the last synchronisation are invalid");
 }
 
+// Sharded beam, P2P exchange: the in-kernel exchanges poll peer memory with a 2 s dead-peer limit, which must only ever
+// see DEVICE-side skew (microseconds).  Host-side skew -- one rank reaching an entry point seconds after the others
+// because its process was busy -- is taken out here: a one-double NCCL all-reduce enqueued on the context's stream at every
+// entry point that goes on to launch exchanging kernels.  It is stream-ordered, so no rank's first exchanging kernel
+// starts before every rank has arrived; NCCL itself waits for late peers without a limit.
+int xr_rendezvous(hps_ctx* c) {
+  if (c->xr.mode != XR_P2P || c->xr.nranks <= 1 || !c->xr_sync) return HPS_OK;
+  if (comm_allreduce_sum_f64(c->comm, c->xr_sync, 1, c->stream)) return fail(c, HPS_ERR_COMM, "rendezvous all-reduce failed");
+  return HPS_OK;
+}
+
 void carve(hps_beam* b, char* slab, double* c[6], u32** loss, u32** lloss) {
   const size_t da = align_up((size_t)b->n_alloc * sizeof(double), 256), ua = align_up((size_t)b->n_alloc * sizeof(u32), 256);
   for (int i = 0; i < 6; ++i) c[i] = reinterpret_cast<double*>(slab + i * da);
@@ -255,6 +267,7 @@ StatReq req(int kind, int a = 0, int bvar = -1, int good = 0, int out0 = 0) {
   return r;
 }
 void stat(hps_beam* b, const StatReq& r) {
+  if (xr_rendezvous(b->ctx) != HPS_OK) b->ctx->comm_failed = 1;
   const LaunchCfg l = cfg(b->ctx, b);
   const BeamView v = view(b);
   launch_stat(l, v, b->st, r);
@@ -331,6 +344,7 @@ void InitPhiAvgGood(hps_beam* b) {  // beam.cpp:655-661
 void UpdateStatForSpaceCharge(hps_beam* b) {
   if (!(b->h.n_global > 2)) return;
   hps_ctx* c = b->ctx;
+  if (xr_rendezvous(c) != HPS_OK) c->comm_failed = 1;
   LaunchCfg l = cfg(c, b);
   BeamView v = view(b);
   KickParams kp;
@@ -465,7 +479,7 @@ void hps_ctx_destroy(hps_ctx* c) {
   cudaSetDevice(c->device);
   for (void* p : c->xr_mapped) if (p) cudaIpcCloseMemHandle(p);
   if (c->xr.seq) cudaFree(c->xr.seq);
-  cudaFree(c->xr_box); cudaFree(c->xr.bins_gather);
+  cudaFree(c->xr_box); cudaFree(c->xr.bins_gather); cudaFree(c->xr_sync);
   comm_destroy(c->comm);
   cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_ops); cudaFree(c->d_opc); cudaFreeHost(c->h_ops);
   for (auto& g : c->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); cudaFree(g.d_ops); cudaFree(g.d_opc); }
@@ -549,6 +563,8 @@ int hps_ctx_comm_init(hps_ctx* c, int rank, int nranks, const void* id) {
   CK(c, cudaMalloc(&misc, misc_bytes));
   CK(c, cudaMemset(misc, 0, misc_bytes));
   CK(c, cudaMalloc(&x.bins_gather, (size_t)nranks * HPS_XR_BINS_CAP * sizeof(double)));
+  CK(c, cudaMalloc(&c->xr_sync, sizeof(double)));
+  CK(c, cudaMemset(c->xr_sync, 0, sizeof(double)));
   x.seq = reinterpret_cast<unsigned long long*>(misc);
   x.err = reinterpret_cast<u32*>(misc + 16);
   x.send = reinterpret_cast<double*>(misc + 32);
@@ -632,6 +648,7 @@ hps_beam* hps_beam_create(hps_ctx* c, uint64_t n_global, double mass, double cha
   b->slab_bytes = 6 * da + 2 * ua;
   bool ok = cudaMalloc(&b->slab, b->slab_bytes) == cudaSuccess && cudaMemsetAsync(b->slab, 0, b->slab_bytes, c->stream) == cudaSuccess &&
             cudaMalloc(&b->st, sizeof(DevStats)) == cudaSuccess && cudaMemsetAsync(b->st, 0, sizeof(DevStats), c->stream) == cudaSuccess &&
+            cudaMemsetAsync(reinterpret_cast<char*>(b->st) + offsetof(DevStats, diag_t0), 0xff, sizeof(unsigned long long), c->stream) == cudaSuccess &&
             cudaMalloc(&b->defer, sizeof(DeferList)) == cudaSuccess && cudaMemsetAsync(b->defer, 0, 8, c->stream) == cudaSuccess &&
             cudaMalloc(&b->tmp, (size_t)b->n_alloc * sizeof(double)) == cudaSuccess;
   if (!ok) {
@@ -929,13 +946,18 @@ int hps_monitor_download(hps_monitor* m, double* out, uint32_t* count) {
   return HPS_OK;
 }
 
-int hps_beam_moment_stats(hps_beam* b, uint64_t out[3], double* pivot_err_max, double* pivot_margin) {
+int hps_beam_moment_stats(hps_beam* b, uint64_t out[18], double* pivot_err_max, double* pivot_margin) {
   hps_ctx* c = b->ctx;
   cudaSetDevice(c->device);
   DevStats h;
   CK(c, cudaMemcpyAsync(&h, b->st, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  if (out) { out[0] = h.n_fused; out[1] = h.n_fallback; out[2] = h.n_deferred; }
+  if (out) {
+    out[0] = h.n_fused; out[1] = h.n_fallback; out[2] = h.n_deferred;
+    for (int k = 0; k < 6; ++k) out[3 + k] = h.diag_ns[k];
+    for (int k = 0; k < 3; ++k) out[9 + k] = h.n_fb[k];
+    for (int k = 0; k < 6; ++k) out[12 + k] = h.fin_ns[k];
+  }
   if (pivot_err_max) *pivot_err_max = h.pivot_err_max;
   if (pivot_margin) *pivot_margin = h.pivot_m;
   return HPS_OK;
@@ -1345,6 +1367,7 @@ int hps_simulate(hps_ctx* c, hps_beam* b, hps_lattice* lat, hps_scheff* sc, uint
   if (sc) { int e = 0; while (e < 32 && (1ull << e) < (unsigned long long)b->h.n_global) ++e; sc->bin_scale = (double)(1ull << (62 - e)); }
   const uint64_t launches0 = c->launches;
   uint64_t sweeps = 0, extra = 0;
+  { int rc = xr_rendezvous(c); if (rc) return rc; }
   CK(c, cudaEventRecord(c->ev0, c->stream));
   if (!sc || sc->mesh_w == 0.0) {
     int rc = run_range(c, b, lat, sc, first, last, &sweeps, &extra);

@@ -76,10 +76,19 @@ struct DevStats {
   // overflows, moments_fallback asks the stand-alone moment kernel (k_moments) to redo the kick's statistics.
   u32 moments_fallback;
   u32 pad0;
-  double pivot_m;            // margin in force [rad]; adapted from the prediction errors seen
+  double pivot_m;            // wrap margin in force [rad]; adapted from the prediction errors seen
+  double pivot_mc;           // marking-threshold margin in force [rad]
+  unsigned long long n_fb[3];  // fallbacks by cause: list overflow, marking threshold outside its band, wrap margin exceeded
   double pivot_err_max;      // largest |<phi>_good - pivot| of the fused kicks so far (diagnostics)
   unsigned long long n_fused, n_fallback, n_deferred;  // kicks finished in the epilogue / by k_moments; deferred particles
   double mon_ref_w;          // k_monitor: energy of the reference particle, handed from its owner to the other blocks / ranks
+  // timeline of the fused sweeps as the finalising block sees it (%globaltimer ns, summed over the launches; diagnostics):
+  // 0 first block's start -> last block's loop end, 1 -> partials folded, 2 -> finaliser done, 3 start skew of the
+  // finalising block, 4 pilot (block 0), 5 launches
+  unsigned long long diag_ns[6];
+  unsigned long long fin_ns[6];  // inside the finaliser: 0 pass 1 (+ block sum), 1 -> <phi>_good known (exchange 1), 2 pass 2 (marking, exchange 2),
+                                 // 3 pass 3 (+ exchange 3), 4 finalisers + Scheff policy, 5 mesh zeroing
+  unsigned long long diag_t0;  // earliest block start of the launch in flight (atomicMin; ~0 between launches)
 };
 
 // side list of the fused-moment epilogue: particles whose classification needs the true <phi>_good

@@ -219,7 +219,10 @@ enum { KF_CNTA = 0, KF_CNTB, KF_SPHI, KF_SU_ALIVE, KF_SU, KF_SU2, KF_SX, KF_SX2,
 enum { KT_NGOOD = 0, KT_NLLOSS, KT_NDEFER, KT_NALIVE_M, KT_NGOOD_M, KT_SPHI, KT_SU_ALIVE, KT_SU, KT_SU2, KT_SX, KT_SX2, KT_SY, KT_SY2,
        KT_SW, KT_R2MAX, KT_SPHI_FC };
 struct FusedCtx {
-  double pivot, m, cand_thr, amb_thr, xa, ya;
+  double pivot;
+  double m;         // margin of the 2 pi wrap of the relative phase: |<phi>_good after marking - pivot| must stay below it
+  double mc;        // margin of the marking threshold: |<phi>_good before marking - pivot| must stay below it
+  double cand_thr, amb_thr, xa, ya;
 };
 struct FusedAcc {  // sums of one loop iteration (registers)
   unsigned long long ca, cb;
@@ -321,10 +324,17 @@ __device__ __noinline__ double pilot_phase(const Op* ops, const OpC* opcs, int n
         if (ccl) tw = t_fac - K_TWOPI * tp_fac * (c[GC_BETA_IN] * ib1 - 1.0) * c[GF_BETAG_OVER_BIN];
         double phi1 = phi + q[G_PHSHIFT];
         if (ccl) phi1 += c[GC_PH_CONST] - c[GF_DG_OVER_WL] * ib1;
+        // (a pivot needs 1e-4 rad, not 1e-16: the phase is reduced in fp64 and its sine / cosine come from the SFU)
+        auto fast_sincos = [](double a, double& sn, double& cs) {
+          const double r = a - K_TWOPI * rint(a * (1.0 / K_TWOPI));
+          float fs, fc;
+          __sincosf((float)r, &fs, &fc);
+          sn = (double)fs; cs = (double)fc;
+        };
         double sinp1, cosp1;
-        sincos(phi1, &sinp1, &cosp1);
+        fast_sincos(phi1, sinp1, cosp1);
         const double prome1 = -c[GC_CON1] * (tp_fac * (sinp1 - c[GC_SINPS]) + sp_fac * (cosp1 - c[GC_COSPS]));
-        sincos(phi1 + prome1, &sinp1, &cosp1);
+        fast_sincos(phi1 + prome1, sinp1, cosp1);
         w += c[GC_AQ_EFL] * tw * cosp1;
         const double ib = inv_beta_of(w, inv_mass);
         const double prome = -2.0 * c[GC_CON1] * tp_fac * (sinp1 - c[GC_SINPS]);
@@ -393,7 +403,11 @@ __device__ void finalize_moments(const double* t, double ref, u32 n_global, DevS
 // Last block of a FIN_KICK_FUSED sweep; every thread of the block calls it with this rank's totals in t[0..16) (shared,
 // KT_* layout).  Ends with DevStats / ScDev exactly as Beam::UpdateStatForSpaceCharge + Scheff::Start's policy leave them,
 // or with st->moments_fallback != 0 (1: redo the whole chain, 2: longitudinal losses are marked, redo the moment sums only).
-__device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const BeamView& b, DevStats* st, ScDev* sc, double* bins,
+// This block is the serial tail of every kick, so it avoids L2 round trips: DevStats and ScDev are copied to shared
+// memory up front, every scalar step works on the copies and they are written back at the end.  (Keeping a thread's
+// side-list entries in registers across the three passes was tried: no gain -- the tail runs once per launch from a cold
+// instruction cache, so its code size matters more than its loads.)
+__device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const BeamView& b, DevStats* st_g, ScDev* sc_g, double* bins,
                                     const KickParams& kp, DeferList* dl, const XrView& xr, int fin_mode) {
   constexpr int NI = 20;
   __shared__ long long s_warp[(HPS_BLOCK / 32) * NI];
@@ -402,27 +416,44 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
   __shared__ double s_x[HPS_XR_NS];   // rounds 2 and 3
   __shared__ double s_R1, s_R2, s_SG0, s_nG1, s_nnew;
   __shared__ u32 s_code, s_Kall, s_ncand;
+  __shared__ DevStats s_st;
+  __shared__ ScDev s_sc;
+  DevStats* const st = &s_st;
+  ScDev* const sc = &s_sc;
   const bool p2p = xr.mode == XR_P2P;
   const double P = f.pivot;
+  unsigned long long tq = threadIdx.x == 0 ? global_ns() : 0ull;
+#define FIN_STAMP(k) if (threadIdx.x == 0) { const unsigned long long tn = global_ns(); st->fin_ns[k] += tn - tq; tq = tn; }
   const u32 cnt = __ldcg(&dl->count);
+  {  // shared copies of the two state structs (8-byte words; one L2 round trip, overlapped with pass 1's loads)
+    const int nw_st = (int)(sizeof(DevStats) / 8), nw_sc = (int)(sizeof(ScDev) / 8);
+    const unsigned long long* gs = reinterpret_cast<const unsigned long long*>(st_g);
+    const unsigned long long* gc = reinterpret_cast<const unsigned long long*>(sc_g);
+    unsigned long long* ls = reinterpret_cast<unsigned long long*>(&s_st);
+    unsigned long long* lc = reinterpret_cast<unsigned long long*>(&s_sc);
+    for (int k = threadIdx.x; k < nw_st + nw_sc; k += blockDim.x) {
+      if (k < nw_st) ls[k] = __ldcg(gs + k); else lc[k - nw_st] = __ldcg(gc + (k - nw_st));
+    }
+  }
   const u32 K = min(cnt, HPS_DEFER_CAP);
   // ---- pass 1: the deferred members of the good set, the candidates
   {
     long long v[5] = {0, 0, 0, 0, (threadIdx.x == 0 && cnt > HPS_DEFER_CAP) ? 1 : 0};  // n good, sum (phi - P) hi lo, candidates, bad
-    for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
-      const DeferEntry& e = dl->e[k];
-      const u32 fl = (u32)(__ldcg(&e.tag) >> 32);
-      const double d = __ldcg(&e.phi) - P;
+    auto one = [&](u32 fl, double phi) {
+      const double d = phi - P;
       if ((fl & 3u) == 1u) {
         v[0] += 1;
         if (!(fabs(d) < 4096.0)) v[4] += 1; else fix_add(v[1], v[2], d * PS_DPHI);
       }
       if (fl & 4u) v[3] += 1;
-    }
+    };
+#pragma unroll 1
+    for (u32 k = threadIdx.x; k < K; k += blockDim.x) one((u32)(__ldcg(&dl->e[k].tag) >> 32), __ldcg(&dl->e[k].phi));
     if (cnt != 0u) block_sum_i64<5>(v, s_warp, s_i);  // (block-uniform condition)
     else if (threadIdx.x < 5) s_i[threadIdx.x] = 0;
   }
   __syncthreads();
+  FIN_STAMP(0)
   if (threadIdx.x < 16) s_g[threadIdx.x] = t[threadIdx.x];
   if (threadIdx.x == 0) {
     s_g[16] = (double)s_i[0]; s_g[17] = __longlong_as_double(s_i[1]); s_g[18] = __longlong_as_double(s_i[2]);
@@ -437,24 +468,28 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
     const double sg0 = s_g[KT_SPHI] + nl * P + fix_value(__double_as_longlong(s_g[17]), __double_as_longlong(s_g[18])) * (1.0 / PS_DPHI);
     const double r1 = n_g0 > 0.0 ? sg0 / n_g0 : -99999.0;
     u32 code = 0u;
-    if (s_g[20] != 0.0 || !(n_g0 > 0.0) || !(fabs(r1 - P) <= f.m) || n_g0 != s_g[KT_NGOOD_M] + nl) code = 1u;
+    if (s_g[20] != 0.0 || n_g0 != s_g[KT_NGOOD_M] + nl) { code = 1u; st->n_fb[0]++; }   // list overflow / out-of-range entry
+    // the candidates are the particles ABOVE pivot + 3 pi - mc: they include everything above the marking threshold
+    // <phi>_good + 3 pi as long as <phi>_good has not come out BELOW pivot - mc
+    else if (!(n_g0 > 0.0) || !(r1 - P >= -f.mc)) { code = 1u; st->n_fb[1]++; }
     s_R1 = r1; s_R2 = r1; s_SG0 = sg0; s_nG1 = n_g0; s_nnew = 0.0; s_code = code; s_Kall = (u32)s_g[21]; s_ncand = (u32)s_g[19];
   }
   __syncthreads();
+  FIN_STAMP(1)
   if (s_code == 0u && s_ncand != 0u) {
     // ---- pass 2: Beam::UpdateLongitudinalLoss (beam_kernel.cu:1549-1559) on the candidates
     const double thr = s_R1 + K_TWOPI + K_PI;
     long long v[4] = {0, 0, 0, 0};  // newly non-zero lloss, marked members of the good set, their sum (phi - P) hi lo
+#pragma unroll 1
     for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
-      DeferEntry& e = dl->e[k];
-      const unsigned long long tag = __ldcg(&e.tag);
+      const unsigned long long tag = __ldcg(&dl->e[k].tag);
       const u32 fl = (u32)(tag >> 32);
-      const double phi = __ldcg(&e.phi);
+      const double phi = __ldcg(&dl->e[k].phi);
       if ((fl & 4u) && phi > thr) {
         b.lloss[(u32)tag] = 1u;
         if (!(fl & 2u)) v[0] += 1;
         if ((fl & 3u) == 1u) { v[1] += 1; fix_add(v[2], v[3], (phi - P) * PS_DPHI); }
-        e.tag = tag | (2ull << 32);
+        dl->e[k].tag = tag | (2ull << 32);
       }
     }
     if (K != 0u) block_sum_i64<4>(v, s_warp, s_i);
@@ -475,8 +510,9 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
     }
     __syncthreads();
   }
+  FIN_STAMP(2)
   const double R2 = s_R2, delta = R2 - P;
-  if (threadIdx.x == 0 && s_code == 0u && !(fabs(delta) <= f.m)) s_code = 2u;  // (marks are written: only the sums are redone)
+  if (threadIdx.x == 0 && s_code == 0u && !(fabs(delta) <= f.m)) { s_code = 2u; st->n_fb[2]++; }  // (marks are written: only the sums are redone)
   __syncthreads();
   // ---- pass 3: the deferred particles' relative phases about the true <phi>_good, summed in fixed point
   // v: 0 n alive, 1 n good, 2 bad, 3-4 sum pr alive, 5-6 sum pr, 7-8 pr^2, 9-10 x, 11-12 x^2, 13-14 y, 15-16 y^2, 17-18 w
@@ -484,19 +520,21 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
     long long v[NI];
 #pragma unroll
     for (int k = 0; k < NI; ++k) v[k] = 0;
-    for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
-      const DeferEntry& e = dl->e[k];
-      const u32 fl = (u32)(__ldcg(&e.tag) >> 32);
-      if (!(fl & 1u)) continue;
-      const double pr = rel_phi(__ldcg(&e.phi), R2);
+    auto one = [&](u32 fl, double phi, double x, double y, double w) {
+      if (!(fl & 1u)) return;
+      const double pr = rel_phi(phi, R2);
       v[0] += 1; fix_add(v[3], v[4], pr);
-      if (fl & 2u) continue;
-      const double x = __ldcg(&e.x), y = __ldcg(&e.y), w = __ldcg(&e.w);
-      if (!(fabs(x) < 2.0 && fabs(y) < 2.0 && fabs(w) < 1024.0)) { v[2] += 1; continue; }
+      if (fl & 2u) return;
+      if (!(fabs(x) < 2.0 && fabs(y) < 2.0 && fabs(w) < 1024.0)) { v[2] += 1; return; }
       v[1] += 1;
       fix_add(v[5], v[6], pr); fix_add(v[7], v[8], pr * pr * PS_PR2);
       fix_add(v[9], v[10], x); fix_add(v[11], v[12], x * x); fix_add(v[13], v[14], y); fix_add(v[15], v[16], y * y);
       fix_add(v[17], v[18], w * PS_W);
+    };
+#pragma unroll 1
+    for (u32 k = threadIdx.x; k < K; k += blockDim.x) {
+      const DeferEntry& e = dl->e[k];
+      one((u32)(__ldcg(&e.tag) >> 32), __ldcg(&e.phi), __ldcg(&e.x), __ldcg(&e.y), __ldcg(&e.w));
     }
     if (K != 0u) block_sum_i64<NI>(v, s_warp, s_i);
     else if (threadIdx.x < NI) s_i[threadIdx.x] = 0;
@@ -508,6 +546,7 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
     if (threadIdx.x < NI) s_x[threadIdx.x] = 0.0;  // bit pattern of the integer 0
     __syncthreads();
   }
+  FIN_STAMP(3)
   if (threadIdx.x == 0) {
     auto I = [&](int k) { return __double_as_longlong(s_x[k]); };
     auto F = [&](int k) { return fix_value(I(k), I(k + 1)); };
@@ -520,7 +559,9 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
     }
     st->need_lloss_pass = 0u;
     st->moments_fallback = code;
-    const double err = fmax(fabs(s_R1 - P), fabs(delta));
+    const double err = fabs(delta), err1 = fabs(s_R1 - P);
+    // the margins follow the prediction errors: generous against the last miss, decaying slowly
+    st->pivot_mc = (err1 == err1) ? fmin(0.5, fmax(fmax(1.0e-3, 0.5 * f.mc), 4.0 * err1)) : 0.1;
     if (code == 0u) {
       const double nm = s_g[KT_NGOOD_M], na = s_g[KT_NALIVE_M];
       double m9[9];
@@ -536,21 +577,41 @@ __device__ void fused_kick_finalize(const double* t, const FusedCtx& f, const Be
       finalize_moments(m9, R2, b.n_global, st, sc, kp, 1);
       st->n_fused++;
       st->n_deferred += (unsigned long long)s_Kall;
-      st->pivot_err_max = fmax(st->pivot_err_max, err);
-      // the margin follows the prediction error: generous against the last miss, decaying slowly
-      st->pivot_m = fmin(0.25, fmax(fmax(1.0e-4, 0.5 * f.m), 16.0 * err));
+      st->pivot_err_max = fmax(st->pivot_err_max, fmax(err, err1));
+      // (a miss is usually a burst of markings that moved <phi>_good in one kick: it says little about the next kick,
+      //  and a wide margin defers a share 2 m / 2 pi of all out-of-bucket particles -- so: small factor, fast decay)
+      // (floor 1e-3 rad: the prediction error of a quiet kick is 1e-5 .. 1e-3, and a wrap band of +-1e-3 rad defers only
+      //  3e-4 of the out-of-bucket particles -- with a floor of 1e-4, 15-20 % of the DTL kicks missed the margin)
+      st->pivot_m = fmin(0.25, fmax(fmax(1.0e-3, 0.25 * f.m), 4.0 * err));
     } else {
+      // (the wrap margin is left alone: a miss is a burst of markings that moved <phi>_good within ONE kick -- measured:
+      //  growing the margin after it defers so many particles on the next kicks that the side list overflows)
       st->n_fallback++;
-      st->pivot_m = (err == err) ? fmin(0.25, fmax(2.0 * f.m, 4.0 * err)) : 0.05;
+      if (!(err == err)) st->pivot_m = 0.05;
     }
     dl->count = 0u;
     s_code = code;
   }
   __syncthreads();
+  FIN_STAMP(4)
   if (s_code == 0u && sc->remesh) {  // ResetBinTbl (space_charge.cu:92-105)
     const u32 nb = kp.nr * kp.nz;
     for (u32 k = threadIdx.x; k < nb; k += blockDim.x) bins[k] = 0.0;
   }
+  FIN_STAMP(5)
+#undef FIN_STAMP
+  __syncthreads();
+  {  // write the state back (diag_ns / diag_t0 are updated by the caller on the global copy right after)
+    const int nw_st = (int)(sizeof(DevStats) / 8), nw_sc = (int)(sizeof(ScDev) / 8);
+    unsigned long long* gs = reinterpret_cast<unsigned long long*>(st_g);
+    unsigned long long* gc = reinterpret_cast<unsigned long long*>(sc_g);
+    const unsigned long long* ls = reinterpret_cast<const unsigned long long*>(&s_st);
+    const unsigned long long* lc = reinterpret_cast<const unsigned long long*>(&s_sc);
+    for (int k = threadIdx.x; k < nw_st + nw_sc; k += blockDim.x) {
+      if (k < nw_st) gs[k] = ls[k]; else gc[k - nw_st] = lc[k - nw_st];
+    }
+  }
+  __syncthreads();
 }
 
 // ---- per-thread asynchronous staging of the NEXT particle pair ------------------------------------------------------
@@ -630,6 +691,12 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
   pdl_launch_dependents();
   pdl_wait();  // the op constants (k_prepare_ops) and everything below come from preceding kernels
   const bool fused = (fin_mode & 3) == FIN_KICK_FUSED;
+  // the first particle pair starts its way from HBM now: its latency hides behind the prologue (op staging, kick
+  // factors, pilot particle)
+  if (PPT == 2 && stage) {
+    const u32 first = blockIdx.x * blockDim.x + threadIdx.x;
+    if (first < ((b.n + 1) >> 1)) stage_issue(reinterpret_cast<PairStage*>(s_acc + SEG_ACC * HPS_BLOCK), b, first);
+  }
   {  // stage the segment's op records (block-uniform) in shared memory
     const int nw = nops * (int)(sizeof(Op) / sizeof(double));
     const double* src = reinterpret_cast<const double*>(ops);
@@ -666,17 +733,22 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       if (ops[k].type == OP_SC_KICK) { kick_prepare(s_k, ops[k].p, b.mass, b.n_global); break; }
   }
   __syncthreads();
+  unsigned long long t_start = 0ull;
   if (fused) {
     if (threadIdx.x == 0) {
+      t_start = global_ns();
+      atomicMin(&st->diag_t0, t_start);
       FusedCtx f;
       f.pivot = pilot_phase(s_ops, s_opc, nops, st->v[HPS_STAT_PHI_AVG_GOOD], st->v[HPS_STAT_W_AVG_GOOD], b.mass, b.charge);
-      double m = st->pivot_m;
+      double m = st->pivot_m, mc = st->pivot_mc;
       if (!(m >= 1.0e-4 && m <= 0.25)) m = 0.05;
-      f.m = m;
-      f.cand_thr = K_TWOPI + K_PI - m;
+      if (!(mc >= 1.0e-4 && mc <= 0.5)) mc = 0.1;
+      f.m = m; f.mc = mc;
+      f.cand_thr = K_TWOPI + K_PI - mc;
       f.amb_thr = K_PI - m;
       f.xa = s_cxy[0]; f.ya = s_cxy[1];
       s_f = f;
+      if (blockIdx.x == 0) st->diag_ns[4] += global_ns() - t_start;
     }
     __syncthreads();
   }
@@ -688,7 +760,6 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
     PairStage* stg = reinterpret_cast<PairStage*>(s_acc + SEG_ACC * HPS_BLOCK);
     const u32 stride = gridDim.x * blockDim.x;
     const u32 first = blockIdx.x * blockDim.x + threadIdx.x;
-    if (stage && first < npairs) stage_issue(stg, b, first);
     for (u32 i2 = first; i2 < npairs; i2 += stride) {
       double2 X, XP, Y, YP, PH, W;
       uint2 L, LL;
@@ -719,13 +790,51 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       const u32 g[2] = {g0, g0 + b.gstride};
       double fc[2] = {0.0, 0.0};
       bool lf[2] = {false, false};
+      // epilogue sums of this iteration (registers; see acc_flush)
+      FusedAcc fa;
+      fa.ca = 0ull; fa.cb = 0ull;
+#pragma unroll
+      for (int s = 0; s < KF_NACC; ++s) fa.s[s] = 0.0;
+      double la[SEGL_NS] = {0.0, 0.0, -DBL_MAX, 0.0, 0.0, 0.0, 0.0, 0.0};
+#ifndef HPS_SEQ_PARTICLE_MAJOR
+#define HPS_SEQ_PARTICLE_MAJOR 0
+#endif
+      if (SEQ != SEQ_ANY && !HPS_SEQ_PARTICLE_MAJOR) {
+        // Pattern sweep: the op sequence is compiled in, both particles of the pair go through each map back to back so
+        // that their independent fp64 chains overlap.
+#define AP2(TYPE, CCLF, K) apply_op<FULL, 2, MATH, TYPE, CCLF>(p, ll, g, valid, s_ops[K], s_opc[K], s_k, s_cxy, field, b, compat, fc, lf, inv_mass)
+        AP2((SEQ & 31), ((SEQ >> 5) & 3) - 1, 0);
+        if ((SEQ >> 8) & 31) AP2(((SEQ >> 8) & 31), ((SEQ >> 13) & 3) - 1, 1);
+        if ((SEQ >> 16) & 31) AP2(((SEQ >> 16) & 31), ((SEQ >> 21) & 3) - 1, 2);
+#undef AP2
+      } else if (SEQ != SEQ_ANY) {
+        // Particle-major form (build experiment, -DHPS_SEQ_PARTICLE_MAJOR=1): ONE copy of the op sequence in the
+        // instruction stream, run for the first and then for the second particle of the pair.  Measured on C4 (16 Mi
+        // particles): 871 vs 669 us per sweep -- the halved instruction footprint does not pay for the lost overlap of
+        // the two particles' dependent fp64 chains at 16 warps per SM.
+#pragma unroll 1
+        for (int rep = 0; rep < 2; ++rep) {
+          if (rep == 1 && !valid[1]) break;
+          Pt q[1] = {rep ? p[1] : p[0]};
+          const u32 ql[1] = {rep ? ll[1] : ll[0]};
+          const u32 qg[1] = {rep ? g[1] : g[0]};
+          const bool qv[1] = {true};
+          double qfc[1] = {0.0};
+          bool qlf[1] = {false};
+#define AP1(TYPE, CCLF, K) apply_op<FULL, 1, MATH, TYPE, CCLF>(q, ql, qg, qv, s_ops[K], s_opc[K], s_k, s_cxy, field, b, compat, qfc, qlf, inv_mass)
+          AP1((SEQ & 31), ((SEQ >> 5) & 3) - 1, 0);
+          if ((SEQ >> 8) & 31) AP1(((SEQ >> 8) & 31), ((SEQ >> 13) & 3) - 1, 1);
+          if ((SEQ >> 16) & 31) AP1(((SEQ >> 16) & 31), ((SEQ >> 21) & 3) - 1, 2);
+#undef AP1
+          if (fused) seg_accumulate_fused(fa, q[0], ql[0], qfc[0], qlf[0], s_f, dl, 2 * i2 + rep);
+          else if (fin_mode != FIN_NONE) seg_accumulate(la, q[0], ql[0], qfc[0], qlf[0]);
+          if (rep) p[1] = q[0]; else p[0] = q[0];
+        }
+      } else {
 #define AP(TYPE, CCLF, K) apply_op<FULL, 2, MATH, TYPE, CCLF>(p, ll, g, valid, s_ops[K], s_opc[K], s_k, s_cxy, field, b, compat, fc, lf, inv_mass)
-      if (SEQ != SEQ_ANY) {
-        AP((SEQ & 31), ((SEQ >> 5) & 3) - 1, 0);
-        if ((SEQ >> 8) & 31) AP(((SEQ >> 8) & 31), ((SEQ >> 13) & 3) - 1, 1);
-        if ((SEQ >> 16) & 31) AP(((SEQ >> 16) & 31), ((SEQ >> 21) & 3) - 1, 2);
-      } else for (int k = 0; k < nops; ++k) AP(-1, -1, k);
+        for (int k = 0; k < nops; ++k) AP(-1, -1, k);
 #undef AP
+      }
       if (nops > 0) {
         if (dirty & 1) reinterpret_cast<double2*>(b.x)[i2] = make_double2(p[0].x, p[1].x);
         if (dirty & 2) reinterpret_cast<double2*>(b.xp)[i2] = make_double2(p[0].xp, p[1].xp);
@@ -736,20 +845,18 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
         if ((dirty & 64) && (p[0].loss != L.x || p[1].loss != L.y))
           reinterpret_cast<uint2*>(b.loss)[i2] = make_uint2(p[0].loss, p[1].loss);
       }
-      if (fused) {
-        FusedAcc c;
-        c.ca = 0ull; c.cb = 0ull;
-#pragma unroll
-        for (int s = 0; s < KF_NACC; ++s) c.s[s] = 0.0;
-        seg_accumulate_fused(c, p[0], ll[0], fc[0], lf[0], s_f, dl, 2 * i2);
-        if (valid[1]) seg_accumulate_fused(c, p[1], ll[1], fc[1], lf[1], s_f, dl, 2 * i2 + 1);
-        fused_flush(col, c, (fin_mode & FIN_FREQ) != 0);
-      } else if (fin_mode != FIN_NONE) {
-        double c[SEGL_NS] = {0.0, 0.0, -DBL_MAX, 0.0, 0.0, 0.0, 0.0, 0.0};
-        seg_accumulate(c, p[0], ll[0], fc[0], lf[0]);
-        if (valid[1]) seg_accumulate(c, p[1], ll[1], fc[1], lf[1]);
-        acc_flush<SEGL_NS>(col, c, 1u << 2);
+      // the epilogue's sums of this pair: after the stores have been issued (the maps' temporaries are dead by now)
+      if (!(SEQ != SEQ_ANY && HPS_SEQ_PARTICLE_MAJOR)) {
+        if (fused) {
+          seg_accumulate_fused(fa, p[0], ll[0], fc[0], lf[0], s_f, dl, 2 * i2);
+          if (valid[1]) seg_accumulate_fused(fa, p[1], ll[1], fc[1], lf[1], s_f, dl, 2 * i2 + 1);
+        } else if (fin_mode != FIN_NONE) {
+          seg_accumulate(la, p[0], ll[0], fc[0], lf[0]);
+          if (valid[1]) seg_accumulate(la, p[1], ll[1], fc[1], lf[1]);
+        }
       }
+      if (fused) fused_flush(col, fa, (fin_mode & FIN_FREQ) != 0);
+      else if (fin_mode != FIN_NONE) acc_flush<SEGL_NS>(col, la, 1u << 2);
     }
   } else {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x) {
@@ -787,9 +894,17 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
   if (fin_mode == FIN_NONE) return;
   double v[SEG_NS];
   if (fused) {
+    const unsigned long long t_loop = threadIdx.x == 0 ? global_ns() : 0ull;
     fused_unpack(col, v);
     if (grid_reduce<SEG_NS>(v, 1u << KT_R2MAX, partials, ticket, s_total, s_scratch, xr, false)) {
+      const unsigned long long t_red = threadIdx.x == 0 ? global_ns() : 0ull;
       fused_kick_finalize(s_total, s_f, b, st, sc, bins, kp, dl, xr, fin_mode);
+      if (threadIdx.x == 0) {
+        const unsigned long long t_fin = global_ns(), t0 = __ldcg(&st->diag_t0);
+        st->diag_ns[0] += t_loop - t0; st->diag_ns[1] += t_red - t_loop; st->diag_ns[2] += t_fin - t_red;
+        st->diag_ns[3] += t_start - t0; st->diag_ns[5] += 1ull;
+        st->diag_t0 = ~0ull;
+      }
     }
     return;
   }

@@ -175,15 +175,18 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], unsigned max_mask, 
     partials[(size_t)blockIdx.x * NS + s] = a;
   }
   __shared__ u32 s_last;
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    // one fence by the thread that takes the ticket: fences are cumulative, so the partials the other threads wrote
+    // before the barrier are ordered before the ticket too (256 fences per block each waited for the thread's own
+    // streaming stores to drain)
+    __threadfence();
     u32 t = atomicAdd(ticket, 1u);
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    __threadfence();
   }
   __syncthreads();
   if (!s_last) return false;
-  __threadfence();
   // last block: thread t folds slot (t % NSP) of the blocks g, g+G, g+2G, ... (g = t / NSP; the loads of
   // one thread are independent, so they overlap); the G group sums are then folded in group order.
   // Every order is fixed, so the result is bit-reproducible for a given grid.

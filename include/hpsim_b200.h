@@ -310,8 +310,13 @@ int hps_monitor_download(hps_monitor*, double* out, uint32_t* count);
  * (src/beam/src/beam.cpp:1003-1016) re-reads the particles for every link of its chain; here the sweep in front of a
  * kick sums the moments about a predicted <phi>_good and re-centres exactly.  out[0] kicks finished that way, out[1]
  * kicks handed back to the stand-alone moment kernel, out[2] particles that had to be resolved one by one with the
- * true <phi>_good; *pivot_err_max: largest |<phi>_good - prediction| [rad]; *pivot_margin: margin in force [rad]. */
-int hps_beam_moment_stats(hps_beam*, uint64_t out[3], double* pivot_err_max, double* pivot_margin);
+ * true <phi>_good; out[3..7]: timeline of those sweeps as their finalising block sees it, %globaltimer ns summed over
+ * out[8] launches -- 3 first block's start -> own loop end, 4 -> block partials folded, 5 -> finaliser done (moments,
+ * exchanges of a sharded beam, Scheff policy), 6 start skew of that block, 7 pilot particle of block 0; out[9..11]:
+ * hand-backs by cause (side list overflowed, marking threshold left its band, wrap margin exceeded); out[12..17]: the
+ * finaliser's own phases in ns (side-list pass 1, <phi>_good, marking pass, relative-phase pass, finalisers + policy, mesh zeroing);
+ * *pivot_err_max: largest |<phi>_good - prediction| [rad]; *pivot_margin: wrap margin in force [rad]. */
+int hps_beam_moment_stats(hps_beam*, uint64_t out[18], double* pivot_err_max, double* pivot_margin);
 
 /* ---- simulate ------------------------------------------------------------ */
 typedef struct hps_run_stats {

@@ -1552,8 +1552,8 @@ int hps_monitor_download(hps_monitor* m, double* out, uint32_t* count) {
   if (count) *count = m->monitor_num;
   return HPS_OK;
 }
-int hps_beam_moment_stats(hps_beam*, uint64_t out[3], double* e, double* m) {  // the oracle runs the reference's chain as it is
-  if (out) { out[0] = out[1] = out[2] = 0; }
+int hps_beam_moment_stats(hps_beam*, uint64_t out[18], double* e, double* m) {  // the oracle runs the reference's chain as it is
+  if (out) for (int k = 0; k < 18; ++k) out[k] = 0;
   if (e) *e = 0.0;
   if (m) *m = 0.0;
   return HPS_OK;

@@ -254,17 +254,22 @@ def test_reference_order_maps_bit_identical_per_op():
 @pytest.mark.parametrize("sc", [False, True])
 def test_reference_modes_agree(sc):
     """HPS_MATH_REFERENCE (default: branch-free exact arithmetic) against HPS_MATH_REFERENCE_NVCC (nvcc's `/` and
-    sqrt) on whole runs, 64 Ki particles: bit-identical through the LEBT (drifts, quadrupoles, bunchers, 236
-    space-charge kicks); equal loss flags and rounding-level agreement at the end of the DTL."""
+    sqrt) on whole runs, 64 Ki particles: bit-identical through the LEBT without space charge (drifts, quadrupoles,
+    bunchers), 1e-11 with its 236 kicks; equal loss flags and rounding-level agreement at the end of the DTL."""
     out = {}
     for last in ("spch_comp_7", "04QM30"):
         for mode in ("reference", "reference_nvcc"):
             with H.math_mode(mode):
                 _, out[mode], _ = run(H.cuda_lib(), 65536, "TBDB02", last, sc)
         a, b = out["reference"], out["reference_nvcc"]
-        if last == "spch_comp_7":
+        if last == "spch_comp_7" and not sc:
             for k in a:
                 assert np.array_equal(a[k], b[k]), k
+        elif last == "spch_comp_7":
+            # with space charge the default mode runs the pattern sweeps (op sequence compiled in), the nvcc mode the generic
+            # sweep: nvcc contracts the kick's interpolation differently in the two, a 1-ulp seed per kick
+            rep = H.compare(a, b, 1e-9)
+            assert rep["loss_equal"] and rep["lloss_equal"] and rep["worst"] < 1e-11, rep
         else:
             rep = H.compare(a, b, 1e-9)
             assert rep["loss_equal"] and rep["lloss_equal"], rep
