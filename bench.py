@@ -61,6 +61,11 @@ _t = os.path.join(ROOT, "profiles", "r2_seg_traffic.json")
 if os.path.exists(_t):
     for _k, _v in json.load(open(_t)).items():
         SEG_TRAFFIC[int(_k)] = (_v["bytes"], _v["source"])
+# what bounds the sweep when it is not HBM (ncu --set full of the dominant pattern sweep: fp64 pipe / issue-slot utilisation)
+SEG_COMPUTE = None
+_t = os.path.join(ROOT, "profiles", "r2_seg_compute.json")
+if os.path.exists(_t):
+    SEG_COMPUTE = json.load(open(_t))
 # particle count of the reference arm.  Measured on B200 (profiles/r2_reference_sweep.txt), TBDB02->48DT, double tables:
 # 64 Ki particles 5.1 s per pass (8.3e7 steps/s), 256 Ki 11.7 s (1.45e8 steps/s): the reference is launch-bound below and
 # atomics-bound above; 25 passes (--steps 20 --warmup 5) at 256 Ki take ~5 min, 1 Mi would take ~15
@@ -466,6 +471,8 @@ def main():
                      "by_kernel_us_per_launch": {k: 1e3 * v["ms"] / v["launches"] for k, v in prof.items() if v["launches"]},
                      "profiled_step_ms": run["device_ms"]},
     }
+    if SEG_COMPUTE:  # the sweep is bound by fp64 instruction issue, not by HBM: the measured pipe utilisation says how close it is
+        line["roofline"]["compute_bound_evidence"] = SEG_COMPUTE
     if sharded:
         cs = (C.c_uint64 * 4)()
         lib.hps_ctx_comm_stats(ctx.h, cs)

@@ -644,6 +644,26 @@ __device__ __forceinline__ void stage_issue(PairStage* s, const BeamView& b, u32
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// the same for the one-particle-per-thread sweeps (8- and 4-byte copies; the slots live in the PairStage area)
+struct OneStage {
+  double d[6][HPS_BLOCK];  // x xp y yp phi w
+  u32 f[2][HPS_BLOCK];     // loss lloss
+};
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((u32)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void stage_issue1(OneStage* s, const BeamView& b, u32 i) {
+  const int t = threadIdx.x;
+  cp_async8(&s->d[0][t], b.x + i);
+  cp_async8(&s->d[1][t], b.xp + i);
+  cp_async8(&s->d[2][t], b.y + i);
+  cp_async8(&s->d[3][t], b.yp + i);
+  cp_async8(&s->d[4][t], b.phi + i);
+  cp_async8(&s->d[5][t], b.w + i);
+  cp_async4(&s->f[0][t], b.loss + i);
+  cp_async4(&s->f[1][t], b.lloss + i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 // PPT = particles per thread.  PPT == 2 moves two adjacent particles with one 128-bit access per
 // array; PPT == 1 halves the register footprint and doubles the resident warps (the maps are chains of
@@ -693,9 +713,10 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
   const bool fused = (fin_mode & 3) == FIN_KICK_FUSED;
   // the first particle pair starts its way from HBM now: its latency hides behind the prologue (op staging, kick
   // factors, pilot particle)
-  if (PPT == 2 && stage) {
+  if (stage) {
     const u32 first = blockIdx.x * blockDim.x + threadIdx.x;
-    if (first < ((b.n + 1) >> 1)) stage_issue(reinterpret_cast<PairStage*>(s_acc + SEG_ACC * HPS_BLOCK), b, first);
+    if (PPT == 2) { if (first < ((b.n + 1) >> 1)) stage_issue(reinterpret_cast<PairStage*>(s_acc + SEG_ACC * HPS_BLOCK), b, first); }
+    else if (SEQ != SEQ_ANY) { if (first < b.n) stage_issue1(reinterpret_cast<OneStage*>(s_acc + SEG_ACC * HPS_BLOCK), b, first); }
   }
   {  // stage the segment's op records (block-uniform) in shared memory
     const int nw = nops * (int)(sizeof(Op) / sizeof(double));
@@ -859,14 +880,41 @@ k_segment(BeamView b, const Op* __restrict__ ops, const OpC* __restrict__ opcs, 
       else if (fin_mode != FIN_NONE) acc_flush<SEGL_NS>(col, la, 1u << 2);
     }
   } else {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x) {
-      const u32 l0 = b.loss[i];
-      Pt p[1] = {{b.x[i], b.xp[i], b.y[i], b.yp[i], b.phi[i], b.w[i], l0}};
-      const u32 ll[1] = {b.lloss[i]};
+    OneStage* stg1 = reinterpret_cast<OneStage*>(s_acc + SEG_ACC * HPS_BLOCK);
+    const bool staged = stage && SEQ != SEQ_ANY;  // (the generic one-particle sweeps serve the rare full-op-set launches)
+    const u32 stride1 = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += stride1) {
+      u32 l0, ll0;
+      Pt p[1];
+      if (staged) {
+        const int t = threadIdx.x;
+        stage_wait();
+        p[0].x = stg1->d[0][t]; p[0].xp = stg1->d[1][t]; p[0].y = stg1->d[2][t]; p[0].yp = stg1->d[3][t];
+        p[0].phi = stg1->d[4][t]; p[0].w = stg1->d[5][t];
+        l0 = stg1->f[0][t]; ll0 = stg1->f[1][t];
+        p[0].loss = l0;
+        // the next copy may overwrite the slots only after these reads have returned: its index depends on the last of them
+        u32 zero;
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(ll0 ^ l0 ^ __double2hiint(p[0].w) ^ __double2hiint(p[0].phi) ^ __double2hiint(p[0].x) ^
+                                                            __double2hiint(p[0].xp) ^ __double2hiint(p[0].y) ^ __double2hiint(p[0].yp)));
+        const u32 nx = i + stride1 + zero;
+        if (nx < b.n) stage_issue1(stg1, b, nx);
+      } else {
+        l0 = b.loss[i]; ll0 = b.lloss[i];
+        p[0].x = b.x[i]; p[0].xp = b.xp[i]; p[0].y = b.y[i]; p[0].yp = b.yp[i]; p[0].phi = b.phi[i]; p[0].w = b.w[i]; p[0].loss = l0;
+      }
+      const u32 ll[1] = {ll0};
       const bool valid[1] = {true};
       const u32 g[1] = {b.offset + i * b.gstride};
       double fc[1] = {0.0};
       bool lf[1] = {false};
+      if (SEQ != SEQ_ANY) {
+#define AP1(TYPE, CCLF, K) apply_op<FULL, 1, MATH, TYPE, CCLF>(p, ll, g, valid, s_ops[K], s_opc[K], s_k, s_cxy, field, b, compat, fc, lf, inv_mass)
+        AP1((SEQ & 31), ((SEQ >> 5) & 3) - 1, 0);
+        if ((SEQ >> 8) & 31) AP1(((SEQ >> 8) & 31), ((SEQ >> 13) & 3) - 1, 1);
+        if ((SEQ >> 16) & 31) AP1(((SEQ >> 16) & 31), ((SEQ >> 21) & 3) - 1, 2);
+#undef AP1
+      } else
       for (int k = 0; k < nops; ++k) apply_op<FULL, 1, MATH>(p, ll, g, valid, s_ops[k], s_opc[k], s_k, s_cxy, field, b, compat, fc, lf, inv_mass);
       if (nops > 0) {
         if (dirty & 1) b.x[i] = p[0].x;
@@ -938,12 +986,17 @@ static SegKernel seg_kernel(int variant) {
 }
 // the pattern sweeps of the default variant (2 particles / thread, reference-order maps, exact arithmetic)
 // (the drift sequences need few registers: 3 resident blocks per SM instead of 2 hide more of their memory latency)
-struct SeqKernel { int seq; int minb; SegKernel fn; };
+struct SeqKernel { int seq; int minb; SegKernel fn; int ppt; };
 static const SeqKernel g_seq_kernels[] = {
-#define SK(S, B) {S, B, k_segment<2, B, false, 2, S>}
+#define SK(S, B) {S, B, k_segment<2, B, false, 2, S>, 2}
+#define SK1(S, B) {S, B, k_segment<1, B, false, 2, S>, 1}
     SK(SEQ_CCL_CELL, 2), SK(SEQ_DRIFT_STEP, 2), SK(SEQ_DRIFT_QUAD, 2), SK(SEQ_QUAD_DRIFT, 2), SK(SEQ_QUAD_GAP1D, 2), SK(SEQ_GAP2D_QUAD, 2),
     SK(SEQ_APER_DRIFT, 2), SK(SEQ_KICK_DRIFT, 2), SK(SEQ_KICK_GAP2C, 2), SK(SEQ_APER_GAP1C, 2),
     SK(SEQ_DRIFT_STEP, 3), SK(SEQ_APER_DRIFT, 3), SK(SEQ_KICK_DRIFT, 3),  // HPSIM_PATTERNS=2
+#ifdef HPS_EXP_PPT1  // build experiment: one particle per thread at 4 blocks per SM for the RF-gap patterns (HPSIM_PATTERNS=4)
+    SK1(SEQ_CCL_CELL, HPS_EXP_PPT1), SK1(SEQ_QUAD_GAP1D, HPS_EXP_PPT1), SK1(SEQ_GAP2D_QUAD, HPS_EXP_PPT1), SK1(SEQ_KICK_GAP2C, HPS_EXP_PPT1), SK1(SEQ_APER_GAP1C, HPS_EXP_PPT1),
+#endif
+#undef SK1
 #undef SK
 };
 static const SeqKernel* seq_kernel(const Op* host_ops, int nops, int want_minb) {
@@ -956,7 +1009,7 @@ static const SeqKernel* seq_kernel(const Op* host_ops, int nops, int want_minb) 
   }
   const SeqKernel* hit = nullptr;
   for (const SeqKernel& e : g_seq_kernels)
-    if (e.seq == code && (!hit || e.minb == want_minb)) hit = &e;
+    if (e.seq == code && e.minb <= want_minb && (!hit || e.minb > hit->minb)) hit = &e;  // the densest variant allowed
   return hit;
 }
 static int seg_full_variant(int variant) { return variant >= 20 ? -3 : (variant >= 10 ? -2 : -1); }
@@ -1284,8 +1337,14 @@ k_moments(BeamView b, DevStats* st, ScDev* sc, double* bins, KickParams kp, int 
 // The scale is 2^(62 - ceil(log2 N)): the largest power of two for which even N unit weights in one bin
 // cannot overflow 63 bits (2^46 at 64 Ki particles, 2^42 at 1 Mi, 2^38 at 16 Mi).
 __host__ __device__ inline double bin_scale(u32 n_global) {
+#ifdef __CUDA_ARCH__
+  // e = ceil(log2 N) without the loop (every thread of the field solve evaluates this: the loop was 17 % of its
+  // instructions, profiles/r2a_ncu_k_field_16mi.txt)
+  const int e = n_global <= 1u ? 0 : 32 - __clz((int)(n_global - 1u));
+#else
   int e = 0;
   while (e < 32 && (1ull << e) < (unsigned long long)n_global) ++e;
+#endif
   return (double)(1ull << (62 - e));
 }
 
@@ -2103,10 +2162,10 @@ void launch_segment(const LaunchCfg& c, const BeamView& b, const Op* host_ops, c
 #define SEG_CALL b, ops, opcs, nops, fin_mode, dirty, compat, st, sc, field, kp, c.partials, c.ticket, bins, dl, c.stage, c.xr
   const size_t smem = segment_smem(nops, c.stage);
   // pattern sweeps (default variant only): the op sequence is compiled in
-  const SeqKernel* pat = (c.seg_variant == 20 && c.patterns && !full) ? seq_kernel(host_ops, nops, c.patterns >= 2 ? 3 : 2) : nullptr;
+  const SeqKernel* pat = (c.seg_variant == 20 && c.patterns && !full) ? seq_kernel(host_ops, nops, c.patterns >= 4 ? 4 : (c.patterns >= 2 ? 3 : 2)) : nullptr;
   if (full) launch_chain(c, seg_kernel(seg_full_variant(c.seg_variant)), dim3(grid1), dim3(HPS_BLOCK), smem, SEG_CALL);
   else if (pat) {
-    const unsigned pairs = (b.n + 1) / 2;
+    const unsigned pairs = pat->ppt == 2 ? (b.n + 1) / 2 : b.n;
     const unsigned grid = std::max(1u, std::min((pairs + HPS_BLOCK - 1) / HPS_BLOCK, (unsigned)(c.num_sms * pat->minb)));
     launch_chain(c, pat->fn, dim3(grid), dim3(HPS_BLOCK), smem, SEG_CALL);
   } else launch_chain(c, seg_kernel(c.seg_variant), dim3(grid2), dim3(HPS_BLOCK), smem, SEG_CALL);

@@ -345,7 +345,9 @@ def test_fused_moment_epilogue_matches_standalone_chain(last, n, tol):
     print("FUSED", last, dumps(ms), dumps({k: rep[k] for k in ("n_loss", "n_lloss", "worst", "median_rel", "p999_rel")}), ra["stat_redo"], rb["stat_redo"])
     assert ra["kicks"] == rb["kicks"] and ra["remesh"] == rb["remesh"], (ra, rb)
     assert ms["fused"] + ms["fallback"] == rb["kicks"], (ms, rb)
-    assert ms["fused"] >= 0.9 * rb["kicks"], ms           # the prediction holds: the fallback is the exception
+    # the prediction holds: the fallback is the exception (its margins adapt to the prediction errors seen: a miss costs
+    # one extra sweep of k_moments, a generous margin costs side-list entries on every kick)
+    assert ms["fused"] >= 0.8 * rb["kicks"], ms
     assert ms["pivot_err_max"] < 0.25, ms
     if tol is not None:
         assert rep["loss_equal"] and rep["lloss_equal"], rep

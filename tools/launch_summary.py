@@ -24,7 +24,7 @@ data = collections.defaultdict(list)
 for k, v in sel:
     data[k].append(v)
 tot = sum(v for _, v in sel)
-print("ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-fast")
-print(f"last {len(sel)} of {len(rows)} launches = one whole C2 pass; cold-cache, serialised launches: compare SHARES; total {tot/1e3:.2f} ms")
+print(sys.argv[3] if len(sys.argv) > 3 else "ncu --metrics gpu__time_duration.sum --clock-control none python bench.py ...")
+print(f"last {len(sel)} of {len(rows)} launches; cold-cache, serialised launches: compare SHARES; total {tot/1e3:.2f} ms")
 for k, v in sorted(data.items(), key=lambda kv: -sum(kv[1])):
-    print(f"{k[:40]:40s} n={len(v):5d} sum={sum(v)/1e3:8.2f} ms  share={100*sum(v)/tot:5.1f}%  median={statistics.median(v):7.1f} us  min={min(v):6.1f} max={max(v):7.1f}")
+    print(f"{k[:56]:56s} n={len(v):5d} sum={sum(v)/1e3:8.2f} ms  share={100*sum(v)/tot:5.1f}%  median={statistics.median(v):7.1f} us  min={min(v):6.1f} max={max(v):7.1f}")
