@@ -279,7 +279,10 @@ int hps_scheff_set_mesh_size(hps_scheff*, uint32_t nr, uint32_t nz);
 int hps_scheff_download_tables(hps_scheff*, double* bins, double* field, double* dr_dz);
 /* SM-clock cycles block 0 of the fused space-charge chain (k_scheff) spent per phase, summed over all
  * kicks so far: 0 moment sweep, 1 reduction tail + policy + grid barrier, 2 deposit + flush, 3 Green
- * slice, 4 grid barrier (+ mesh push of a sharded beam), 5 field solve; 6-7 unused. */
+ * slice, 4 grid barrier (+ mesh push of a sharded beam), 5 field solve; 6 unused.
+ * out[7] is a COUNT, not cycles: particles the charge deposit dropped because their axial bin index came out as nz + 1
+ * (zz / dzg rounds up to nz exactly) -- there the reference writes one row past its table
+ * (src/simulation/inc/space_charge_kernel.cu:199-216); the one documented deviation of the deposit. */
 int hps_scheff_phase_cycles(hps_scheff*, uint64_t out[8]);
 
 /* ---- online monitor outputs ------------------------------------------------
