@@ -187,6 +187,7 @@ BeamView view(const hps_beam* b) {
   v.n = b->n; v.offset = b->offset; v.gstride = b->gstride; v.n_global = b->h.n_global;
   const u32 np2 = next_pow2(b->h.n_global);
   v.np2_quarter = np2 >= 4 ? np2 / 4 : 1;
+  v.streaming = (b->ctx->stage >= 0 ? b->ctx->stage != 0 : b->slab_bytes > ((size_t)96 << 20)) ? 1u : 0u;  // (as LaunchCfg::stage)
   v.mass = b->h.mass; v.charge = b->h.charge;
   return v;
 }

@@ -146,6 +146,7 @@ struct BeamView {
   u32 gstride;  // global index of local particle i = offset + i * gstride (sharded beams are interleaved)
   u32 n_global;
   u32 np2_quarter;  // NextPow2(n_global)/4: stride of the reference's kick launch (H2)
+  u32 streaming;    // the beam is larger than the L2 keeps between sweeps: its traffic is marked evict-first (HPS_EVICT_FIRST)
   double mass, charge;
 };
 

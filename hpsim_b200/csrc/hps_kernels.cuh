@@ -65,6 +65,20 @@ __device__ __forceinline__ double2 ld_f64x2(const double* base, u32 i2) {
   asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(reinterpret_cast<const double2*>(base) + i2));
   return v;
 }
+// the same with the evict-first (cache-streaming) hint when `cs` is set: the statistic / deposit sweeps of a beam that
+// streams through the L2 (BeamView::streaming) must not push the rest of the working set out of it
+__device__ __forceinline__ double2 ld_f64x2(const double* base, u32 i2, u32 cs) {
+  double2 v;
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p ld.global.cs.v2.f64 {%0, %1}, [%2]; @!p ld.global.v2.f64 {%0, %1}, [%2]; }"
+               : "=d"(v.x), "=d"(v.y) : "l"(reinterpret_cast<const double2*>(base) + i2), "r"(cs));
+  return v;
+}
+__device__ __forceinline__ uint2 ld_u32x2(const u32* base, u32 i2, u32 cs) {
+  uint2 v;
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p ld.global.cs.v2.u32 {%0, %1}, [%2]; @!p ld.global.v2.u32 {%0, %1}, [%2]; }"
+               : "=r"(v.x), "=r"(v.y) : "l"(reinterpret_cast<const uint2*>(base) + i2), "r"(cs));
+  return v;
+}
 __device__ __forceinline__ uint2 ld_u32x2(const u32* base, u32 i2) {
   uint2 v;
   asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(reinterpret_cast<const uint2*>(base) + i2));
