@@ -50,3 +50,22 @@ def test_planner_counts(first, last, kicks, gaps):
     assert int(m["max_ops_per_segment"]) <= 24
     if last == 6537:
         assert abs(float(m["freq"]) - 805.0) < 1e-9 and 795.0 < float(m["design_w"]) < 805.0, p.stdout
+
+
+def test_pattern_sweeps_cover_the_full_linac():
+    """The ten op sequences k_segment is compiled for (SEQ_* in hps_kernels.cu) against the planner's own segments of the full
+    linac: together they are at least 99.5 % of the sweeps (9 086 of 9 108), led by the CCL cell and the drift step."""
+    import harness as H
+    exe = H.build_tool("host_maps")
+    p = subprocess.run([exe, "plan", os.path.join(ROOT, "tests", "golden", "lansce.lat"), "62", "6537", "0.025"],
+                       capture_output=True, text=True, timeout=120, env=dict(os.environ, HPS_PLAN_PATTERNS="1"))
+    assert p.returncode == 0, p.stderr
+    hist = {m.group(2).strip(): int(m.group(1)) for m in re.finditer(r"PATTERN\s+(\d+)\s+(.*)", p.stdout)}
+    compiled = ["KICK gap2c gap1c | kick", "KICK drift drift | kick", "KICK drift quad | kick", "KICK quad drift | kick",
+                "KICK quad gap1d | kick", "KICK gap2d quad | kick", "capert drift | kick", "KICK drift | aperture",
+                "KICK gap2c | aperture", "capert gap1c | kick"]
+    total = sum(hist.values())
+    covered = sum(hist.get(k, 0) for k in compiled)
+    assert total == 9108, total
+    assert hist["KICK gap2c gap1c | kick"] == 4855 and hist["KICK drift drift | kick"] == 3030, hist
+    assert covered >= 0.995 * total, (covered, total)
